@@ -1,0 +1,86 @@
+"""ctypes binding of libapyib_b200.so (the C-ABI declared in include/apyib_b200.h).
+
+There is NO fallback: if the shared library cannot be loaded the import raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+F64, C128 = 0, 1
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_vp = C.c_void_p
+_i64 = C.c_int64
+_int = C.c_int
+_dbl = C.c_double
+
+# name -> (restype, argtypes); must list every symbol of include/apyib_b200.h
+SIGNATURES = {
+    "apyib_version": (_int, []),
+    "apyib_last_error": (C.c_char_p, []),
+    "apyib_device_info": (_int, [_int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), _i64p]),
+    "apyib_graph_begin": (_int, [_vp]),
+    "apyib_graph_end": (_int, [_vp, C.POINTER(_vp)]),
+    "apyib_graph_launch": (_int, [_vp, _vp]),
+    "apyib_graph_destroy": (_int, [_vp]),
+    "apyib_contract": (_int, [_int, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _int, _int, _int, _int, _dbl, _dbl, _dbl, _dbl, _int, _i64, _i64, _i64, _vp, _vp]),
+    "apyib_gather4": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _dbl, _i32p, _i64p, _dbl, _vp]),
+    "apyib_gather2": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _vp]),
+    "apyib_mp2_t2_energy": (_int, [_int, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp]),
+    "apyib_reduce_scratch_len": (_i64, []),
+    "apyib_ci_update": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "apyib_symmetrize_ijab": (_int, [_int, _vp, _vp, _i64, _i64, _vp]),
+    "apyib_dots": (_int, [_int, _vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp]),
+    "apyib_diis_push": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "apyib_diis_solve": (_int, [_int, _vp, _int, _int, _vp, _vp, _vp]),
+    "apyib_lincomb_energy_rms": (_int, [_int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "apyib_iter_advance": (_int, [_vp, _vp]),
+    "apyib_copy": (_int, [_int, _vp, _vp, _i64, _vp]),
+    "apyib_axpby": (_int, [_int, _i64, _dbl, _dbl, _vp, _int, _dbl, _dbl, _vp, _vp]),
+    "apyib_det_outer": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "apyib_det_matvec": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _int, _vp, _vp, _vp]),
+    "apyib_det_matvec_work_len": (_i64, [_i64, _i64, _int, _int]),
+    "apyib_get_slices": (_int, [_int, _int, _int, _int, _i32p]),
+    "apyib_det_enumeration": (_int, [_int, _int, _int, _i32p, _i64p, _i32p, _i64p]),
+    "apyib_det_index_lists": (_int, [_int, _i32p, _i64, _int, _i32p]),
+    "apyib_so_index_lists": (_int, [_int, _int, _i32p, _i64, _int, _i32p]),
+    "apyib_peak_fp64": (_int, [_int, _int, _f64p, C.POINTER(C.c_float)]),
+    "apyib_peak_copy": (_int, [_vp, _vp, _i64, _int, _f64p]),
+}
+
+
+class ApyibB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    path = _build.LIB
+    if not os.path.exists(path):
+        # built in-tree by __graft_entry__.build(); try once here (nvcc is part of the image)
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale -> loud failure
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise ApyibB200Error("libapyib_b200 call failed (%d): %s" % (rc, lib.apyib_last_error().decode()))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise ApyibB200Error("apyib_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback")

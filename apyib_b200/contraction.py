@@ -1,0 +1,97 @@
+"""einsum-style front end of the DMMA contraction kernel (csrc/contract.cu).
+
+Each call is one `opt_einsum.contract(...)` of the reference.  Instead of transposing
+operands into GEMM layout, the regrouping of tensor indices into (m | k | n) is encoded in six
+integer offset tables (cached per signature on the device); operands may be arbitrary strided
+views (slices / swapaxes of a bigger tensor), exactly like the numpy views the reference feeds
+to opt_einsum.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import lib, check
+from .device import dtype_code, ptr, stream_ptr, device
+
+_table_cache = {}
+
+
+def _offsets(dims, strides):
+    """Linearised element offsets of a compound index (last index fastest)."""
+    off = np.zeros(1, dtype=np.int64)
+    for d, s in zip(dims, strides):
+        off = (off[:, None] + (np.arange(d, dtype=np.int64) * s)[None, :]).reshape(-1)
+    return off
+
+
+def _plan(spec, A, B, out):
+    key = (spec, tuple(A.shape), tuple(A.stride()), tuple(B.shape), tuple(B.stride()),
+           tuple(out.shape), tuple(out.stride()), A.device.index)
+    p = _table_cache.get(key)
+    if p is not None:
+        return p
+    ins, o = spec.replace(" ", "").split("->")
+    sa, sb = ins.split(",")
+    assert len(sa) == A.dim() and len(sb) == B.dim() and len(o) == out.dim(), spec
+    size = {}
+    for s, t in ((sa, A), (sb, B), (o, out)):
+        for ch, d in zip(s, t.shape):
+            assert size.setdefault(ch, d) == d, "inconsistent size for index %s in %s" % (ch, spec)
+    m_idx = [ch for ch in o if ch in sa and ch not in sb]
+    n_idx = [ch for ch in o if ch in sb and ch not in sa]
+    k_idx = [ch for ch in sa if ch in sb and ch not in o]
+    assert len(m_idx) + len(n_idx) == len(o), "batch / repeated output indices unsupported: " + spec
+    assert set(sa) == set(m_idx) | set(k_idx) and set(sb) == set(n_idx) | set(k_idx), \
+        "every index must be m, n or k: " + spec
+    st = lambda s, t: dict(zip(s, t.stride()))
+    stA, stB, stO = st(sa, A), st(sb, B), st(o, out)
+    # order k by A's layout (largest stride first) so that the fastest k index is contiguous in A if possible
+    k_idx.sort(key=lambda ch: -stA[ch])
+    dims = lambda idx: [size[ch] for ch in idx]
+    tabs = [
+        _offsets(dims(m_idx), [stA[ch] for ch in m_idx]),
+        _offsets(dims(k_idx), [stA[ch] for ch in k_idx]),
+        _offsets(dims(k_idx), [stB[ch] for ch in k_idx]),
+        _offsets(dims(n_idx), [stB[ch] for ch in n_idx]),
+        _offsets(dims(m_idx), [stO[ch] for ch in m_idx]),
+        _offsets(dims(n_idx), [stO[ch] for ch in n_idx]),
+    ]
+    M, K, N = len(tabs[0]), len(tabs[1]), len(tabs[3])
+    fast = lambda stmap, kk, other: int(bool(kk) and (not other or stmap[kk[-1]] <= min(stmap[c] for c in other)))
+    a_kfast = fast(stA, k_idx, m_idx)
+    b_kfast = fast(stB, k_idx, n_idx)
+    dev = torch.from_numpy(np.concatenate(tabs)).to(device())
+    sizes = [M, K, K, N, M, N]
+    ptrs, off = [], 0
+    for s in sizes:
+        ptrs.append(dev.data_ptr() + 8 * off)
+        off += s
+    p = (M, N, K, ptrs, a_kfast, b_kfast, dev)
+    _table_cache[key] = p
+    return p
+
+
+def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
+    """out = alpha * einsum(spec, op(A), op(B)) + beta * out, on the current stream."""
+    assert A.dtype == B.dtype == out.dtype, "mixed dtypes: %s %s %s" % (A.dtype, B.dtype, out.dtype)
+    M, N, K, ptrs, a_kfast, b_kfast, _keep = _plan(spec, A, B, out)
+    alpha, beta = complex(alpha), complex(beta)
+    check(lib.apyib_contract(dtype_code(A), ptr(A), ptr(B), ptr(out), M, N, K,
+                             *[C.c_void_p(p) for p in ptrs],
+                             a_kfast, b_kfast, int(conj_a), int(conj_b),
+                             alpha.real, alpha.imag, beta.real, beta.imag,
+                             1, 0, 0, 0, C.c_void_p(0), stream_ptr()))
+    return out
+
+
+def contract_new(spec, A, B, alpha=1.0, conj_a=False, conj_b=False):
+    """Allocating variant: returns a fresh dense tensor with the output index order of spec."""
+    ins, o = spec.replace(" ", "").split("->")
+    sa, sb = ins.split(",")
+    size = dict(zip(sa, A.shape))
+    size.update(zip(sb, B.shape))
+    out = torch.empty([size[ch] for ch in o], dtype=A.dtype, device=A.device)
+    return contract(spec, A, B, out, alpha, 0.0, conj_a, conj_b)

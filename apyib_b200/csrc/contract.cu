@@ -1,0 +1,266 @@
+// Tensor contraction on the FP64 tensor path (DMMA, mma.sync.m8n8k4.f64) for sm_100a.
+//
+//   C[c_m[m] + c_n[n]] = alpha * sum_k opA(A[a_m[m] + a_k[k]]) * opB(B[b_k[k] + b_n[n]]) + beta * C
+//
+// One launch == one `opt_einsum.contract` of the reference (ci_wfn.py:84-90, 211-218,
+// 310-333, 458-482; utils.py:240-252, 274-277, 381).  The reference lets opt_einsum
+// transpose-copy the operands into GEMM layout; here the regrouping of tensor
+// indices into (m | k | n) lives in six offset tables, and the operand tiles are gathered
+// straight into shared memory with per-element cp.async (a complex128 element is exactly one
+// 16-byte LDGSTS), so no transposed copy of an amplitude or integral block is ever made.
+//
+// Complex arithmetic: one 16-byte LDS gives a thread the (re, im) pair of its A (or B)
+// fragment element; the complex product is four real DMMAs on the same fragments
+// (Cr += Ar*Br, Cr += (-Ai)*Bi, Ci += Ar*Bi, Ci += Ai*Br), so the kernel does the
+// "complex GEMM as 4 real GEMMs" split of the north star entirely in registers.
+//
+// FP64 has no tcgen05/TMEM path on sm_100a (`tcgen05.mma.kind::f64` does not exist);
+// the FP64 tensor instruction is the warp-level DMMA.8x8x4.
+#include "common.cuh"
+
+namespace apyib {
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int BYTES> __device__ __forceinline__ void cp_async(void *smem, const void *gmem, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    int src = valid ? BYTES : 0;   // src-size 0 -> zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(s), "l"(gmem), "n"(BYTES), "r"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+struct ContractArgs {
+    const void *A, *B;
+    void *C;
+    const int64_t *a_m, *a_k, *b_k, *b_n, *c_m, *c_n;
+    int64_t M, N, K;
+    int64_t a_bs, b_bs, c_bs;
+    const int32_t *active;
+    double alpha_re, alpha_im, beta_re, beta_im;
+    int a_kfast, b_kfast, conj_a, conj_b;
+};
+
+template <bool CPLX> struct elem_t { using type = double; };
+template <> struct elem_t<true> { using type = cplx; };
+
+// BM x BN CTA tile, BK slab, warps arranged (BM/WM) x (BN/WN), each warp WM x WN.
+template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+contract_kernel(const ContractArgs p) {
+    using T = typename elem_t<CPLX>::type;
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr int EB = CPLX ? 16 : 8;
+    // row pitch: conflict-free fragment reads: pitch = 2 (mod 8) complex, 4 (mod 16) real
+    constexpr int LDA = BM + (CPLX ? 2 : 4);
+    constexpr int LDB = BN + (CPLX ? 2 : 4);
+    constexpr int TM = WM / 8, TN = WN / 8;
+    constexpr int ITA = (BM * BK) / NT, ITB = (BN * BK) / NT;
+    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile/threads mismatch");
+    static_assert(BK % 4 == 0, "BK must be a multiple of the DMMA k");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *As = reinterpret_cast<T *>(smem_raw);                       // [STAGES][BK][LDA]
+    T *Bs = As + (size_t)STAGES * BK * LDA;                        // [STAGES][BK][LDB]
+
+    const int z = blockIdx.z;
+    if (p.active != nullptr && p.active[z] == 0) return;
+    const T *A = reinterpret_cast<const T *>(p.A) + (size_t)z * p.a_bs;
+    const T *B = reinterpret_cast<const T *>(p.B) + (size_t)z * p.b_bs;
+    T *C = reinterpret_cast<T *>(p.C) + (size_t)z * p.c_bs;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
+    const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+
+    // per-thread gather coordinates (fixed for the whole kernel)
+    int a_mi[ITA], a_ki[ITA], b_ni[ITB], b_ki[ITB];
+    int64_t a_off[ITA], b_off[ITB];
+    bool a_ok[ITA], b_ok[ITB];
+#pragma unroll
+    for (int i = 0; i < ITA; ++i) {
+        int e = tid + i * NT;
+        a_mi[i] = p.a_kfast ? e / BK : e % BM;
+        a_ki[i] = p.a_kfast ? e % BK : e / BM;
+        a_ok[i] = (m0 + a_mi[i]) < p.M;
+        a_off[i] = a_ok[i] ? p.a_m[m0 + a_mi[i]] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < ITB; ++i) {
+        int e = tid + i * NT;
+        b_ni[i] = p.b_kfast ? e / BK : e % BN;
+        b_ki[i] = p.b_kfast ? e % BK : e / BN;
+        b_ok[i] = (n0 + b_ni[i]) < p.N;
+        b_off[i] = b_ok[i] ? p.b_n[n0 + b_ni[i]] : 0;
+    }
+
+    auto load_slab = [&](int stage, int64_t kbase) {
+        T *as = As + (size_t)stage * BK * LDA;
+        T *bs = Bs + (size_t)stage * BK * LDB;
+#pragma unroll
+        for (int i = 0; i < ITA; ++i) {
+            int64_t k = kbase + a_ki[i];
+            bool ok = a_ok[i] && k < p.K;
+            int64_t off = ok ? a_off[i] + p.a_k[k] : 0;
+            cp_async<EB>(as + a_ki[i] * LDA + a_mi[i], A + off, ok);
+        }
+#pragma unroll
+        for (int i = 0; i < ITB; ++i) {
+            int64_t k = kbase + b_ki[i];
+            bool ok = b_ok[i] && k < p.K;
+            int64_t off = ok ? b_off[i] + p.b_k[k] : 0;
+            cp_async<EB>(bs + b_ki[i] * LDB + b_ni[i], B + off, ok);
+        }
+    };
+
+    double cr[TM][TN][2];
+    double ci[CPLX ? TM : 1][CPLX ? TN : 1][2];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            cr[i][j][0] = cr[i][j][1] = 0.0;
+            if (CPLX) ci[i][j][0] = ci[i][j][1] = 0.0;
+        }
+
+    const int64_t nslab = (p.K + BK - 1) / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nslab) load_slab(s, (int64_t)s * BK);
+        cp_async_commit();
+    }
+
+    const int fr = lane >> 2, fk = lane & 3;   // fragment row (or col) / k within the 8x4 atom
+    const double sa = p.conj_a ? -1.0 : 1.0, sb = p.conj_b ? -1.0 : 1.0;
+
+    for (int64_t kt = 0; kt < nslab; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {   // prefetch slab kt + STAGES - 1 into the stage freed in the previous iteration
+            int64_t nk = kt + STAGES - 1;
+            if (nk < nslab) load_slab((int)(nk % STAGES), nk * BK);
+            cp_async_commit();
+        }
+        const T *as = As + (size_t)(kt % STAGES) * BK * LDA;
+        const T *bs = Bs + (size_t)(kt % STAGES) * BK * LDB;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            T af[TM], bf[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) af[i] = as[(kk + fk) * LDA + wm0 + i * 8 + fr];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bf[j] = bs[(kk + fk) * LDB + wn0 + j * 8 + fr];
+            if constexpr (CPLX) {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const double ar = af[i].x, ai = sa * af[i].y, nai = -ai;
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        const double br = bf[j].x, bi = sb * bf[j].y;
+                        dmma884(cr[i][j][0], cr[i][j][1], ar, br);
+                        dmma884(ci[i][j][0], ci[i][j][1], ar, bi);
+                        dmma884(cr[i][j][0], cr[i][j][1], nai, bi);
+                        dmma884(ci[i][j][0], ci[i][j][1], ai, br);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) dmma884(cr[i][j][0], cr[i][j][1], af[i], bf[j]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread owns rows fr (+8i), column pairs 2*fk (+8j) of its warp tile
+    const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int64_t m = m0 + wm0 + i * 8 + fr;
+        if (m >= p.M) continue;
+        const int64_t om = p.c_m[m];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int64_t n = n0 + wn0 + j * 8 + fk * 2 + q;
+                if (n >= p.N) continue;
+                T *dst = C + om + p.c_n[n];
+                if constexpr (CPLX) {
+                    double xr = cr[i][j][q], xi = ci[i][j][q];
+                    double vr = p.alpha_re * xr - p.alpha_im * xi, vi = p.alpha_re * xi + p.alpha_im * xr;
+                    if (has_beta) {
+                        cplx o = *dst;
+                        vr += p.beta_re * o.x - p.beta_im * o.y;
+                        vi += p.beta_re * o.y + p.beta_im * o.x;
+                    }
+                    *dst = make_cplx(vr, vi);
+                } else {
+                    double v = p.alpha_re * cr[i][j][q];
+                    if (has_beta) v += p.beta_re * (*dst);
+                    *dst = v;
+                }
+            }
+        }
+    }
+}
+
+template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES>
+static int launch_contract(const ContractArgs &a, int batch, cudaStream_t st) {
+    using T = typename elem_t<CPLX>::type;
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    constexpr int LDA = BM + (CPLX ? 2 : 4), LDB = BN + (CPLX ? 2 : 4);
+    constexpr size_t smem = (size_t)STAGES * BK * (LDA + LDB) * sizeof(T);
+    auto kern = contract_kernel<CPLX, BM, BN, BK, WM, WN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((a.N + BN - 1) / BN), (unsigned)((a.M + BM - 1) / BM), (unsigned)batch);
+    kern<<<grid, NT, smem, st>>>(a);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+}  // namespace apyib
+
+using namespace apyib;
+
+extern "C" int apyib_contract(int dtype, const void *d_A, const void *d_B, void *d_C, int64_t M, int64_t N,
+                              int64_t K, const int64_t *d_a_m, const int64_t *d_a_k, const int64_t *d_b_k,
+                              const int64_t *d_b_n, const int64_t *d_c_m, const int64_t *d_c_n, int a_kfast,
+                              int b_kfast, int conj_a, int conj_b, double alpha_re, double alpha_im,
+                              double beta_re, double beta_im, int batch, int64_t a_bstride,
+                              int64_t b_bstride, int64_t c_bstride, const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && batch <= 65535, "sizes");
+    APYIB_REQUIRE(d_A && d_B && d_C && d_a_m && d_a_k && d_b_k && d_b_n && d_c_m && d_c_n, "null pointer");
+    if (M == 0 || N == 0) return APYIB_OK;
+    APYIB_REQUIRE((M + 31) / 32 <= 65535, "M too large for grid.y");
+    ContractArgs a;
+    a.A = d_A; a.B = d_B; a.C = d_C;
+    a.a_m = d_a_m; a.a_k = d_a_k; a.b_k = d_b_k; a.b_n = d_b_n; a.c_m = d_c_m; a.c_n = d_c_n;
+    a.M = M; a.N = N; a.K = K;
+    a.a_bs = a_bstride; a.b_bs = b_bstride; a.c_bs = c_bstride;
+    a.active = d_active;
+    a.alpha_re = alpha_re; a.alpha_im = alpha_im; a.beta_re = beta_re; a.beta_im = beta_im;
+    a.a_kfast = a_kfast; a.b_kfast = b_kfast; a.conj_a = conj_a; a.conj_b = conj_b;
+    cudaStream_t st = (cudaStream_t)stream;
+    // tile choice: 64x64 when that already yields >= 1 wave of CTAs on 148 SMs, else 32x32
+    const int64_t big_tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
+    const bool big = big_tiles >= 148;
+    if (dtype == APYIB_C128) {
+        return big ? launch_contract<true, 64, 64, 8, 32, 32, 3>(a, batch, st)
+                   : launch_contract<true, 32, 32, 8, 16, 16, 3>(a, batch, st);
+    }
+    return big ? launch_contract<false, 64, 64, 16, 32, 32, 3>(a, batch, st)
+               : launch_contract<false, 32, 32, 16, 16, 16, 3>(a, batch, st);
+}

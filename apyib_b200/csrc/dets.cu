@@ -1,0 +1,275 @@
+// Determinants of substituted occupied-overlap matrices (aats.py:120-130, 558-642) and the
+// fused det-table x amplitude-vector products of the AAT assembly (aats.py:718-737 ...).
+//
+// One sub-warp ("group" of G = 4/8/16/32 lanes, n <= G) per n x n complex matrix: lane l owns
+// matrix row l in registers, Gaussian elimination with partial pivoting (LAPACK zgetrf pivot
+// rule: max |re|+|im|) runs with warp shuffles, rows are never physically swapped -- the
+// permutation parity is tracked with a ballot.  The matrix is formed on the fly from the
+// (L1/L2-resident) MO overlap S and two index lists, so neither the substituted matrices nor,
+// in the fused variant, the determinant table (the reference's 8-index tensor, aats.py:575)
+// ever exist in memory.
+#include "common.cuh"
+
+namespace apyib {
+
+constexpr int kDetThreads = 256;
+
+template <int G>
+__device__ __forceinline__ cplx group_lu_det(cplx (&a)[G], const int n, const int l) {
+    // lanes >= n are padding: never pivot, never updated
+    bool done = (l >= n);
+    cplx det = make_cplx(1.0, 0.0);
+    int parity = 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gbase = lane & ~(unsigned)(G - 1);
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        if (k < n) {
+            double best = done ? -1.0 : (fabs(a[k].x) + fabs(a[k].y));
+            int who = l;
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off, G);
+                const int ow = __shfl_xor_sync(0xffffffffu, who, off, G);
+                if (ob > best || (ob == best && ow < who)) {
+                    best = ob;
+                    who = ow;
+                }
+            }
+            const unsigned undone = (__ballot_sync(0xffffffffu, !done) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
+            parity ^= __popc(undone & ((1u << who) - 1u)) & 1;
+            cplx pv;
+            pv.x = __shfl_sync(0xffffffffu, a[k].x, who, G);
+            pv.y = __shfl_sync(0xffffffffu, a[k].y, who, G);
+            det = det * pv;
+            if (l == who) done = true;
+            cplx f = make_cplx(0.0, 0.0);
+            if (!done && best > 0.0) f = cdiv(a[k], pv);
+#pragma unroll
+            for (int j = k + 1; j < G; ++j) {
+                if (j < n) {
+                    cplx pj;
+                    pj.x = __shfl_sync(0xffffffffu, a[j].x, who, G);
+                    pj.y = __shfl_sync(0xffffffffu, a[j].y, who, G);
+                    a[j].x -= f.x * pj.x - f.y * pj.y;
+                    a[j].y -= f.x * pj.y + f.y * pj.x;
+                }
+            }
+        }
+    }
+    if (parity) det = make_cplx(-det.x, -det.y);
+    return det;
+}
+
+// grid: x = row blocks (kDetThreads/G rows each), y = column chunks.
+// OUTER : out[r*ncol + c] = det
+// !OUTER: Zp[(chunk*ny + iy)*nrow + r] = sum_{c in chunk} det(r,c) * Y[iy*ncol + c]
+template <int G, bool OUTER>
+__global__ void __launch_bounds__(kDetThreads)
+det_kernel(const cplx *__restrict__ S, int ns, int n, const int32_t *__restrict__ rows, int64_t nrow,
+           const int32_t *__restrict__ cols, int64_t ncol, int64_t chunk_len, const cplx *__restrict__ Y, int ny,
+           cplx *__restrict__ out) {
+    constexpr int GPB = kDetThreads / G;
+    const int l = threadIdx.x % G;
+    const int64_t r = (int64_t)blockIdx.x * GPB + threadIdx.x / G;
+    const bool rvalid = r < nrow;
+    const int64_t c0 = (int64_t)blockIdx.y * chunk_len;
+    int64_t c1 = c0 + chunk_len;
+    if (c1 > ncol) c1 = ncol;
+
+    const cplx *Srow = S;
+    if (rvalid && l < n) Srow = S + (int64_t)rows[r * n + l] * ns;
+
+    constexpr int NYMAX = 4;
+    cplx z[NYMAX];
+#pragma unroll
+    for (int q = 0; q < NYMAX; ++q) z[q] = make_cplx(0.0, 0.0);
+
+    for (int64_t c = c0; c < c1; ++c) {
+        cplx a[G];
+        const int32_t *cl = cols + c * n;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            if (j < n) {
+                if (rvalid && l < n) a[j] = ldg(&Srow[__ldg(&cl[j])]);
+                else a[j] = make_cplx(j == l ? 1.0 : 0.0, 0.0);
+            }
+        }
+        const cplx d = group_lu_det<G>(a, n, l);
+        if (l == 0 && rvalid) {
+            if (OUTER) {
+                out[r * ncol + c] = d;
+            } else {
+#pragma unroll
+                for (int q = 0; q < NYMAX; ++q)
+                    if (q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
+            }
+        }
+    }
+    if (!OUTER && l == 0 && rvalid) {
+#pragma unroll
+        for (int q = 0; q < NYMAX; ++q)
+            if (q < ny) out[((int64_t)blockIdx.y * ny + q) * nrow + r] = z[q];
+    }
+}
+
+// Z[q*nrow + r] = sum_chunk Zp[(chunk*ny + q)*nrow + r]   (fixed order)
+__global__ void __launch_bounds__(256) chunk_reduce_kernel(const cplx *Zp, int nchunk, int64_t len, cplx *Z) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        cplx s = make_cplx(0.0, 0.0);
+        for (int ch = 0; ch < nchunk; ++ch) s = s + Zp[(int64_t)ch * len + i];
+        Z[i] = s;
+    }
+}
+
+template <bool OUTER>
+static int launch_det(int G, dim3 grid, cudaStream_t st, const cplx *S, int ns, int n, const int32_t *rows,
+                      int64_t nrow, const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny,
+                      cplx *out) {
+    switch (G) {
+        case 4: det_kernel<4, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
+        case 8: det_kernel<8, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
+        case 16: det_kernel<16, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
+        default: det_kernel<32, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
+    }
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+static int group_size(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)); }
+
+}  // namespace apyib
+
+using namespace apyib;
+
+extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                               const int32_t *d_cols, int64_t ncol, void *d_out, void *stream) {
+    APYIB_REQUIRE(d_S && d_rows && d_cols && d_out, "null pointer");
+    APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
+    if (nrow == 0 || ncol == 0) return APYIB_OK;
+    const int G = group_size(n);
+    const int64_t gpb = kDetThreads / G;
+    const int64_t rb = (nrow + gpb - 1) / gpb;
+    int64_t nchunk = (148 * 8 + rb - 1) / rb;
+    if (nchunk > ncol) nchunk = ncol;
+    if (nchunk > 65535) nchunk = 65535;
+    if (nchunk < 1) nchunk = 1;
+    const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
+    nchunk = (ncol + chunk_len - 1) / chunk_len;
+    APYIB_REQUIRE(rb <= 2147483647LL, "too many rows");
+    dim3 grid((unsigned)rb, (unsigned)nchunk);
+    return launch_det<true>(G, grid, (cudaStream_t)stream, (const cplx *)d_S, ns, n, d_rows, nrow, d_cols, ncol,
+                            chunk_len, nullptr, 0, (cplx *)d_out);
+}
+
+// Z[iy*nrow + r] = sum_c det(S[rows[r], cols[c]]) * Y[iy*ncol + c]
+// d_work: scratch of apyib_det_matvec_work_len(nrow, ncol, ny, n) complex128 elements.
+extern "C" int64_t apyib_det_matvec_nchunk(int64_t nrow, int64_t ncol, int n) {
+    const int G = group_size(n);
+    const int64_t gpb = kDetThreads / G;
+    const int64_t rb = (nrow + gpb - 1) / gpb;
+    int64_t nchunk = (148 * 8 + rb - 1) / rb;
+    if (nchunk > ncol) nchunk = ncol;
+    if (nchunk > 4096) nchunk = 4096;
+    if (nchunk < 1) nchunk = 1;
+    const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
+    return (ncol + chunk_len - 1) / chunk_len;
+}
+
+extern "C" int64_t apyib_det_matvec_work_len(int64_t nrow, int64_t ncol, int ny, int n) {
+    return apyib_det_matvec_nchunk(nrow, ncol, n) * ny * nrow;
+}
+
+extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                                const int32_t *d_cols, int64_t ncol, const void *d_Y, int ny, void *d_Z,
+                                void *d_work, void *stream) {
+    APYIB_REQUIRE(d_S && d_rows && d_cols && d_Y && d_Z && d_work, "null pointer");
+    APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
+    APYIB_REQUIRE(ny >= 1 && ny <= 4, "1 <= ny <= 4");
+    if (nrow == 0) return APYIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ncol == 0) {
+        APYIB_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(cplx) * ny * nrow, st));
+        return APYIB_OK;
+    }
+    const int G = group_size(n);
+    const int64_t gpb = kDetThreads / G;
+    const int64_t rb = (nrow + gpb - 1) / gpb;
+    const int64_t nchunk = apyib_det_matvec_nchunk(nrow, ncol, n);
+    const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
+    dim3 grid((unsigned)rb, (unsigned)nchunk);
+    int rc = launch_det<false>(G, grid, st, (const cplx *)d_S, ns, n, d_rows, nrow, d_cols, ncol, chunk_len,
+                               (const cplx *)d_Y, ny, (cplx *)d_work);
+    if (rc != APYIB_OK) return rc;
+    const int64_t len = (int64_t)ny * nrow;
+    int64_t b = (len + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    chunk_reduce_kernel<<<(unsigned)b, 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+// ---- host-side bit-exact index tables -------------------------------------------------------
+extern "C" int apyib_get_slices(int nbf, int ndocc, int nfzc, int spin_orbital, int32_t b[16]) {
+    APYIB_REQUIRE(b != nullptr && nbf >= ndocc && ndocc >= nfzc && nfzc >= 0, "sizes");
+    // C_list (utils.py:192-197)
+    b[0] = 0; b[1] = nfzc; b[2] = nfzc; b[3] = ndocc; b[4] = ndocc; b[5] = nbf; b[6] = nfzc; b[7] = nbf;
+    const int s = spin_orbital ? 2 : 1;   // utils.py:200-209
+    b[8] = 0; b[9] = s * nfzc;
+    b[10] = 0; b[11] = s * ndocc - s * nfzc;
+    b[12] = s * ndocc - s * nfzc; b[13] = s * nbf - s * nfzc;
+    b[14] = 0; b[15] = s * nbf - s * nfzc;
+    return APYIB_OK;
+}
+
+extern "C" int apyib_det_enumeration(int ndocc, int nfzc, int nvirt, int32_t *h_singles, int64_t *n_singles,
+                                     int32_t *h_doubles, int64_t *n_doubles) {
+    APYIB_REQUIRE(ndocc >= nfzc && nfzc >= 0 && nvirt >= 0, "sizes");
+    int64_t ns = 0, nd = 0;
+    for (int i = nfzc; i < ndocc; ++i)
+        for (int a = 0; a < nvirt; ++a) {
+            if (h_singles) { h_singles[2 * ns] = i; h_singles[2 * ns + 1] = a; }
+            ++ns;
+            for (int j = i + 1; j < ndocc; ++j)
+                for (int bb = a + 1; bb < nvirt; ++bb) {
+                    if (h_doubles) {
+                        h_doubles[4 * nd] = i; h_doubles[4 * nd + 1] = a;
+                        h_doubles[4 * nd + 2] = j; h_doubles[4 * nd + 3] = bb;
+                    }
+                    ++nd;
+                }
+        }
+    if (n_singles) *n_singles = ns;
+    if (n_doubles) *n_doubles = nd;
+    return APYIB_OK;
+}
+
+extern "C" int apyib_det_index_lists(int n, const int32_t *h_sub, int64_t count, int nsub, int32_t *h_out) {
+    APYIB_REQUIRE(h_out && (h_sub || nsub == 0) && n >= 1 && nsub >= 0, "arguments");
+    for (int64_t q = 0; q < count; ++q) {
+        int32_t *o = h_out + q * n;
+        for (int j = 0; j < n; ++j) o[j] = j;
+        for (int t = 0; t < nsub; ++t) {
+            const int32_t pos = h_sub[(q * nsub + t) * 2], vir = h_sub[(q * nsub + t) * 2 + 1];
+            APYIB_REQUIRE(pos >= 0 && pos < n && vir >= 0, "substitution out of range");
+            o[pos] = vir + n;
+        }
+    }
+    return APYIB_OK;
+}
+
+extern "C" int apyib_so_index_lists(int nso, int nocc, const int32_t *h_sub, int64_t count, int nsub,
+                                    int32_t *h_out) {
+    APYIB_REQUIRE(h_out && (h_sub || nsub == 0) && nso >= nocc && nocc >= 1 && nso <= 4096, "arguments");
+    int32_t perm[4096];
+    for (int64_t q = 0; q < count; ++q) {
+        for (int j = 0; j < nso; ++j) perm[j] = j;
+        for (int t = 0; t < nsub; ++t) {   // sequential pair swaps, aats.py:123-126
+            const int32_t x = h_sub[(q * nsub + t) * 2], y = h_sub[(q * nsub + t) * 2 + 1];
+            APYIB_REQUIRE(x >= 0 && x < nso && y >= 0 && y < nso, "swap index out of range");
+            const int32_t tmp = perm[x]; perm[x] = perm[y]; perm[y] = tmp;
+        }
+        for (int j = 0; j < nocc; ++j) h_out[q * nocc + j] = perm[j];
+    }
+    return APYIB_OK;
+}

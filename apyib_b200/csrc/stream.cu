@@ -1,0 +1,553 @@
+// HBM-streaming kernels of the hot path: block gather / spin blocking / antisymmetrisation,
+// MP2 amplitudes + energy, CI Jacobi update, DIIS dots / extrapolation with fused energy and
+// rms reductions.  All reductions are deterministic (fixed summation order, no float atomics).
+#include "common.cuh"
+
+namespace apyib {
+
+constexpr int kThreads = 256;
+
+// --------------------------------------------------------------------------------------
+// gather4 / gather2
+// --------------------------------------------------------------------------------------
+struct Gather4Args {
+    int64_t sd[4];      // source dims (spatial)
+    int64_t od[4];      // output dims
+    int perm1[4], perm2[4];
+    int64_t st1[4], st2[4];
+    double c1, c2;
+    int spin;
+};
+
+template <typename T>
+__device__ __forceinline__ T fetch4(const T *src, const int64_t (&sd)[4], int spin, int64_t p0, int64_t p1,
+                                    int64_t p2, int64_t p3) {
+    if (spin) {
+        if (((p0 ^ p1) & 1) || ((p2 ^ p3) & 1)) return scalar<T>::zero();
+        p0 >>= 1; p1 >>= 1; p2 >>= 1; p3 >>= 1;
+    }
+    return src[((p0 * sd[1] + p1) * sd[2] + p2) * sd[3] + p3];
+}
+
+template <typename T> __global__ void __launch_bounds__(kThreads) gather4_kernel(const T *src, T *out, Gather4Args g) {
+    const int64_t total = g.od[0] * g.od[1] * g.od[2] * g.od[3];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t x[4], r = idx;
+        x[3] = r % g.od[3]; r /= g.od[3];
+        x[2] = r % g.od[2]; r /= g.od[2];
+        x[1] = r % g.od[1]; r /= g.od[1];
+        x[0] = r;
+        T v = fetch4<T>(src, g.sd, g.spin, g.st1[0] + x[g.perm1[0]], g.st1[1] + x[g.perm1[1]],
+                        g.st1[2] + x[g.perm1[2]], g.st1[3] + x[g.perm1[3]]);
+        v = g.c1 * v;
+        if (g.c2 != 0.0) {
+            T w = fetch4<T>(src, g.sd, g.spin, g.st2[0] + x[g.perm2[0]], g.st2[1] + x[g.perm2[1]],
+                            g.st2[2] + x[g.perm2[2]], g.st2[3] + x[g.perm2[3]]);
+            v = v + g.c2 * w;
+        }
+        out[idx] = v;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+gather2_kernel(const T *src, T *out, int64_t s0, int64_t s1, int64_t o0, int64_t o1, int pa, int pb, int64_t st0,
+               int64_t st1, int spin) {
+    const int64_t total = o0 * o1;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t x[2] = {idx / o1, idx % o1};
+        int64_t p = st0 + x[pa], q = st1 + x[pb];
+        T v = scalar<T>::zero();
+        if (spin) {
+            if (((p ^ q) & 1) == 0) v = src[(p >> 1) * s1 + (q >> 1)];
+        } else {
+            v = src[p * s1 + q];
+        }
+        out[idx] = v;
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// MP2  (mp2_wfn.py:42-59, 64-87)
+// --------------------------------------------------------------------------------------
+template <typename T, bool SO>
+__global__ void __launch_bounds__(kThreads)
+mp2_kernel(const T *eri, int64_t n, int64_t o, const double *eps, T *t2, double *E_out, double *partials) {
+    const int64_t O = SO ? 2 * o : o, V = SO ? 2 * (n - o) : (n - o);
+    const int64_t total = O * O * V * V;
+    const int64_t sd[4] = {n, n, n, n};
+    double acc[2] = {0.0, 0.0};
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = idx;
+        const int64_t b = r % V; r /= V;
+        const int64_t a = r % V; r /= V;
+        const int64_t j = r % O;
+        const int64_t i = r / O;
+        const int64_t A = O + a, B = O + b;
+        double D;
+        T num, L;
+        if (SO) {
+            D = eps[i >> 1] + eps[j >> 1] - eps[A >> 1] - eps[B >> 1];
+            // <ab||ij> = (ai|bj) - (aj|bi) ;  <ij||ab> = (ia|jb) - (ib|ja)
+            num = fetch4<T>(eri, sd, 1, A, i, B, j) - fetch4<T>(eri, sd, 1, A, j, B, i);
+            L = 0.25 * (fetch4<T>(eri, sd, 1, i, A, j, B) - fetch4<T>(eri, sd, 1, i, B, j, A));
+        } else {
+            D = eps[i] + eps[j] - eps[A] - eps[B];
+            num = fetch4<T>(eri, sd, 0, A, i, B, j);
+            L = 2.0 * fetch4<T>(eri, sd, 0, i, A, j, B) - fetch4<T>(eri, sd, 0, i, B, j, A);
+        }
+        const T t = scalar<T>::div_real(num, D);
+        t2[idx] = t;
+        const T e = L * t;
+        acc[0] += scalar<T>::re(e);
+        acc[1] += scalar<T>::im(e);
+    }
+    grid_sum_finish<2, kThreads>(acc, partials, [&](double(&tot)[2]) {
+        E_out[0] = tot[0];
+        E_out[1] = tot[1];
+    });
+}
+
+// --------------------------------------------------------------------------------------
+// CI update  r <- r - E t ; t <- t + r / D
+// --------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+ci_update_kernel(T *r, T *t, const double *E, const double *eps_o, const double *eps_v, int64_t o, int64_t v,
+                 int64_t n1, int64_t n2, int sh) {
+    const T Ec = scalar<T>::make(E[0], E[1]);
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        double D;
+        if (idx < n1) {
+            const int64_t a = idx % v, i = idx / v;
+            D = eps_o[i >> sh] - eps_v[a >> sh];
+        } else {
+            int64_t q = idx - n1;
+            const int64_t b = q % v; q /= v;
+            const int64_t a = q % v; q /= v;
+            const int64_t j = q % o;
+            const int64_t i = q / o;
+            D = eps_o[i >> sh] + eps_o[j >> sh] - eps_v[a >> sh] - eps_v[b >> sh];
+        }
+        const T tv = t[idx];
+        const T rv = r[idx] - Ec * tv;
+        r[idx] = rv;
+        t[idx] = tv + scalar<T>::div_real(rv, D);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) symmetrize_kernel(const T *h, T *out, int64_t o, int64_t v) {
+    const int64_t total = o * o * v * v;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t q = idx;
+        const int64_t b = q % v; q /= v;
+        const int64_t a = q % v; q /= v;
+        const int64_t j = q % o;
+        const int64_t i = q / o;
+        out[idx] = h[idx] + h[((j * o + i) * v + b) * v + a];
+    }
+}
+
+// --------------------------------------------------------------------------------------
+// dots: out[j] = sum_i op(x_j[i]) * y[i]
+// --------------------------------------------------------------------------------------
+constexpr int kMaxVec = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+dots_kernel(const T *x, int64_t xs, int nvec, const T *y, int64_t len, int conj_x, double *out, double *partials) {
+    double acc[2 * kMaxVec];
+#pragma unroll
+    for (int k = 0; k < 2 * kMaxVec; ++k) acc[k] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const T yv = y[i];
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            if (j < nvec) {
+                T xv = x[(int64_t)j * xs + i];
+                if (conj_x) xv = scalar<T>::cj(xv);
+                const T p = xv * yv;
+                acc[2 * j] += scalar<T>::re(p);
+                acc[2 * j + 1] += scalar<T>::im(p);
+            }
+        }
+    }
+    grid_sum_finish<2 * kMaxVec, kThreads>(acc, partials, [&](double(&tot)[2 * kMaxVec]) {
+        for (int j = 0; j < nvec; ++j) {
+            out[2 * j] = tot[2 * j];
+            out[2 * j + 1] = tot[2 * j + 1];
+        }
+    });
+}
+
+// DIIS push: copy (r, t) into ring slot (it-1)%8 and refresh row/column `slot` of the Gram
+// matrix B[m][n] = sum conj(e_m) e_n (utils.py:117-121; the reference rebuilds all of B every
+// iteration, only one row/column actually changes).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+diis_push_kernel(const T *r, const T *t, T *hist_e, T *hist_t, int64_t len, const int *iter, double *B,
+                 double *partials) {
+    const int it = *iter;
+    const int slot = (it - 1) % kMaxVec;
+    const int m = it < kMaxVec ? it : kMaxVec;
+    double acc[2 * kMaxVec];
+#pragma unroll
+    for (int k = 0; k < 2 * kMaxVec; ++k) acc[k] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const T rv = r[i];
+        hist_e[(int64_t)slot * len + i] = rv;
+        hist_t[(int64_t)slot * len + i] = t[i];
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) {
+            if (j < m) {
+                const T ev = (j == slot) ? rv : hist_e[(int64_t)j * len + i];
+                const T p = scalar<T>::cj(ev) * rv;     // <e_j | e_slot>
+                acc[2 * j] += scalar<T>::re(p);
+                acc[2 * j + 1] += scalar<T>::im(p);
+            }
+        }
+    }
+    grid_sum_finish<2 * kMaxVec, kThreads>(acc, partials, [&](double(&tot)[2 * kMaxVec]) {
+        // B stored as complex (re,im) 8x8 row-major regardless of dtype
+        for (int j = 0; j < m; ++j) {
+            B[2 * (j * kMaxVec + slot)] = tot[2 * j];
+            B[2 * (j * kMaxVec + slot) + 1] = tot[2 * j + 1];
+            B[2 * (slot * kMaxVec + j)] = tot[2 * j];
+            B[2 * (slot * kMaxVec + j) + 1] = -tot[2 * j + 1];
+        }
+    });
+}
+
+// Bordered system  [B -1; -1 0] c = (0,..,0,-1)  with partial pivoting (np.linalg.solve,
+// utils.py:122-135).  m <= 8 -> at most 9x9; one thread is plenty.
+__global__ void diis_solve_kernel(const double *B, int ldb, const int *iter, int m_fixed, double *c) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int m = m_fixed;
+    if (iter != nullptr) m = (*iter < kMaxVec) ? *iter : kMaxVec;
+    const int n = m + 1;
+    cplx Amat[(kMaxVec + 1) * (kMaxVec + 2)];
+    const int ld = kMaxVec + 2;
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) {
+            cplx v;
+            if (i < m && j < m) v = make_cplx(B[2 * (i * ldb + j)], B[2 * (i * ldb + j) + 1]);
+            else if (i == m && j == m) v = make_cplx(0.0, 0.0);
+            else v = make_cplx(-1.0, 0.0);
+            Amat[i * ld + j] = v;
+        }
+        Amat[i * ld + n] = make_cplx(i == m ? -1.0 : 0.0, 0.0);
+    }
+    for (int k = 0; k < n; ++k) {
+        int piv = k;
+        double best = abs2(Amat[k * ld + k]);
+        for (int i = k + 1; i < n; ++i) {
+            double a = abs2(Amat[i * ld + k]);
+            if (a > best) { best = a; piv = i; }
+        }
+        if (piv != k)
+            for (int j = k; j <= n; ++j) {
+                cplx tmp = Amat[k * ld + j];
+                Amat[k * ld + j] = Amat[piv * ld + j];
+                Amat[piv * ld + j] = tmp;
+            }
+        const cplx pv = Amat[k * ld + k];
+        for (int i = k + 1; i < n; ++i) {
+            const cplx f = cdiv(Amat[i * ld + k], pv);
+            for (int j = k + 1; j <= n; ++j) Amat[i * ld + j] = Amat[i * ld + j] - f * Amat[k * ld + j];
+        }
+    }
+    cplx x[kMaxVec + 1];
+    for (int i = n - 1; i >= 0; --i) {
+        cplx s = Amat[i * ld + n];
+        for (int j = i + 1; j < n; ++j) s = s - Amat[i * ld + j] * x[j];
+        x[i] = cdiv(s, Amat[i * ld + i]);
+    }
+    for (int j = 0; j < m; ++j) {
+        c[2 * j] = x[j].x;
+        c[2 * j + 1] = x[j].y;
+    }
+}
+
+// t <- sum_j c_j T_j (m from *iter or fixed; m == 0 keeps t), E = sum w t, rms1/rms2.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+lincomb_kernel(const T *hist, int64_t hs, const int *iter, int m_fixed, const double *c, T *t, const T *t_old,
+               const T *w, int64_t n1, int64_t len, double *out, double *partials) {
+    int m = m_fixed;
+    if (iter != nullptr) m = (*iter < kMaxVec) ? *iter : kMaxVec;
+    T cj[kMaxVec];
+#pragma unroll
+    for (int j = 0; j < kMaxVec; ++j) cj[j] = (j < m) ? scalar<T>::make(c[2 * j], c[2 * j + 1]) : scalar<T>::zero();
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        T tv;
+        if (m > 0) {
+            tv = scalar<T>::zero();
+#pragma unroll
+            for (int j = 0; j < kMaxVec; ++j)
+                if (j < m) tv = tv + cj[j] * hist[(int64_t)j * hs + i];
+            t[i] = tv;
+        } else {
+            tv = t[i];
+        }
+        const T e = w[i] * tv;
+        acc[0] += scalar<T>::re(e);
+        acc[1] += scalar<T>::im(e);
+        const T d = t_old[i] - tv;
+        const T d2 = d * d;
+        const int k = (i < n1) ? 2 : 4;
+        acc[k] += scalar<T>::re(d2);
+        acc[k + 1] += scalar<T>::im(d2);
+    }
+    grid_sum_finish<6, kThreads>(acc, partials, [&](double(&tot)[6]) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out[k] = tot[k];
+    });
+}
+
+__global__ void iter_advance_kernel(int *iter) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *iter += 1;
+}
+
+template <typename T> __global__ void __launch_bounds__(kThreads) copy_kernel(T *dst, const T *src, int64_t len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// y <- alpha * op(x) + beta * y   (beta == 0: y is write-only)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+axpby_kernel(int64_t len, T alpha, const T *x, int conj_x, T beta, int has_beta, T *y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        T xv = x[i];
+        if (conj_x) xv = scalar<T>::cj(xv);
+        T v = alpha * xv;
+        if (has_beta) v = v + beta * y[i];
+        y[i] = v;
+    }
+}
+
+static int stream_grid(int64_t n) {
+    int64_t b = (n + kThreads - 1) / kThreads;
+    const int64_t cap = 148 * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace apyib
+
+using namespace apyib;
+
+extern "C" int64_t apyib_reduce_scratch_len(void) { return (int64_t)kReduceMaxBlocks * kReduceMaxVals + 2; }
+
+extern "C" int apyib_gather4(int dtype, const void *d_src, const int64_t src_dims[4], int spin, void *d_out,
+                             const int64_t out_dims[4], const int32_t perm1[4], const int64_t start1[4], double c1,
+                             const int32_t perm2[4], const int64_t start2[4], double c2, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_src && d_out, "null pointer");
+    Gather4Args g;
+    int64_t total = 1;
+    for (int k = 0; k < 4; ++k) {
+        g.sd[k] = src_dims[k];
+        g.od[k] = out_dims[k];
+        g.perm1[k] = perm1[k];
+        g.st1[k] = start1[k];
+        g.perm2[k] = perm2 ? perm2[k] : perm1[k];
+        g.st2[k] = start2 ? start2[k] : start1[k];
+        APYIB_REQUIRE(perm1[k] >= 0 && perm1[k] < 4, "perm1");
+        APYIB_REQUIRE(g.perm2[k] >= 0 && g.perm2[k] < 4, "perm2");
+        total *= out_dims[k];
+    }
+    // bounds: every source index must stay inside the (spin-expanded) source
+    for (int k = 0; k < 4; ++k) {
+        const int64_t lim = spin ? 2 * src_dims[k] : src_dims[k];
+        APYIB_REQUIRE(start1[k] >= 0 && start1[k] + out_dims[perm1[k]] <= lim, "block 1 out of range");
+        if (c2 != 0.0) APYIB_REQUIRE(g.st2[k] >= 0 && g.st2[k] + out_dims[g.perm2[k]] <= lim, "block 2 out of range");
+    }
+    g.c1 = c1; g.c2 = c2; g.spin = spin;
+    if (total == 0) return APYIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == APYIB_C128)
+        gather4_kernel<cplx><<<stream_grid(total), kThreads, 0, st>>>((const cplx *)d_src, (cplx *)d_out, g);
+    else
+        gather4_kernel<double><<<stream_grid(total), kThreads, 0, st>>>((const double *)d_src, (double *)d_out, g);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_gather2(int dtype, const void *d_src, const int64_t src_dims[2], int spin, void *d_out,
+                             const int64_t out_dims[2], const int32_t perm[2], const int64_t start[2], void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_src && d_out, "null pointer");
+    for (int k = 0; k < 2; ++k) {
+        const int64_t lim = spin ? 2 * src_dims[k] : src_dims[k];
+        APYIB_REQUIRE(perm[k] == 0 || perm[k] == 1, "perm");
+        APYIB_REQUIRE(start[k] >= 0 && start[k] + out_dims[perm[k]] <= lim, "block out of range");
+    }
+    const int64_t total = out_dims[0] * out_dims[1];
+    if (total == 0) return APYIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == APYIB_C128)
+        gather2_kernel<cplx><<<stream_grid(total), kThreads, 0, st>>>((const cplx *)d_src, (cplx *)d_out, src_dims[0],
+                                                                     src_dims[1], out_dims[0], out_dims[1], perm[0],
+                                                                     perm[1], start[0], start[1], spin);
+    else
+        gather2_kernel<double><<<stream_grid(total), kThreads, 0, st>>>((const double *)d_src, (double *)d_out,
+                                                                       src_dims[0], src_dims[1], out_dims[0],
+                                                                       out_dims[1], perm[0], perm[1], start[0],
+                                                                       start[1], spin);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, int64_t o, const double *d_eps,
+                                   int spin_orbital, void *d_t2, double *d_E, double *d_partials, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_eri_mo && d_eps && d_t2 && d_E && d_partials, "null pointer");
+    APYIB_REQUIRE(n > 0 && o >= 0 && o <= n, "sizes");
+    const int64_t O = spin_orbital ? 2 * o : o, V = spin_orbital ? 2 * (n - o) : (n - o);
+    const int64_t total = O * O * V * V;
+    const int grid = stream_grid(total);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MP2_LAUNCH(T, SO) \
+    mp2_kernel<T, SO><<<grid, kThreads, 0, st>>>((const T *)d_eri_mo, n, o, d_eps, (T *)d_t2, d_E, d_partials)
+    if (dtype == APYIB_C128) {
+        if (spin_orbital) MP2_LAUNCH(cplx, true); else MP2_LAUNCH(cplx, false);
+    } else {
+        if (spin_orbital) MP2_LAUNCH(double, true); else MP2_LAUNCH(double, false);
+    }
+#undef MP2_LAUNCH
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_ci_update(int dtype, void *d_r, void *d_t, const double *d_E, const double *d_eps_o,
+                               const double *d_eps_v, int64_t o, int64_t v, int has_singles, int spin_orbital,
+                               void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_r && d_t && d_E && d_eps_o && d_eps_v, "null pointer");
+    const int64_t n1 = has_singles ? o * v : 0, n2 = o * o * v * v;
+    if (n1 + n2 == 0) return APYIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(n1 + n2);
+    const int sh = spin_orbital ? 1 : 0;
+    if (dtype == APYIB_C128)
+        ci_update_kernel<cplx><<<grid, kThreads, 0, st>>>((cplx *)d_r, (cplx *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh);
+    else
+        ci_update_kernel<double><<<grid, kThreads, 0, st>>>((double *)d_r, (double *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_symmetrize_ijab(int dtype, const void *d_half, void *d_out, int64_t o, int64_t v, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_half && d_out && d_half != d_out, "pointers (must be out of place)");
+    const int64_t total = o * o * v * v;
+    if (total == 0) return APYIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == APYIB_C128)
+        symmetrize_kernel<cplx><<<stream_grid(total), kThreads, 0, st>>>((const cplx *)d_half, (cplx *)d_out, o, v);
+    else
+        symmetrize_kernel<double><<<stream_grid(total), kThreads, 0, st>>>((const double *)d_half, (double *)d_out, o, v);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_dots(int dtype, const void *d_x, int64_t x_stride, int nvec, const void *d_y, int64_t len,
+                          int conj_x, double *d_out, double *d_partials, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_x && d_y && d_out && d_partials, "null pointer");
+    APYIB_REQUIRE(nvec >= 1 && nvec <= kMaxVec, "nvec");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(len);
+    if (dtype == APYIB_C128)
+        dots_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_x, x_stride, nvec, (const cplx *)d_y, len, conj_x, d_out, d_partials);
+    else
+        dots_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_x, x_stride, nvec, (const double *)d_y, len, conj_x, d_out, d_partials);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_diis_push(int dtype, const void *d_r, const void *d_t, void *d_hist_e, void *d_hist_t,
+                               int64_t len, const int32_t *d_iter, double *d_B, double *d_partials, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_r && d_t && d_hist_e && d_hist_t && d_iter && d_B && d_partials, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(len);
+    if (dtype == APYIB_C128)
+        diis_push_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_r, (const cplx *)d_t, (cplx *)d_hist_e, (cplx *)d_hist_t, len, d_iter, d_B, d_partials);
+    else
+        diis_push_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_r, (const double *)d_t, (double *)d_hist_e, (double *)d_hist_t, len, d_iter, d_B, d_partials);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_diis_solve(int dtype, const double *d_B, int ldb, int m, const int32_t *d_iter, double *d_c,
+                                void *stream) {
+    (void)dtype;
+    APYIB_REQUIRE(d_B && d_c, "null pointer");
+    APYIB_REQUIRE(d_iter != nullptr || (m >= 1 && m <= kMaxVec), "m");
+    diis_solve_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_B, ldb, d_iter, m, d_c);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_lincomb_energy_rms(int dtype, const void *d_hist, int64_t hist_stride, int m,
+                                        const int32_t *d_iter, const double *d_c, void *d_t, const void *d_t_old,
+                                        const void *d_w, int64_t n1, int64_t len, double *d_out, double *d_partials,
+                                        void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_t && d_t_old && d_w && d_out && d_partials, "null pointer");
+    APYIB_REQUIRE(m >= 0 && m <= kMaxVec, "m");
+    APYIB_REQUIRE((m == 0 && d_iter == nullptr) || (d_hist && d_c), "history");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(len);
+    if (dtype == APYIB_C128)
+        lincomb_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_hist, hist_stride, d_iter, m, d_c, (cplx *)d_t, (const cplx *)d_t_old, (const cplx *)d_w, n1, len, d_out, d_partials);
+    else
+        lincomb_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_hist, hist_stride, d_iter, m, d_c, (double *)d_t, (const double *)d_t_old, (const double *)d_w, n1, len, d_out, d_partials);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_iter_advance(int32_t *d_iter, void *stream) {
+    APYIB_REQUIRE(d_iter, "null pointer");
+    iter_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_iter);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_copy(int dtype, void *d_dst, const void *d_src, int64_t len, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_dst && d_src, "null pointer");
+    if (len == 0) return APYIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == APYIB_C128)
+        copy_kernel<cplx><<<stream_grid(len), kThreads, 0, st>>>((cplx *)d_dst, (const cplx *)d_src, len);
+    else
+        copy_kernel<double><<<stream_grid(len), kThreads, 0, st>>>((double *)d_dst, (const double *)d_src, len);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_axpby(int dtype, int64_t len, double alpha_re, double alpha_im, const void *d_x, int conj_x,
+                           double beta_re, double beta_im, void *d_y, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_x && d_y, "null pointer");
+    if (len == 0) return APYIB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int hb = (beta_re != 0.0 || beta_im != 0.0) ? 1 : 0;
+    if (dtype == APYIB_C128)
+        axpby_kernel<cplx><<<stream_grid(len), kThreads, 0, st>>>(len, make_cplx(alpha_re, alpha_im), (const cplx *)d_x,
+                                                                 conj_x, make_cplx(beta_re, beta_im), hb, (cplx *)d_y);
+    else
+        axpby_kernel<double><<<stream_grid(len), kThreads, 0, st>>>(len, alpha_re, (const double *)d_x, 0, beta_re, hb,
+                                                                   (double *)d_y);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}

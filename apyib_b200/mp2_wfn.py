@@ -1,0 +1,56 @@
+"""MP2 wavefunction -- drop-in for apyib/mp2_wfn.py (same constructor, solve methods, returns).
+
+The amplitudes and the energy come out of ONE streaming kernel (csrc/stream.cu: mp2_kernel):
+denominators are formed on the fly from the orbital energies, the spin-orbital variant
+spin-blocks and antisymmetrises the spatial MO integrals on the fly (the reference first
+materialises the (2n)^4 spin-orbital tensor with an interpreted loop, utils.py:317-365).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import lib, check
+from .device import to_device, to_host, empty, zeros, dtype_code, ptr, stream_ptr, reduce_scratch
+from .utils import get_slices, compute_ERI_MO_dev
+
+
+class mp2_wfn(object):
+    """Reference: apyib/mp2_wfn.py:16-87."""
+
+    def __init__(self, parameters, wfn):
+        self.parameters = parameters
+        self.H = wfn.H
+        self.wfn = wfn
+        self.C = wfn.C
+        self.C_list, self.I_list = get_slices(self.parameters, self.wfn)
+        o, v = self.C_list[1], self.C_list[2]
+        self.eps_o = np.asarray(wfn.eps)[o]
+        self.eps_v = np.asarray(wfn.eps)[v]
+        self.D_ijab = (self.eps_o.reshape(-1, 1, 1, 1) + self.eps_o.reshape(-1, 1, 1)
+                       - self.eps_v.reshape(-1, 1) - self.eps_v)           # mp2_wfn.py:39
+
+    def _solve(self, spin_orbital):
+        ERI_MO = compute_ERI_MO_dev(self.parameters, self.wfn, self.C_list)   # (n,n,n,n) chemists'
+        n = ERI_MO.shape[0]
+        o = len(self.eps_o)
+        eps = to_device(np.concatenate([self.eps_o, self.eps_v]).real.astype(np.float64))
+        O, V = (2 * o, 2 * (n - o)) if spin_orbital else (o, n - o)
+        t2 = empty((O, O, V, V), ERI_MO.dtype)
+        E = zeros((2,), torch.float64)
+        check(lib.apyib_mp2_t2_energy(dtype_code(ERI_MO), ptr(ERI_MO), n, o, ptr(eps), int(spin_orbital),
+                                      ptr(t2), ptr(E), ptr(reduce_scratch()), stream_ptr()))
+        e = to_host(E)
+        if ERI_MO.dtype == torch.complex128:
+            E_MP2 = np.complex128(complex(e[0], e[1]))
+        else:
+            E_MP2 = np.float64(e[0])
+        return E_MP2, to_host(t2)
+
+    def solve_MP2(self):
+        """Reference: mp2_wfn.py:42-59.  Returns (E_MP2, t2[o,o,v,v])."""
+        return self._solve(False)
+
+    def solve_MP2_SO(self):
+        """Reference: mp2_wfn.py:64-87.  Returns (E_MP2, t2[O,O,V,V]) in the spin-orbital basis."""
+        return self._solve(True)

@@ -1,0 +1,195 @@
+"""Drop-in counterparts of the hot-path helpers in apyib/utils.py.
+
+Same names, argument meaning and return types (numpy arrays) as the reference; every
+function also has a `*_dev` variant returning CUDA tensors, which is what the solver classes use
+so that integrals never bounce through the host.  All arithmetic runs in libapyib_b200 kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import lib, check
+from .contraction import contract, contract_new
+from .device import (to_device, to_host, empty, zeros, dtype_code, ptr, stream_ptr, reduce_scratch, i32, i64)
+
+SPATIAL_METHODS = ("RHF", "MP2", "CID", "CISD")
+SO_METHODS = ("MP2_SO", "CID_SO", "CISD_SO")
+
+
+# ---------------------------------------------------------------------------------------------
+# a1  get_slices                                                        (apyib/utils.py:184-213)
+# ---------------------------------------------------------------------------------------------
+def get_slices(parameters, wfn):
+    nfzc = wfn.H.basis_set.n_frozen_core()
+    method = parameters["method"]
+    if method in SPATIAL_METHODS:
+        so = 0
+    elif method in SO_METHODS:
+        so = 1
+    else:
+        raise ValueError("unknown method %r" % (method,))
+    b = (C.c_int32 * 16)()
+    check(lib.apyib_get_slices(int(wfn.nbf), int(wfn.ndocc), int(nfzc), so, b))
+    sl = [slice(int(b[2 * k]), int(b[2 * k + 1])) for k in range(8)]
+    return sl[:4], sl[4:]
+
+
+# ---------------------------------------------------------------------------------------------
+# upload-once cache of the per-geometry AO integrals (north star: "uploaded once")
+# ---------------------------------------------------------------------------------------------
+def ao_on_device(wfn, want_complex):
+    H = wfn.H
+    cache = getattr(H, "_apyib_b200_dev", None)
+    if cache is None:
+        cache = {}
+        try:
+            H._apyib_b200_dev = cache
+        except AttributeError:
+            pass
+    key = "c" if want_complex else "r"
+    if key not in cache:
+        dt = torch.complex128 if want_complex else torch.float64
+        h = np.asarray(H.T) + np.asarray(H.V)
+        if not want_complex and (np.iscomplexobj(h) or np.iscomplexobj(H.ERI)):
+            raise TypeError("complex integrals need the complex path")
+        cache[key] = (to_device(h, dt), to_device(np.asarray(H.ERI), dt))
+    return cache[key]
+
+
+def _is_complex(wfn):
+    return bool(np.iscomplexobj(wfn.C) or np.iscomplexobj(wfn.H.T) or np.iscomplexobj(wfn.H.V)
+                or np.iscomplexobj(wfn.H.ERI))
+
+
+# ---------------------------------------------------------------------------------------------
+# a2  compute_F_MO                                                      (apyib/utils.py:217-254)
+# ---------------------------------------------------------------------------------------------
+def compute_F_MO_dev(parameters, wfn, C_list):
+    f, o, v, t = C_list
+    cplx = _is_complex(wfn)
+    dt = torch.complex128 if cplx else torch.float64
+    h, G = ao_on_device(wfn, cplx)
+    Cd = to_device(np.asarray(wfn.C), dt)
+    Gx = G.swapaxes(1, 2)                                   # strided view, no copy
+
+    def fock_like(h_in, Cocc):
+        D = contract_new("mp,np->mn", Cocc, Cocc, conj_b=True)
+        F = h_in.clone()
+        contract("ls,mnls->mn", D, G, F, alpha=2.0, beta=1.0)       # + 2 J
+        contract("ls,mnls->mn", D, Gx, F, alpha=-1.0, beta=1.0)     # - K
+        return D, F
+
+    E_fc = 0
+    if parameters["freeze_core"] == True:  # noqa: E712 (reference semantics, utils.py:238)
+        D_fc, h_fc = fock_like(h, Cd[:, f])
+        hs = h + h_fc
+        e = zeros((2,), torch.float64)
+        check(lib.apyib_dots(dtype_code(hs), ptr(D_fc.transpose(0, 1).contiguous()), 0, 1, ptr(hs),
+                             hs.numel(), 0, ptr(e), ptr(reduce_scratch()), stream_ptr()))
+        eh = to_host(e)
+        E_fc = complex(eh[0], eh[1]) if cplx else float(eh[0])
+        h = h_fc
+    _, F_AO = fock_like(h, Cd[:, o])
+    Ct = Cd[:, t]
+    tmp = contract_new("ij,jq->iq", F_AO, Ct)
+    F_MO = contract_new("ip,iq->pq", Ct, tmp, conj_a=True)
+    return F_MO, E_fc
+
+
+def compute_F_MO(parameters, wfn, C_list):
+    F, E_fc = compute_F_MO_dev(parameters, wfn, C_list)
+    return to_host(F), E_fc
+
+
+# ---------------------------------------------------------------------------------------------
+# a3  compute_ERI_MO                                                    (apyib/utils.py:258-279)
+# ---------------------------------------------------------------------------------------------
+def compute_ERI_MO_dev(parameters, wfn, C_list):
+    cplx = _is_complex(wfn)
+    dt = torch.complex128 if cplx else torch.float64
+    _, G = ao_on_device(wfn, cplx)
+    Ct = to_device(np.asarray(wfn.C), dt)[:, C_list[3]]
+    X = contract_new("mnlg,gs->mnls", G, Ct)
+    X = contract_new("mnls,lr->mnrs", X, Ct, conj_b=True)
+    X = contract_new("nq,mnrs->mqrs", Ct, X)
+    X = contract_new("mp,mqrs->pqrs", Ct, X, conj_a=True)
+    return X
+
+
+def compute_ERI_MO(parameters, wfn, C_list):
+    return to_host(compute_ERI_MO_dev(parameters, wfn, C_list))
+
+
+# ---------------------------------------------------------------------------------------------
+# a4  spin blocking                                             (apyib/utils.py:283-365, 393-422)
+# ---------------------------------------------------------------------------------------------
+def spin_block_2_dev(X):
+    n0, n1 = X.shape
+    Xc = X.contiguous()
+    out = empty((2 * n0, 2 * n1), X.dtype)
+    check(lib.apyib_gather2(dtype_code(Xc), ptr(Xc), i64([n0, n1]), 1, ptr(out), i64([2 * n0, 2 * n1]),
+                            i32([0, 1]), i64([0, 0]), stream_ptr()))
+    return out
+
+
+def gather4(src, spin, out_shape, perm1, start1, c1=1.0, perm2=None, start2=None, c2=0.0):
+    """out[x] = c1*G(start1 + x[perm1]) + c2*G(start2 + x[perm2]) -- see include/apyib_b200.h."""
+    assert src.is_contiguous()
+    out = empty(tuple(out_shape), src.dtype)
+    p2 = i32(perm2) if perm2 is not None else i32(perm1)
+    s2 = i64(start2) if start2 is not None else i64(start1)
+    check(lib.apyib_gather4(dtype_code(src), ptr(src), i64(src.shape), int(spin), ptr(out), i64(out_shape),
+                            i32(perm1), i64(start1), float(c1), p2, s2, float(c2), stream_ptr()))
+    return out
+
+
+def spin_block_4_dev(X):
+    n = list(X.shape)
+    return gather4(X.contiguous(), 1, [2 * d for d in n], [0, 1, 2, 3], [0, 0, 0, 0])
+
+
+def compute_F_SO(wfn, F_MO):
+    return to_host(spin_block_2_dev(to_device(F_MO)))
+
+
+def compute_ERI_SO(wfn, ERI_MO):
+    return to_host(spin_block_4_dev(to_device(ERI_MO)))
+
+
+def compute_so_overlap(nbf, mo_overlap):
+    return to_host(spin_block_2_dev(to_device(mo_overlap)))
+
+
+# ---------------------------------------------------------------------------------------------
+# a14  MO overlap                                                       (apyib/utils.py:370-388)
+# ---------------------------------------------------------------------------------------------
+def mo_overlap_dev(C_bra, S_ao, C_ket):
+    """C_bra^H S_AO C_ket on the device; S_AO is the (mixed-geometry) AO overlap, a host input."""
+    cplx = any(np.iscomplexobj(x) for x in (C_bra, S_ao, C_ket))
+    dt = torch.complex128 if cplx else torch.float64
+    Cb, S, Ck = to_device(C_bra, dt), to_device(S_ao, dt), to_device(C_ket, dt)
+    tmp = contract_new("mn,nq->mq", S, Ck)
+    return contract_new("mp,mq->pq", Cb, tmp, conj_a=True)
+
+
+def compute_mo_overlap(ndocc, nbf, bra_basis, bra_wfn, ket_basis, ket_wfn, ao_overlap=None):
+    """Reference signature plus an explicit AO overlap: Psi4's mixed-basis `ao_overlap` is a host
+    input (the integral provider supplies it)."""
+    if ao_overlap is None:
+        from .hostchem import provider_ao_overlap
+        ao_overlap = provider_ao_overlap(bra_basis, ket_basis)
+    return to_host(mo_overlap_dev(bra_wfn, ao_overlap, ket_wfn))
+
+
+# ---------------------------------------------------------------------------------------------
+# a11  compute_phase                                                    (apyib/utils.py:427-446)
+# ---------------------------------------------------------------------------------------------
+def compute_phase(ndocc, nbf, unperturbed_basis, unperturbed_wfn, ket_basis, ket_wfn, ao_overlap=None):
+    S = compute_mo_overlap(ndocc, nbf, unperturbed_basis, unperturbed_wfn, ket_basis, ket_wfn, ao_overlap)
+    d = np.diagonal(S)
+    N = np.sqrt(d * np.conjugate(d))
+    phase = d / N
+    return np.asarray(ket_wfn) * (phase ** -1)[None, :]

@@ -1,0 +1,176 @@
+"""GPU parity tests of the individual kernels (through the C-ABI) against numpy / the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rng, shape, cplx):
+    x = rng.standard_normal(shape)
+    if cplx:
+        x = x + 1j * rng.standard_normal(shape)
+    return x
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("spec,shapes", [
+    ("mk,kn->mn", [(70, 33), (33, 45)]),
+    ("mk,kn->mn", [(200, 130), (130, 190)]),
+    ("ijef,abef->ijab", [(5, 5, 7, 7), (7, 7, 7, 7)]),
+    ("kbcj,ikac->ijab", [(4, 6, 6, 4), (4, 4, 6, 6)]),
+    ("ls,mnls->mn", [(9, 9), (9, 9, 9, 9)]),
+    ("jb,ijab->ia", [(4, 6), (4, 4, 6, 6)]),
+    ("mnlg,gs->mnls", [(6, 6, 6, 6), (6, 5)]),
+    ("mk,kn->mn", [(1, 1), (1, 1)]),
+    ("ia,jb->iajb", [(3, 4), (2, 5)]),
+])
+def test_contract_matches_einsum(spec, shapes, cplx):
+    from apyib_b200.contraction import contract
+    from apyib_b200.device import to_device, to_host
+    rng = np.random.default_rng(1)
+    A, B = _rand(rng, shapes[0], cplx), _rand(rng, shapes[1], cplx)
+    ref = np.einsum(spec, A, B)
+    out0 = _rand(rng, ref.shape, cplx)
+    dA, dB, dO = to_device(A), to_device(B), to_device(out0)
+    alpha, beta = (0.5 - 0.25j, 1.5 + 0.5j) if cplx else (0.5, 1.5)
+    contract(spec, dA, dB, dO, alpha, beta)
+    want = alpha * ref + beta * out0
+    assert np.abs(to_host(dO) - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+    # conjugated operands + beta = 0 must ignore (possibly NaN) previous contents
+    dO.fill_(float("nan"))
+    contract(spec, dA, dB, dO, 1.0, 0.0, conj_a=True, conj_b=True)
+    want = np.einsum(spec, A.conj(), B.conj())
+    assert np.abs(to_host(dO) - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_contract_strided_views(cplx):
+    """operands that are slices / swapaxes views, as the reference feeds to opt_einsum"""
+    from apyib_b200.contraction import contract
+    from apyib_b200.device import to_device, to_host
+    rng = np.random.default_rng(2)
+    n, o = 9, 3
+    E = _rand(rng, (n, n, n, n), cplx)
+    t2 = _rand(rng, (o, o, n - o, n - o), cplx)
+    W = E.swapaxes(1, 2)
+    dE, dt = to_device(E), to_device(t2)
+    dW = dE.swapaxes(1, 2)
+    r = np.zeros_like(t2)
+    dr = to_device(r)
+    contract("abcd,ijcd->ijab", dW[o:, o:, o:, o:], dt, dr, 1.0, 0.0)
+    contract("kbcj,ikac->ijab", dW[:o, o:, o:, :o], dt, dr, -1.0, 1.0)
+    want = np.einsum("abcd,ijcd->ijab", W[o:, o:, o:, o:], t2) - np.einsum("kbcj,ikac->ijab", W[:o, o:, o:, :o], t2)
+    assert np.abs(to_host(dr) - want).max() < 1e-12
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+@pytest.mark.parametrize("spin", [0, 1])
+def test_gather4_blocks(cplx, spin):
+    from oracle import apyib_oracle as orc
+    from apyib_b200.ci_wfn import w_block
+    from apyib_b200.device import to_device, to_host
+    rng = np.random.default_rng(3)
+    n, o = 6, 2
+    E = _rand(rng, (n, n, n, n), cplx)
+    G = orc.spin_block_4(E) if spin else E
+    W = G.swapaxes(1, 2)
+    f = 2 if spin else 1
+    O, V = f * o, f * (n - o)
+    os_, vs = slice(0, O), slice(O, O + V)
+    bd = {"o": (0, O), "v": (O, O + V)}
+    sp = dict(i="o", j="o", k="o", a="v", b="v", c="v")
+    dE = to_device(E)
+    got = to_host(w_block(dE, "kbcj", "kbcj", sp, bd, spin, 1.0, -1.0))
+    want = W[os_, vs, vs, os_] - W.swapaxes(2, 3)[os_, vs, vs, os_]
+    assert np.array_equal(got, want)
+    got = to_host(w_block(dE, "abij", "ijab", sp, bd, spin, 2.0, -1.0))
+    want = 2.0 * W.swapaxes(0, 2).swapaxes(1, 3)[os_, os_, vs, vs] - W.swapaxes(2, 3).swapaxes(0, 2).swapaxes(1, 3)[os_, os_, vs, vs]
+    assert np.abs(got - want).max() < 1e-15
+
+
+def test_spin_block_bit_exact():
+    from oracle import apyib_oracle as orc
+    from apyib_b200 import utils
+    rng = np.random.default_rng(4)
+    F = _rand(rng, (5, 5), True)
+    E = _rand(rng, (3, 4, 3, 4), True)
+    assert np.array_equal(utils.compute_F_SO(None, F), orc.spin_block_2(F))
+    assert np.array_equal(utils.compute_ERI_SO(None, E), orc.spin_block_4(E))
+    assert np.array_equal(utils.compute_so_overlap(5, F), orc.spin_block_2(F))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 12, 16, 17, 24, 32])
+def test_det_outer_vs_numpy(n):
+    from apyib_b200._lib import lib, check
+    from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
+    rng = np.random.default_rng(5 + n)
+    ns = n + 5
+    S = np.eye(ns) + 0.3 * (rng.standard_normal((ns, ns)) + 1j * rng.standard_normal((ns, ns)))
+    nrow, ncol = 37, 29
+    rows = np.array([rng.permutation(ns)[:n] for _ in range(nrow)], dtype=np.int32)
+    cols = np.array([rng.permutation(ns)[:n] for _ in range(ncol)], dtype=np.int32)
+    dS, dr, dc = to_device(S), torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
+    out = empty((nrow, ncol), torch.complex128)
+    check(lib.apyib_det_outer(ptr(dS), ns, n, ptr(dr), nrow, ptr(dc), ncol, ptr(out), stream_ptr()))
+    want = np.linalg.det(S[rows[:, None, :, None], cols[None, :, None, :]])
+    got = to_host(out)
+    assert np.abs(got - want).max() < 1e-11 * max(1.0, np.abs(want).max())
+
+
+def test_det_singular_and_tiny_pivots():
+    from apyib_b200._lib import lib, check
+    from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
+    n = 6
+    S = np.zeros((n, n), dtype=np.complex128)
+    S[np.arange(n), (np.arange(n) + 1) % n] = 1.0          # cyclic permutation matrix, zero diagonal
+    rows = np.arange(n, dtype=np.int32)[None, :]
+    dS, dr = to_device(S), torch.from_numpy(rows).cuda()
+    out = empty((1, 1), torch.complex128)
+    check(lib.apyib_det_outer(ptr(dS), n, n, ptr(dr), 1, ptr(dr), 1, ptr(out), stream_ptr()))
+    assert abs(to_host(out)[0, 0] - np.linalg.det(S)) < 1e-14
+    S[:, 0] = 0.0                                          # exactly singular
+    dS = to_device(S)
+    check(lib.apyib_det_outer(ptr(dS), n, n, ptr(dr), 1, ptr(dr), 1, ptr(out), stream_ptr()))
+    assert to_host(out)[0, 0] == 0
+
+
+@pytest.mark.parametrize("n", [4, 9, 16])
+def test_det_matvec_vs_numpy(n):
+    from apyib_b200._lib import lib, check
+    from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
+    rng = np.random.default_rng(50 + n)
+    ns = n + 6
+    S = np.eye(ns) + 0.2 * (rng.standard_normal((ns, ns)) + 1j * rng.standard_normal((ns, ns)))
+    nrow, ncol, ny = 53, 211, 3
+    rows = np.array([rng.permutation(ns)[:n] for _ in range(nrow)], dtype=np.int32)
+    cols = np.array([rng.permutation(ns)[:n] for _ in range(ncol)], dtype=np.int32)
+    Y = rng.standard_normal((ny, ncol)) + 1j * rng.standard_normal((ny, ncol))
+    dS, dr, dc, dY = to_device(S), torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda(), to_device(Y)
+    Z = empty((ny, nrow), torch.complex128)
+    work = empty((int(lib.apyib_det_matvec_work_len(nrow, ncol, ny, n)),), torch.complex128)
+    check(lib.apyib_det_matvec(ptr(dS), ns, n, ptr(dr), nrow, ptr(dc), ncol, ptr(dY), ny, ptr(Z), ptr(work), stream_ptr()))
+    D = np.linalg.det(S[rows[:, None, :, None], cols[None, :, None, :]])
+    want = Y @ D.T
+    assert np.abs(to_host(Z) - want).max() < 1e-11 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_dots_and_axpby(cplx):
+    from apyib_b200._lib import lib, check
+    from apyib_b200.device import to_device, to_host, zeros, ptr, stream_ptr, reduce_scratch, dtype_code
+    rng = np.random.default_rng(6)
+    n, nv = 100003, 5
+    X, y = _rand(rng, (nv, n), cplx), _rand(rng, (n,), cplx)
+    dX, dy = to_device(X), to_device(y)
+    out = zeros((2 * nv,), torch.float64)
+    for cj in (0, 1):
+        check(lib.apyib_dots(dtype_code(dX), ptr(dX), n, nv, ptr(dy), n, cj, ptr(out), ptr(reduce_scratch()), stream_ptr()))
+        got = to_host(out).reshape(nv, 2)
+        want = (X.conj() if cj else X) @ y
+        assert np.abs(got[:, 0] + 1j * got[:, 1] - want).max() < 1e-10
+    check(lib.apyib_axpby(dtype_code(dX), n, 0.5, 0.25 if cplx else 0.0, ptr(dX[1]), 1, 2.0, 0.0, ptr(dy), stream_ptr()))
+    a = (0.5 + 0.25j) if cplx else 0.5
+    assert np.abs(to_host(dy) - (a * X[1].conj() + 2.0 * y)).max() < 1e-13
