@@ -524,8 +524,8 @@ extern "C" int apyib_iter_advance(int32_t *d_iter, void *stream) {
 
 extern "C" int apyib_copy(int dtype, void *d_dst, const void *d_src, int64_t len, void *stream) {
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
-    APYIB_REQUIRE(d_dst && d_src, "null pointer");
     if (len == 0) return APYIB_OK;
+    APYIB_REQUIRE(d_dst && d_src, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == APYIB_C128)
         copy_kernel<cplx><<<stream_grid(len), kThreads, 0, st>>>((cplx *)d_dst, (const cplx *)d_src, len);

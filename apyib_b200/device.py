@@ -85,13 +85,18 @@ class Graph:
         self._exec = None
 
     def capture(self, fn):
-        st = torch.cuda.current_stream()
-        check(lib.apyib_graph_begin(C.c_void_p(st.cuda_stream)))
-        try:
-            fn()
-        finally:
-            h = C.c_void_p()
-            rc = lib.apyib_graph_end(C.c_void_p(st.cuda_stream), C.byref(h))
+        """Records the launches `fn` enqueues (nothing executes).  The legacy default stream
+        cannot be captured, so recording happens on a private side stream; `fn` must only
+        launch libapyib_b200 kernels on the *current* stream and must not allocate."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            check(lib.apyib_graph_begin(C.c_void_p(side.cuda_stream)))
+            try:
+                fn()
+            finally:
+                h = C.c_void_p()
+                rc = lib.apyib_graph_end(C.c_void_p(side.cuda_stream), C.byref(h))
         check(rc)
         self._exec = h
 
