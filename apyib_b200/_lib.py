@@ -45,6 +45,7 @@ SIGNATURES = {
     "apyib_axpby": (_int, [_int, _i64, _dbl, _dbl, _vp, _int, _dbl, _dbl, _vp, _vp]),
     "apyib_det_outer": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _int, _vp, _vp, _vp]),
+    "apyib_pack_doubles": (_int, [_vp, _i64, _int, _int, _int, _int, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec_work_len": (_i64, [_i64, _i64, _int, _int]),
     "apyib_get_slices": (_int, [_int, _int, _int, _int, _i32p]),
     "apyib_det_enumeration": (_int, [_int, _int, _int, _i32p, _i64p, _i32p, _i64p]),

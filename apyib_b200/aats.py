@@ -1,0 +1,531 @@
+"""Finite-difference atomic axial tensors -- drop-in for apyib/aats.py.
+
+Public surface kept: AAT(...) constructor, compute_SO_det, compute_normalization,
+compute_all_dets, compute_spatial_aats, compute_SO_aats (+ the nine compute_SO_I_* terms).
+
+B200 design:
+  * every substituted determinant is an LU done by a sub-warp on the device
+    (csrc/dets.cu); substituted matrices are formed on the fly from the MO overlap and index lists;
+  * the reference materialises the antisymmetrised determinant tensors (8 indices,
+    aats.py:575/630) and then contracts them with amplitudes.  Here the antisymmetric completion
+    is folded into the amplitude vectors (apyib_pack_doubles) and the det-table x vector
+    products are fused into the LU kernel (apyib_det_matvec) -- the tables never exist;
+  * the remaining o^2 v^2-sized contractions go through the DMMA contraction kernel;
+  * determinant families that do not depend on (alpha, beta) -- uu, up/un[beta], pu/nu[alpha] -- are
+    evaluated once per molecule for all bra/ket amplitude vectors and cached, instead of being
+    recomputed for every tensor element as `compute_spatial_aats` does in the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import config
+from ._lib import lib, check
+from .contraction import contract, contract_new
+from .device import to_device, to_host, empty, zeros, ptr, stream_ptr, reduce_scratch, device
+from .utils import mo_overlap_dev, spin_block_2_dev, SO_METHODS
+
+_C128 = torch.complex128
+_tables = {}
+
+
+def _i32_host(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class _Tables:
+    """Index tables of compute_all_dets' enumeration (aats.py:581-618), built by the C library
+    (bit-exact contract) and uploaded once per (ndocc, nfzc, nvirt)."""
+
+    def __init__(self, no, nf, nv):
+        self.no, self.nf, self.nv = no, nf, nv
+        ns, nd = C.c_int64(), C.c_int64()
+        check(lib.apyib_det_enumeration(no, nf, nv, None, C.byref(ns), None, C.byref(nd)))
+        self.n1, self.n2 = ns.value, nd.value
+        self.singles = np.zeros((self.n1, 2), dtype=np.int32)
+        self.doubles = np.zeros((self.n2, 4), dtype=np.int32)
+        check(lib.apyib_det_enumeration(no, nf, nv, _i32_host(self.singles)[1], None,
+                                        _i32_host(self.doubles)[1], None))
+        self.L = []
+        for sub, cnt, nsub in ((None, 1, 0), (self.singles, self.n1, 1), (self.doubles, self.n2, 2)):
+            out = np.zeros((max(cnt, 1), no), dtype=np.int32)
+            if cnt:
+                check(lib.apyib_det_index_lists(no, _i32_host(sub)[1] if sub is not None else None, cnt, nsub,
+                                                _i32_host(out)[1]))
+            self.L.append(torch.from_numpy(out[:cnt].copy()).to(device()))
+        self.doubles_dev = torch.from_numpy(self.doubles.copy()).to(device())
+
+    @staticmethod
+    def get(no, nf, nv):
+        key = (no, nf, nv, torch.cuda.current_device())
+        if key not in _tables:
+            _tables[key] = _Tables(no, nf, nv)
+        return _tables[key]
+
+
+def _det_outer(S, n, rows, cols):
+    out = empty((rows.shape[0], cols.shape[0]), _C128)
+    check(lib.apyib_det_outer(ptr(S), S.shape[0], n, ptr(rows), rows.shape[0], ptr(cols), cols.shape[0], ptr(out),
+                              stream_ptr()))
+    return out
+
+
+def _det_matvec(S, n, rows, cols, Y):
+    """Z[q, r] = sum_c det(S[rows[r], cols[c]]) Y[q, c]; any number of vectors (<= 4 per launch)."""
+    Y = Y.contiguous()
+    nq, nrow, ncol = Y.shape[0], rows.shape[0], cols.shape[0]
+    Z = empty((nq, nrow), _C128)
+    for q0 in range(0, nq, 4):
+        q1 = min(nq, q0 + 4)
+        work = empty((int(lib.apyib_det_matvec_work_len(nrow, ncol, q1 - q0, n)),), _C128)
+        check(lib.apyib_det_matvec(ptr(S), S.shape[0], n, ptr(rows), nrow, ptr(cols), ncol, ptr(Y[q0:q1]), q1 - q0,
+                                   ptr(Z[q0:q1]), ptr(work), stream_ptr()))
+    return Z
+
+
+def _stack(ts):
+    return torch.stack([to_device(np.asarray(t), _C128) for t in ts])
+
+
+def _axpby(alpha, x, beta, y, conj_x=False):
+    a, b = complex(alpha), complex(beta)
+    check(lib.apyib_axpby(1, x.numel(), a.real, a.imag, ptr(x), int(conj_x), b.real, b.imag, ptr(y), stream_ptr()))
+    return y
+
+
+def _vdot(x, y, conj_x=True):
+    """sum op(x) * y over equally laid out device tensors -> python complex"""
+    out = zeros((2,), torch.float64)
+    check(lib.apyib_dots(1, ptr(x), 0, 1, ptr(y), x.numel(), int(conj_x), ptr(out), ptr(reduce_scratch()), stream_ptr()))
+    h = to_host(out)
+    return complex(h[0], h[1])
+
+
+class AAT(object):
+    """The atomic axial tensor object computed by finite difference (aats.py:19-115)."""
+
+    def __init__(self, parameters, wfn, unperturbed_wfn, unperturbed_basis, unperturbed_T, nuc_pos_wfn, nuc_neg_wfn,
+                 nuc_pos_basis, nuc_neg_basis, nuc_pos_T, nuc_neg_T, mag_pos_wfn, mag_neg_wfn, mag_pos_basis,
+                 mag_neg_basis, mag_pos_T, mag_neg_T, nuc_pert_strength, mag_pert_strength):
+        from .hostchem import provider_ao_overlap
+        self.nuc_pos_wfn, self.nuc_neg_wfn = nuc_pos_wfn, nuc_neg_wfn
+        self.nuc_pos_T, self.nuc_neg_T = nuc_pos_T, nuc_neg_T
+        self.mag_pos_wfn, self.mag_neg_wfn = mag_pos_wfn, mag_neg_wfn
+        self.mag_pos_T, self.mag_neg_T = mag_pos_T, mag_neg_T
+        self.nuc_pert_strength, self.mag_pert_strength = nuc_pert_strength, mag_pert_strength
+        self.unperturbed_wfn, self.unperturbed_T = unperturbed_wfn, unperturbed_T
+        natom = len(nuc_pos_wfn) // 3
+        self.nbf, self.ndocc = wfn.nbf, wfn.ndocc
+        self.nfzc = wfn.H.basis_set.n_frozen_core()
+        self.parameters = parameters
+        so = parameters["method"] in SO_METHODS
+
+        def ovl(bb, Cb, kb, Ck):          # utils.compute_mo_overlap (+ compute_so_overlap), utils.py:370-422
+            S = mo_overlap_dev(Cb, provider_ao_overlap(bb, kb), Ck)
+            if so:
+                S = spin_block_2_dev(S)
+            return to_host(S)
+
+        U, Ub = self.unperturbed_wfn, unperturbed_basis
+        if parameters["method"] != "RHF":
+            self.overlap_uu = ovl(Ub, U, Ub, U)
+            self.overlap_up = [ovl(Ub, U, mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)]
+            self.overlap_un = [ovl(Ub, U, mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)]
+            self.overlap_pu = [ovl(nuc_pos_basis[a], nuc_pos_wfn[a], Ub, U) for a in range(3 * natom)]
+            self.overlap_nu = [ovl(nuc_neg_basis[a], nuc_neg_wfn[a], Ub, U) for a in range(3 * natom)]
+        n3 = 3 * natom
+        self.overlap_pp = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
+        self.overlap_pn = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
+        self.overlap_np = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
+        self.overlap_nn = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
+        self._cache = {}
+
+    @classmethod
+    def from_parts(cls, method, nbf, ndocc, nfzc, h_R, h_B, **parts):
+        """Build from precomputed overlaps / amplitude lists (what __init__ leaves on `self`);
+        used by tests and by the sharded driver, which computes overlaps rank-locally."""
+        self = cls.__new__(cls)
+        self.parameters = {"method": method}
+        self.nbf, self.ndocc, self.nfzc = nbf, ndocc, nfzc
+        self.nuc_pert_strength, self.mag_pert_strength = h_R, h_B
+        for k, v in parts.items():
+            setattr(self, k, v)
+        self._cache = {}
+        return self
+
+    # ---------------------------------------------------------------------------------------
+    # aats.py:120-130
+    def compute_SO_det(self, overlap, bra_indices, ket_indices):
+        nocc = 2 * self.ndocc
+        S = to_device(np.asarray(overlap), _C128)
+        nso = S.shape[0]
+        lists = []
+        for idx in (bra_indices, ket_indices):
+            out = np.zeros((1, nocc), dtype=np.int32)
+            sub, p = _i32_host(np.asarray(idx, dtype=np.int32).reshape(-1))
+            check(lib.apyib_so_index_lists(nso, nocc, p if len(idx) else None, 1, len(idx) // 2, _i32_host(out)[1]))
+            lists.append(torch.from_numpy(out).to(device()))
+        return complex(to_host(_det_outer(S, nocc, lists[0], lists[1]))[0, 0])
+
+    # ---------------------------------------------------------------------------------------
+    # aats.py:134-157
+    def compute_normalization(self, alpha, beta, normalization):
+        m = self.parameters["method"]
+        if m == "RHF" or normalization == "intermediate":
+            return 1, 1, 1, 1, 1
+        cisd = m == "CISD_SO"
+
+        def N(T):
+            t2 = to_device(np.asarray(T[2]), _C128)
+            x = T[0] ** 2 + 0.25 * _vdot(t2, t2)
+            if cisd:
+                t1 = to_device(np.asarray(T[1]), _C128)
+                x = x + _vdot(t1, t1)
+            return 1 / np.sqrt(x)
+
+        return (N(self.unperturbed_T), N(self.nuc_pos_T[alpha]), N(self.nuc_neg_T[alpha]),
+                N(self.mag_pos_T[beta]), N(self.mag_neg_T[beta]))
+
+    # ---------------------------------------------------------------------------------------
+    # aats.py:558-642
+    def compute_all_dets(self, overlap):
+        """All singly / doubly row- and/or column-substituted determinants of one MO overlap, in the
+        reference's nine return objects (materialised; use compute_spatial_aats for the fused path)."""
+        no, nf, nv = self.ndocc, self.nfzc, self.nbf - self.ndocc
+        o = no - nf
+        T = _Tables.get(no, nf, nv)
+        S = to_device(np.asarray(overlap), _C128)
+        R0, R1, R2 = T.L
+        d = lambda r, c: to_host(_det_outer(S, no, r, c))
+        det_S = complex(d(R0, R0)[0, 0])
+        si, sa = T.singles[:, 0] - nf, T.singles[:, 1]
+        di, da, dj, db = T.doubles[:, 0] - nf, T.doubles[:, 1], T.doubles[:, 2] - nf, T.doubles[:, 3]
+        z = lambda *s: np.zeros(s, dtype=np.complex128)
+        ia_S, S_kc = z(o, nv), z(o, nv)
+        iajb_S, S_kcld, ia_S_kc = z(o, nv, o, nv), z(o, nv, o, nv), z(o, nv, o, nv)
+        iajb_S_kc, ia_S_kcld = z(o, nv, o, nv, o, nv), z(o, nv, o, nv, o, nv)
+        iajb_S_kcld = z(*((o, nv) * 4))
+        if T.n1:
+            ia_S[si, sa] = d(R1, R0)[:, 0]
+            S_kc[si, sa] = d(R0, R1)[0, :]
+            ia_S_kc[si[:, None], sa[:, None], si[None, :], sa[None, :]] = d(R1, R1)
+        if T.n2:
+            iajb_S[di, da, dj, db] = d(R2, R0)[:, 0]
+            S_kcld[di, da, dj, db] = d(R0, R2)[0, :]
+            iajb_S_kc[di[:, None], da[:, None], dj[:, None], db[:, None], si[None, :], sa[None, :]] = d(R2, R1)
+            # stored [i][a][j][b][k][c] with COLUMNS (i,a),(j,b) and ROW (k,c) substituted (aats.py:604-606)
+            ia_S_kcld[di[None, :], da[None, :], dj[None, :], db[None, :], si[:, None], sa[:, None]] = d(R1, R2)
+            iajb_S_kcld[di[:, None], da[:, None], dj[:, None], db[:, None],
+                        di[None, :], da[None, :], dj[None, :], db[None, :]] = d(R2, R2)
+        a4 = lambda X: X - X.swapaxes(0, 2) - X.swapaxes(1, 3) + X.swapaxes(0, 2).swapaxes(1, 3)
+        iajb_S, S_kcld, iajb_S_kc, ia_S_kcld = a4(iajb_S), a4(S_kcld), a4(iajb_S_kc), a4(ia_S_kcld)
+        ia_S_kcld = ia_S_kcld.swapaxes(0, 4).swapaxes(1, 5).swapaxes(2, 4).swapaxes(3, 5)       # aats.py:629
+        X = a4(iajb_S_kcld)
+        iajb_S_kcld = X - X.swapaxes(4, 6) - X.swapaxes(5, 7) + X.swapaxes(4, 6).swapaxes(5, 7)  # aats.py:630
+        return det_S, ia_S, S_kc, iajb_S, S_kcld, ia_S_kc, iajb_S_kc, ia_S_kcld, iajb_S_kcld
+
+    # ---------------------------------------------------------------------------------------
+    # spatial route
+    # ---------------------------------------------------------------------------------------
+    def _spatial_norms(self, normalization):
+        """N, N_np[3N], N_nn[3N], N_mp[3], N_mn[3] of aats.py:652-669."""
+        key = ("norms", normalization)
+        if key in self._cache:
+            return self._cache[key]
+        m = self.parameters["method"]
+        n3 = len(self.nuc_pos_T)
+        if m == "RHF" or normalization == "intermediate":
+            res = (1, [1] * n3, [1] * n3, [1] * 3, [1] * 3)
+        else:
+            cisd = m == "CISD"
+
+            def N(T):
+                t2 = to_device(np.asarray(T[2]), _C128)
+                sw = zeros((1,), _C128)
+                contract("ijab,ijba->", t2, t2, sw.view(()), 1.0, 0.0, conj_a=True)
+                x = T[0] + (2 * _vdot(t2, t2) - complex(to_host(sw)[0]))
+                if cisd:
+                    t1 = to_device(np.asarray(T[1]), _C128)
+                    x = x + 2 * _vdot(t1, t1)
+                return 1 / np.sqrt(x)
+
+            res = (N(self.unperturbed_T), [N(T) for T in self.nuc_pos_T], [N(T) for T in self.nuc_neg_T],
+                   [N(T) for T in self.mag_pos_T], [N(T) for T in self.mag_neg_T])
+        self._cache[key] = res
+        return res
+
+    def _spatial_amps(self, normalization):
+        """Scaled amplitude combinations of aats.py:690-711 for ALL alpha / beta, on the device:
+        kets  Y_t (1), Y_dH (3);  bras X_c (1), X_dR (3N)."""
+        key = ("amps", normalization)
+        if key in self._cache:
+            return self._cache[key]
+        cisd = self.parameters["method"] == "CISD"
+        N, N_np, N_nn, N_mp, N_mn = self._spatial_norms(normalization)
+        n3 = len(self.nuc_pos_T)
+
+        def build(idx):
+            if idx == 1 and not cisd:
+                return None
+            T0 = to_device(np.asarray(self.unperturbed_T[idx]), _C128)
+            t = _axpby(N, T0, 0.0, torch.empty_like(T0))
+            tc = _axpby(np.conj(N), T0, 0.0, torch.empty_like(T0), conj_x=True)
+            dH, dR = [], []
+            for b in range(3):
+                x = _axpby(N_mp[b], to_device(np.asarray(self.mag_pos_T[b][idx]), _C128), 0.0, torch.empty_like(T0))
+                dH.append(_axpby(-N_mn[b], to_device(np.asarray(self.mag_neg_T[b][idx]), _C128), 1.0, x))
+            for a in range(n3):
+                x = _axpby(np.conj(N_np[a]), to_device(np.asarray(self.nuc_pos_T[a][idx]), _C128), 0.0,
+                           torch.empty_like(T0), conj_x=True)
+                dR.append(_axpby(-np.conj(N_nn[a]), to_device(np.asarray(self.nuc_neg_T[a][idx]), _C128), 1.0, x,
+                                 conj_x=True))
+            return dict(t=t[None], tc=tc[None], dH=torch.stack(dH), dR=torch.stack(dR))
+
+        res = {1: build(1), 2: build(2)}
+        self._cache[key] = res
+        return res
+
+    def _block(self, S_host, X1, X2, Y1, Y2):
+        """Contributions of ONE overlap matrix for nx bra and ny ket amplitude sets.
+        Returns dict of [nx, ny] numpy arrays (before the +/- sign and the N factors of S0/0S)."""
+        no, nf, nv = self.ndocc, self.nfzc, self.nbf - self.ndocc
+        o = no - nf
+        cisd = X1 is not None
+        T = _Tables.get(no, nf, nv)
+        R0, R1, R2 = T.L
+        S = to_device(np.asarray(S_host), _C128)
+        nx, ny = X2.shape[0], Y2.shape[0]
+        P = T.n2
+        dS = _det_outer(S, no, R0, R0)                                  # det_S
+        A = _det_outer(S, no, R1, R0).view(o, nv)                       # ia_S
+        B = _det_outer(S, no, R0, R1).view(o, nv)                       # S_kc
+        G = _det_outer(S, no, R1, R1).view(o, nv, o, nv)                # ia_S_kc
+        out = {}
+        cn = contract_new
+        if P:
+            D20 = _det_outer(S, no, R2, R0).view(1, P)                  # iajb_S  (restricted)
+            D02 = _det_outer(S, no, R0, R2).view(1, P)                  # S_kcld  (restricted)
+            Xh, Yh = empty((nx, P), _C128), empty((ny, P), _C128)
+            n2 = o * o * nv * nv
+            check(lib.apyib_pack_doubles(ptr(X2), n2, nx, o, nv, nf, ptr(T.doubles_dev), P, ptr(Xh), stream_ptr()))
+            check(lib.apyib_pack_doubles(ptr(Y2), n2, ny, o, nv, nf, ptr(T.doubles_dev), P, ptr(Yh), stream_ptr()))
+        wy = cn("qklcd,ld->qkc", Y2, B)                                 # sum_ld y2[k,l,c,d] S_ld
+        ux = cn("xijab,jb->xia", X2, A)                                 # sum_jb x2[i,j,a,b] jb_S
+        uxp = cn("xijab,ia->xjb", X2, A)                                # sum_ia x2[i,j,a,b] ia_S
+        T1 = cn("iakc,qklcd->qiald", G, Y2)
+        Z = cn("qiald,jbld->qiajb", T1, G)
+        dd = {"c6": cn("xijab,qiajb->xq", X2, Z)}
+        if P:
+            z22 = _det_matvec(S, no, R2, R2, Yh)                         # the P x P table, fused
+            ys = [wy.reshape(ny, -1)] + ([Y1.reshape(ny, -1)] if cisd else [])
+            z21 = _det_matvec(S, no, R2, R1, torch.cat(ys, 0))
+            z12 = _det_matvec(S, no, R1, R2, Yh)
+            dd["c1"] = cn("xr,qr->xq", Xh, z22)
+            dd["v1"] = cn("xr,qr->xq", Xh, D20)
+            dd["v2"] = cn("xr,qr->xq", D02, Yh)
+            dd["c3"] = cn("xr,qr->xq", Xh, z21[:ny])
+            uxs = _axpby(1.0, uxp, 1.0, ux.clone())                      # ux + ux' 
+            dd["c4"] = cn("xr,qr->xq", uxs.reshape(nx, -1), z12)
+        if cisd:
+            Gy1 = cn("iakc,qkc->qia", G, Y1)
+            Gwy = cn("iakc,qkc->qia", G, wy)
+            dd["s_xGy"] = cn("xia,qia->xq", X1, Gy1)
+            dd["s_xA"] = cn("xia,qia->xq", X1, A[None])
+            dd["s_yB"] = cn("xkc,qkc->xq", B[None], Y1)
+            dd["ds3"] = cn("xia,qia->xq", ux, Gy1)
+            dd["sd3"] = cn("xia,qia->xq", X1, Gwy)
+            dd["d0b"] = cn("xjb,qjb->xq", uxp, A[None])
+            dd["0db"] = cn("xkc,qkc->xq", B[None], wy)
+            if P:
+                dd["ds1"] = cn("xr,qr->xq", Xh, z21[ny:])
+                dd["sd1"] = cn("xr,qr->xq", X1.reshape(nx, -1), z12)
+        h = {k: to_host(v) for k, v in dd.items()}
+        dSh = complex(to_host(dS)[0, 0])
+        zero = np.zeros((nx, ny), dtype=np.complex128)
+        g = lambda k: h.get(k, zero)
+        v1, v2 = g("v1"), g("v2")                                        # [nx,1], [1,ny]
+        out["DD"] = 0.125 * (dSh * g("c1") + v1 * v2 + 4 * g("c3") + 2 * g("c4") + 8 * g("c6"))
+        if cisd:
+            xA, yB = g("s_xA"), g("s_yB")
+            out["SS"] = 2 * (dSh * g("s_xGy") + xA * yB)
+            out["DS"] = 0.5 * dSh * g("ds1") + 0.5 * v1 * yB + 2 * g("ds3")
+            out["SD"] = 0.5 * dSh * g("sd1") + 0.5 * xA * v2 + 2 * g("sd3")
+            out["S0"] = 2 * xA * dSh + zero
+            out["0S"] = 2 * yB * dSh + zero
+            out["D0"] = 0.5 * v1 * dSh + g("d0b") + zero
+            out["0D"] = 0.5 * v2 * dSh + g("0db") + zero
+        return out
+
+    def _spatial_terms(self, alpha, beta, normalization):
+        m = self.parameters["method"]
+        N, N_np, N_nn, N_mp, N_mn = self._spatial_norms(normalization)
+        no = self.ndocc
+        I = dict.fromkeys(("00", "0D", "D0", "DD", "0S", "S0", "SS", "SD", "DS"), 0)
+        R0 = _Tables.get(no, self.nfzc, self.nbf - no).L[0]
+
+        def d2(S):
+            return complex(to_host(_det_outer(to_device(np.asarray(S), _C128), no, R0, R0))[0, 0]) ** 2
+
+        a, b = alpha, beta
+        I["00"] = (d2(self.overlap_pp[a][b]) * N_np[a] * N_mp[b] - d2(self.overlap_pn[a][b]) * N_np[a] * N_mn[b]
+                   - d2(self.overlap_np[a][b]) * N_nn[a] * N_mp[b] + d2(self.overlap_nn[a][b]) * N_nn[a] * N_mn[b])
+        if m == "RHF":
+            return I
+        cisd = m == "CISD"
+        amps = self._spatial_amps(normalization)
+        A1, A2 = amps[1], amps[2]
+        pick = lambda Am, k: None if Am is None else Am[k]
+
+        def cached(name, S, bra, ket):
+            key = ("blk", name, normalization)
+            if key not in self._cache:
+                self._cache[key] = self._block(S, pick(A1, bra), A2[bra], pick(A1, ket), A2[ket])
+            return self._cache[key]
+
+        def add(res, sign, ix, iq, s0_N=None, os_N=None, d0=False, od=False):
+            I["DD"] += sign * res["DD"][ix, iq]
+            if cisd:
+                for k in ("SS", "DS", "SD"):
+                    I[k] += sign * res[k][ix, iq]
+                if s0_N is not None:
+                    I["S0"] += sign * res["S0"][ix, iq] * s0_N
+                if os_N is not None:
+                    I["0S"] += sign * res["0S"][ix, iq] * os_N
+                if d0:
+                    I["D0"] += sign * res["D0"][ix, iq]
+                if od:
+                    I["0D"] += sign * res["0D"][ix, iq]
+
+        add(cached("uu", self.overlap_uu, "dR", "dH"), +1, a, b)
+        add(cached(("up", b), self.overlap_up[b], "dR", "t"), +1, a, 0, s0_N=N_mp[b], d0=True)
+        add(cached(("un", b), self.overlap_un[b], "dR", "t"), -1, a, 0, s0_N=N_mn[b], d0=True)
+        add(cached(("pu", a), self.overlap_pu[a], "tc", "dH"), +1, 0, b, os_N=N_np[a], od=True)
+        add(cached(("nu", a), self.overlap_nu[a], "tc", "dH"), -1, 0, b, os_N=N_nn[a], od=True)
+        blk = lambda S: self._block(S, pick(A1, "tc"), A2["tc"], pick(A1, "t"), A2["t"])
+        add(blk(self.overlap_pp[a][b]), +1, 0, 0, s0_N=N_mp[b], os_N=N_np[a], d0=True, od=True)
+        add(blk(self.overlap_pn[a][b]), -1, 0, 0, s0_N=N_mn[b], os_N=N_np[a], d0=True, od=True)
+        add(blk(self.overlap_np[a][b]), -1, 0, 0, s0_N=N_mp[b], os_N=N_nn[a], d0=True, od=True)
+        add(blk(self.overlap_nn[a][b]), +1, 0, 0, s0_N=N_mn[b], os_N=N_nn[a], d0=True, od=True)
+        return I
+
+    def compute_spatial_aats(self, alpha, beta, normalization="full"):
+        """Reference: aats.py:646-1055.  Returns Im(I)/(4 h_R h_B) for one (alpha, beta)."""
+        t0 = time.time()
+        I = self._spatial_terms(alpha, beta, normalization)
+        tot = sum(I.values())
+        if config.VERBOSE:
+            print(f"AAT element computed in {time.time() - t0} seconds.")
+        return (1 / (4 * self.nuc_pert_strength * self.mag_pert_strength)) * np.imag(tot)
+
+    # ---------------------------------------------------------------------------------------
+    # spin-orbital brute-force route (aats.py:161-554)
+    # ---------------------------------------------------------------------------------------
+    def _so_lists(self):
+        key = ("solists",)
+        if key in self._cache:
+            return self._cache[key]
+        nocc, nso = 2 * self.ndocc, 2 * self.nbf
+        occ, vir = range(nocc), range(nocc, nso)
+        tup = {0: np.zeros((1, 0), dtype=np.int32),
+               1: np.array([(i, a) for i in occ for a in vir], dtype=np.int32).reshape(-1, 2),
+               2: np.array([(i, a, j, b) for i in occ for a in vir for j in occ for b in vir],
+                           dtype=np.int32).reshape(-1, 4)}
+        L = {}
+        for k, t in tup.items():
+            out = np.zeros((len(t), nocc), dtype=np.int32)
+            check(lib.apyib_so_index_lists(nso, nocc, _i32_host(t)[1] if k else None, len(t), k, _i32_host(out)[1]))
+            L[k] = torch.from_numpy(out).to(device())
+        self._cache[key] = L
+        return L
+
+    def _so_terms(self, alpha, beta, normalization):
+        m = self.parameters["method"]
+        cisd = m == "CISD_SO"
+        nocc = 2 * self.ndocc
+        N, N_np, N_nn, N_mp, N_mn = self.compute_normalization(alpha, beta, normalization)
+        L = self._so_lists()
+        dev = lambda S: to_device(np.asarray(S), _C128)
+        if m == "RHF":
+            sb = lambda S: spin_block_2_dev(dev(S))                      # aats.py:165-169 (not in place)
+        else:
+            sb = dev
+        a, b = alpha, beta
+        Spp, Spn, Snp, Snn = sb(self.overlap_pp[a][b]), sb(self.overlap_pn[a][b]), sb(self.overlap_np[a][b]), sb(self.overlap_nn[a][b])
+        one = to_device(np.ones((1, 1)), _C128)
+
+        def bil(S, bk, kk, X, Y):
+            """sum_{r,c} X[r] det(S[bra r, ket c]) Y[c]"""
+            Z = _det_matvec(S, nocc, L[bk], L[kk], Y.reshape(1, -1))
+            return complex(to_host(contract_new("xr,qr->xq", X.reshape(1, -1), Z))[0, 0])
+
+        def stencil(bk, kk, X, Y):
+            return (bil(Spp, bk, kk, X, Y) * N_np * N_mp - bil(Spn, bk, kk, X, Y) * N_np * N_mn
+                    - bil(Snp, bk, kk, X, Y) * N_nn * N_mp + bil(Snn, bk, kk, X, Y) * N_nn * N_mn)
+
+        I = dict.fromkeys(("00", "0D", "D0", "DD", "0S", "S0", "SS", "SD", "DS"), 0)
+        I["00"] = stencil(0, 0, one, one)
+        if m == "RHF":
+            return I
+        U, P_, Ng, Mp, Mn = self.unperturbed_T, self.nuc_pos_T[a], self.nuc_neg_T[a], self.mag_pos_T[b], self.mag_neg_T[b]
+
+        def amps(idx):
+            T0 = dev(U[idx])
+            tc = _axpby(1.0, T0, 0.0, torch.empty_like(T0), conj_x=True)
+            dH = _axpby(-1.0, dev(Mn[idx]), 1.0, dev(Mp[idx]).clone())
+            dR = _axpby(1.0, dev(P_[idx]), 0.0, torch.empty_like(T0), conj_x=True)
+            dR = _axpby(-1.0, dev(Ng[idx]), 1.0, dR, conj_x=True)
+            if idx == 2:   # loop order (i,a,j,b)   <- t2[i][j][a][b]
+                T0, tc, dH, dR = (x.permute(0, 2, 1, 3).contiguous() for x in (T0, tc, dH, dR))
+            return {0: None, "t": T0, "tc": tc, "dH": dH, "dR": dR}
+
+        A = {1: amps(1) if cisd else None, 2: amps(2)}
+        Suu, Sup, Sun = dev(self.overlap_uu), dev(self.overlap_up[b]), dev(self.overlap_un[b])
+        Spu, Snu = dev(self.overlap_pu[a]), dev(self.overlap_nu[a])
+
+        def term(bk, kk):
+            g = lambda k, name: one if k == 0 else A[k][name]
+            pref = (0.25 if bk == 2 else 1.0) * (0.25 if kk == 2 else 1.0)
+            tot = stencil(bk, kk, g(bk, "tc"), g(kk, "t"))
+            if bk and kk:
+                tot += bil(Suu, bk, kk, g(bk, "dR"), g(kk, "dH")) * N * N
+            if bk:
+                tot += (bil(Sup, bk, kk, g(bk, "dR"), g(kk, "t")) * N * N_mp
+                        - bil(Sun, bk, kk, g(bk, "dR"), g(kk, "t")) * N * N_mn)
+            if kk:
+                tot += (bil(Spu, bk, kk, g(bk, "tc"), g(kk, "dH")) * N_np * N
+                        - bil(Snu, bk, kk, g(bk, "tc"), g(kk, "dH")) * N_nn * N)
+            return pref * tot
+
+        I["0D"], I["D0"], I["DD"] = term(0, 2), term(2, 0), term(2, 2)
+        if cisd:
+            I["0S"], I["S0"], I["SS"], I["SD"], I["DS"] = term(0, 1), term(1, 0), term(1, 1), term(1, 2), term(2, 1)
+        return I
+
+    def _so_scaled(self, name, alpha, beta, normalization):
+        k = 1 / (4 * self.nuc_pert_strength * self.mag_pert_strength)
+        return k * np.imag(self._so_terms(alpha, beta, normalization)[name])
+
+    def compute_SO_I_00(self, alpha, beta, normalization): return self._so_scaled("00", alpha, beta, normalization)
+    def compute_SO_I_0D(self, alpha, beta, normalization): return self._so_scaled("0D", alpha, beta, normalization)
+    def compute_SO_I_D0(self, alpha, beta, normalization): return self._so_scaled("D0", alpha, beta, normalization)
+    def compute_SO_I_DD(self, alpha, beta, normalization): return self._so_scaled("DD", alpha, beta, normalization)
+    def compute_SO_I_0S(self, alpha, beta, normalization): return self._so_scaled("0S", alpha, beta, normalization)
+    def compute_SO_I_S0(self, alpha, beta, normalization): return self._so_scaled("S0", alpha, beta, normalization)
+    def compute_SO_I_SS(self, alpha, beta, normalization): return self._so_scaled("SS", alpha, beta, normalization)
+    def compute_SO_I_SD(self, alpha, beta, normalization): return self._so_scaled("SD", alpha, beta, normalization)
+    def compute_SO_I_DS(self, alpha, beta, normalization): return self._so_scaled("DS", alpha, beta, normalization)
+
+    def compute_SO_aats(self, alpha, beta, normalization="full"):
+        """Reference: aats.py:520-554."""
+        t0 = time.time()
+        I = self._so_terms(alpha, beta, normalization)
+        k = 1 / (4 * self.nuc_pert_strength * self.mag_pert_strength)
+        tot = sum(k * np.imag(x) for x in I.values())
+        if config.VERBOSE:
+            print(f"AAT element computed in {time.time() - t0} seconds.")
+        return tot

@@ -122,6 +122,24 @@ __global__ void __launch_bounds__(256) chunk_reduce_kernel(const cplx *Zp, int n
     }
 }
 
+// Antisymmetric completion folded into the amplitudes (aats.py:620-630 applied to the tensor
+// is equivalent to applying it to the amplitude that multiplies it):
+//   out[q*P + r] = sum over the 4 (i<->j, a<->b) images of (x - x.swapaxes(2,3))
+//               = 2 ( x[i,j,a,b] - x[i,j,b,a] - x[j,i,a,b] + x[j,i,b,a] ),  r = (i,a,j,b), i<j, a<b
+__global__ void __launch_bounds__(256)
+pack_doubles_kernel(const cplx *__restrict__ x, int64_t xstride, int nq, int o, int v, int nf,
+                    const int32_t *__restrict__ tab, int64_t P, cplx *__restrict__ out) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < P * nq;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx % P, q = idx / P;
+        const int i = tab[4 * r] - nf, a = tab[4 * r + 1], j = tab[4 * r + 2] - nf, b = tab[4 * r + 3];
+        const cplx *t = x + q * xstride;
+        auto at = [&](int p0, int p1, int p2, int p3) { return t[(((int64_t)p0 * o + p1) * v + p2) * v + p3]; };
+        const cplx s = at(i, j, a, b) - at(i, j, b, a) - at(j, i, a, b) + at(j, i, b, a);
+        out[idx] = make_cplx(2.0 * s.x, 2.0 * s.y);
+    }
+}
+
 template <bool OUTER>
 static int launch_det(int G, dim3 grid, cudaStream_t st, const cplx *S, int ns, int n, const int32_t *rows,
                       int64_t nrow, const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny,
@@ -205,6 +223,19 @@ extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d
     int64_t b = (len + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
     chunk_reduce_kernel<<<(unsigned)b, 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_pack_doubles(const void *d_x, int64_t x_stride, int nq, int o, int v, int nf,
+                                  const int32_t *d_doubles, int64_t P, void *d_out, void *stream) {
+    APYIB_REQUIRE(d_x && d_doubles && d_out, "null pointer");
+    APYIB_REQUIRE(nq >= 1 && o >= 0 && v >= 0 && nf >= 0, "sizes");
+    if (P == 0) return APYIB_OK;
+    int64_t b = (P * nq + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    pack_doubles_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>((const cplx *)d_x, x_stride, nq, o, v, nf,
+                                                                     d_doubles, P, (cplx *)d_out);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }

@@ -1,0 +1,112 @@
+"""compute_parallel_aats -- drop-in for apyib/parallel.py:16-48.
+
+The reference forks a 4-process multiprocessing.Pool over the (alpha, beta) tensor elements and
+solves all finite-difference points serially first.  Here the unit of parallelism is the GPU:
+
+  phase 1  the 6N+6 displaced / field points are partitioned over the ranks (one process per
+           GPU, torch.distributed); every rank runs full, independent solves (no collective);
+  exchange one all_gather_object of the per-point (C, T_list) blobs -- every AAT element
+           needs the amplitudes of the unperturbed, R+-alpha and B+-beta points;
+  phase 2  tensor rows alpha are partitioned over the ranks; each rank evaluates its rows with
+           the fused determinant kernels;
+  gather   final all-gather of the (3N, 3) float64 tensor (NCCL on GPUs, gloo in CPU tests).
+
+With world_size == 1 (or no process group) it degenerates to the single-GPU path.
+`num_processes` is accepted for signature compatibility and ignored.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import config
+from .aats import AAT
+from .energy import energy
+from .fin_diff import finite_difference, aat_points, point_cost
+from .hostchem import Hamiltonian, hf_wfn
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return None, 0, 1
+
+
+def partition(items, costs, world):
+    """Longest-processing-time static partition; deterministic, identical on every rank."""
+    order = sorted(range(len(items)), key=lambda i: (-costs[i], i))
+    load = [0.0] * world
+    owner = [0] * len(items)
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
+
+
+def compute_parallel_aats(parameters, nuc_pert_strength, mag_pert_strength, normalization='full', num_processes=4):
+    dist, rank, world = _dist()
+    E_list, T_list, C, basis = energy(parameters)
+    E_tot = E_list[0] + E_list[1] + E_list[2]
+    if config.VERBOSE and rank == 0:
+        print("Total Energy: ", E_tot)
+    H = Hamiltonian(parameters)
+    wfn = hf_wfn(H)
+    natom = H.molecule.natom()
+
+    fd = finite_difference(parameters, basis, C)
+    pts = aat_points(natom)
+    owner = partition(pts, [point_cost(p[0]) for p in pts], world)
+    mine = [p for p, o in zip(pts, owner) if o == rank]
+    lists = fd.compute_AAT(nuc_pert_strength, mag_pert_strength, points=mine)
+    if world > 1:
+        # exchange (C, T) of every point; basis handles are rebuilt locally (geometry only)
+        blob = {}
+        for p in mine:
+            i0 = 0 if p[2] > 0 else 1
+            grp = 0 if p[0] == "R" else 6
+            blob[p] = (lists[grp + i0][p[1]], lists[grp + 4 + i0][p[1]])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, blob)
+        lists = [list(x) for x in lists]
+        for part in gathered:
+            for p, (Cp, Tp) in part.items():
+                i0 = 0 if p[2] > 0 else 1
+                grp = 0 if p[0] == "R" else 6
+                lists[grp + i0][p[1]] = Cp
+                lists[grp + 4 + i0][p[1]] = Tp
+        for p in pts:                      # basis handles for points solved elsewhere
+            i0 = 0 if p[2] > 0 else 1
+            grp = 0 if p[0] == "R" else 6
+            if lists[grp + 2 + i0][p[1]] is None:
+                if p[0] == "R":
+                    fd.parameters["geom"] = fd._displaced([(p[1], p[2] * nuc_pert_strength)])
+                    lists[grp + 2 + i0][p[1]] = Hamiltonian(fd.parameters).basis_set
+                    fd._reset()
+                else:
+                    lists[grp + 2 + i0][p[1]] = basis
+    (nuc_pos_C, nuc_neg_C, nuc_pos_basis, nuc_neg_basis, nuc_pos_T, nuc_neg_T,
+     mag_pos_C, mag_neg_C, mag_pos_basis, mag_neg_basis, mag_pos_T, mag_neg_T) = lists
+
+    AATs = AAT(parameters, wfn, C, basis, T_list, nuc_pos_C, nuc_neg_C, nuc_pos_basis, nuc_neg_basis, nuc_pos_T,
+               nuc_neg_T, mag_pos_C, mag_neg_C, mag_pos_basis, mag_neg_basis, mag_pos_T, mag_neg_T,
+               nuc_pert_strength, mag_pert_strength)
+    spatial = parameters['method'] in ('RHF', 'MP2', 'CID', 'CISD')
+    fn = AATs.compute_spatial_aats if spatial else AATs.compute_SO_aats
+    rows = [a for a in range(3 * natom) if a % world == rank]
+    I = np.zeros((3 * natom, 3))
+    for a in rows:
+        for b in range(3):
+            I[a, b] = fn(a, b, normalization)
+    if world > 1:
+        import torch
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(I).to(dev)
+        dist.all_reduce(t)                 # rows are disjoint -> sum == gather of the (3N,3) tensor
+        I = t.cpu().numpy()
+    if config.VERBOSE and rank == 0:
+        print(I, "\n")
+    return I

@@ -180,6 +180,14 @@ int apyib_det_matvec(const void *d_S, int ns, int n,
                      const void *d_Y, int ny, void *d_Z, void *d_work, void *stream);
 int64_t apyib_det_matvec_work_len(int64_t nrow, int64_t ncol, int ny, int n);
 
+/* Restricted-pair packing of doubles amplitudes, complex128 only:
+ *   out[q*P + r] = 2 (x_q[i,j,a,b] - x_q[i,j,b,a] - x_q[j,i,a,b] + x_q[j,i,b,a]),  r = (i,a,j,b)
+ * for the P rows of the doubles enumeration (apyib_det_enumeration; i,j carry the frozen-core
+ * offset nf).  This is `t - t.swapaxes(2,3)` (aats.py:732 etc.) summed over the four images
+ * that the antisymmetric completion of the determinant tensors (aats.py:620-630) generates.   */
+int apyib_pack_doubles(const void *d_x, int64_t x_stride, int nq, int o, int v, int nf,
+                       const int32_t *d_doubles, int64_t P, void *d_out, void *stream);
+
 /* Host-side, bit-exact index tables ---------------------------------------------
  * get_slices (utils.py:184-213): bounds[0..7] = C_list f,o,v,t (start,stop pairs
  * flattened f0,f1,o0,o1,...) ; bounds[8..15] = I_list.                               */

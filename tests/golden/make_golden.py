@@ -1,0 +1,165 @@
+"""Generates the committed golden fixtures.  Runs ONLY in the build container (needs
+/root/reference); the GPU box and the CPU test-suite read the committed outputs.
+
+  python tests/golden/make_golden.py
+
+(A) reference_literals.json -- the hard-coded known-answer values of the reference's own tests
+    for its (H2)_2 molecule (tests/test_008_CISD_SO.py, test_011_AAT.py, test_012_AAT_SO.py,
+    test_013_AAT_parallel.py), extracted from the test sources with `ast` (numbers are data;
+    no reference code is copied).  Everything else in the reference's test-suite needs p/d
+    functions and therefore a real Psi4.
+(B) synthetic_*.npz -- outputs of the UNMODIFIED reference classes (stub-imported through
+    oracle/ref_harness.py) on the seeded synthetic inputs of oracle.apyib_oracle, for the
+    solvers, compute_all_dets, compute_spatial_aats and compute_SO_aats.
+"""
+from __future__ import annotations
+
+import ast
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import apyib_oracle as orc, ref_harness   # noqa: E402
+
+REF_TESTS = "/root/reference/apyib/tests"
+
+
+def quiet(f, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f(*a, **k)
+
+
+# ---------------------------------------------------------------------------------------------
+def extract_literals():
+    cases = []
+    for fname in ("test_008_CISD_SO.py", "test_011_AAT.py", "test_012_AAT_SO.py", "test_013_AAT_parallel.py"):
+        src = open(os.path.join(REF_TESTS, fname)).read()
+        tree = ast.parse(src)
+        for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+            seg = ast.get_source_segment(src, fn)
+            if '(H2)_2' not in seg:
+                continue
+            case = {"file": fname, "test": fn.name, "line": fn.lineno, "arrays": {}, "skipped_in_reference":
+                    any("skip" in ast.unparse(d) for d in fn.decorator_list)}
+            env = {"np": np}
+            for node in ast.walk(fn):
+                if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name):
+                    name = node.targets[0].id
+                    if name == "parameters" and isinstance(node.value, ast.Dict):
+                        for k, v in zip(node.value.keys, node.value.values):
+                            key = ast.literal_eval(k)
+                            if key != "geom":
+                                case.setdefault("parameters", {})[key] = ast.literal_eval(v)
+                    elif name.endswith("_ref") or name in ("psi4_CISD",):
+                        try:
+                            val = eval(compile(ast.Expression(node.value), "<lit>", "eval"), env)
+                        except Exception:
+                            continue
+                        env[name] = val
+                        case["arrays"][name] = np.asarray(val).tolist()
+                if isinstance(node, ast.Call):
+                    f = node.func
+                    attr = f.attr if isinstance(f, ast.Attribute) else getattr(f, "id", "")
+                    if attr in ("compute_parallel_aats", "compute_AAT"):
+                        nums = [ast.literal_eval(a) for a in node.args if isinstance(a, ast.Constant)]
+                        if len(nums) >= 2:
+                            case["h_R"], case["h_B"] = nums[-2], nums[-1]
+                        if attr == "compute_parallel_aats":
+                            case["route"] = "parallel"
+                    if attr in ("compute_parallel_aats", "compute_spatial_aats", "compute_SO_aats"):
+                        case.setdefault("normalization", "full")
+                        for kw in node.keywords:
+                            if kw.arg == "normalization":
+                                case["normalization"] = ast.literal_eval(kw.value)
+                        if attr != "compute_parallel_aats":
+                            case["route"] = attr
+            cases.append(case)
+    geom = None
+    src = open("/root/reference/apyib/data/molecules.py").read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "H2_2":
+            geom = ast.literal_eval(node.value)
+    return {"molecule": "(H2)_2", "geom": geom, "source": "apyib/data/molecules.py:46-55", "cases": cases}
+
+
+# ---------------------------------------------------------------------------------------------
+def par(method, fc=False, maxit=120, diis=True, conv=1e-12):
+    return {"method": method, "freeze_core": fc, "DIIS": diis, "max_iterations": maxit,
+            "e_convergence": conv, "d_convergence": conv}
+
+
+SOLVER_CASES = [  # name, nbf, ndocc, nfzc, complex, seed
+    ("r7", 7, 3, 0, False, 11), ("c7fc", 7, 3, 1, True, 12), ("c6", 6, 2, 0, True, 13), ("r8fc", 8, 3, 1, False, 14),
+]
+AAT_SPATIAL = [("MP2", 5, 2, 0, 101), ("CID", 6, 3, 1, 102), ("CISD", 5, 2, 0, 103), ("CISD", 6, 3, 1, 104),
+               ("RHF", 5, 2, 0, 105)]
+AAT_SO = [("MP2_SO", 3, 1, 0, 201), ("CISD_SO", 3, 1, 0, 202), ("CID_SO", 4, 1, 0, 203), ("RHF", 3, 1, 0, 204)]
+
+
+def synthetic(ns):
+    out = {}
+    for name, nbf, no, nf, cplx, seed in SOLVER_CASES:
+        w = orc.rotated_wfn(nbf, no, seed, cplx, nf)
+        for m in ("MP2", "MP2_SO"):
+            r = ns.mp2_wfn.mp2_wfn(par(m, nf > 0), w)
+            E, t2 = r.solve_MP2() if m == "MP2" else r.solve_MP2_SO()
+            out["%s/%s/E" % (name, m)], out["%s/%s/t2" % (name, m)] = np.asarray(E), t2
+        for m in ("CID", "CID_SO", "CISD", "CISD_SO"):
+            r = ns.ci_wfn.ci_wfn(par(m, nf > 0), w)
+            res = quiet(getattr(r, "solve_" + m))
+            for k, v in zip(("E", "t1", "t2") if len(res) == 3 else ("E", "t2"), res):
+                out["%s/%s/%s" % (name, m, k)] = np.asarray(v)
+            # fixed 4 iterations, no early exit, DIIS on: pins the iteration path itself
+            r = ns.ci_wfn.ci_wfn(par(m, nf > 0, maxit=4, conv=0.0), w)
+            res = quiet(getattr(r, "solve_" + m))
+            out["%s/%s/E_it4" % (name, m)] = np.asarray(res[0])
+            out["%s/%s/t2_it4" % (name, m)] = np.asarray(res[-1])
+        r = ns.ci_wfn.ci_wfn(par("CISD", nf > 0), w)
+        out["%s/F_MO" % name], out["%s/ERI_MO" % name] = r.F_MO, r.ERI_MO
+    np.savez_compressed(os.path.join(HERE, "synthetic_solvers.npz"), **out)
+
+    out = {}
+    for (nbf, no, nf, seed) in ((5, 2, 0, 301), (6, 3, 1, 302), (7, 3, 0, 303)):
+        A = orc.synthetic_aat_inputs("CISD", nbf, no, nf, 1, seed, h=1e-2)
+        R = ref_harness.make_ref_aat(ns, A)
+        res = R.compute_all_dets(A.overlap_pp[1][2])
+        for k, v in enumerate(res):
+            out["dets_%d_%d_%d/%d" % (nbf, no, nf, k)] = np.asarray(v)
+    for method, nbf, no, nf, seed in AAT_SPATIAL:
+        for norm in ("full", "intermediate"):
+            A = orc.synthetic_aat_inputs(method, nbf, no, nf, 1, seed, h=1e-3)
+            R = ref_harness.make_ref_aat(ns, A)
+            vals = [[quiet(R.compute_spatial_aats, a, b, norm) for b in range(3)] for a in range(3)]
+            out["spatial/%s_%d_%d_%d_%s" % (method, nbf, no, nf, norm)] = np.array(vals)
+    for method, nbf, no, nf, seed in AAT_SO:
+        for norm in ("full", "intermediate"):
+            vals = []
+            for (a, b) in ((0, 0), (1, 2), (2, 1)):
+                A = orc.synthetic_aat_inputs(method, nbf, no, nf, 1, seed, h=1e-3)   # RHF route mutates overlaps
+                R = ref_harness.make_ref_aat(ns, A)
+                vals.append(quiet(R.compute_SO_aats, a, b, norm))
+            out["so/%s_%d_%d_%d_%s" % (method, nbf, no, nf, norm)] = np.array(vals)
+    S = orc.synthetic_aat_inputs("CISD_SO", 4, 2, 0, 1, 401, h=0.2).overlap_uu
+    R = ref_harness.make_ref_aat(ns, orc.synthetic_aat_inputs("CISD_SO", 4, 2, 0, 1, 401, h=0.2))
+    idx = [([], []), ([0, 5], []), ([], [1, 6]), ([0, 4, 1, 5], [2, 6]), ([0, 4, 0, 5], [1, 7, 3, 7]), ([2, 6, 3, 6], [0, 4, 1, 5])]
+    out["so_det/S"] = S
+    out["so_det/vals"] = np.array([R.compute_SO_det(S, b, k) for b, k in idx])
+    out["so_det/idx"] = np.array([json.dumps(x) for x in idx])
+    np.savez_compressed(os.path.join(HERE, "synthetic_aat.npz"), **out)
+
+
+if __name__ == "__main__":
+    lit = extract_literals()
+    json.dump(lit, open(os.path.join(HERE, "reference_literals.json"), "w"), indent=1)
+    print("literals:", [(c["test"], sorted(c["arrays"])) for c in lit["cases"]])
+    ns = ref_harness.load()
+    synthetic(ns)
+    print("wrote", sorted(os.listdir(HERE)))

@@ -1,0 +1,113 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    from apyib_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "apyib_b200.h")).read()
+    declared = set(re.findall(r"\b(apyib_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(_lib.lib, name), "libapyib_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.lib.apyib_version() == 100
+
+
+def test_get_slices_bit_exact_vs_oracle():
+    from oracle import apyib_oracle as orc
+    from apyib_b200 import utils
+    for nbf, no, nf in ((7, 5, 0), (7, 5, 1), (22, 9, 2), (86, 16, 4)):
+        w = orc.Wfn(np.eye(nbf), np.arange(nbf, dtype=float), no, np.eye(nbf), np.eye(nbf), np.zeros((1,) * 4), nfzc=nf)
+        for m in ("RHF", "MP2", "CID", "CISD", "MP2_SO", "CID_SO", "CISD_SO"):
+            assert utils.get_slices({"method": m}, w) == tuple(orc.get_slices({"method": m}, w))
+    with pytest.raises(ValueError):
+        utils.get_slices({"method": "CCSD"}, w)
+
+
+def test_det_enumeration_and_index_lists_bit_exact():
+    from oracle import apyib_oracle as orc
+    from apyib_b200._lib import lib, check
+    for no, nf, nv in ((2, 0, 2), (3, 1, 3), (5, 0, 2), (9, 2, 13), (4, 0, 1), (1, 0, 3)):
+        ns, nd = C.c_int64(), C.c_int64()
+        check(lib.apyib_det_enumeration(no, nf, nv, None, C.byref(ns), None, C.byref(nd)))
+        s = np.zeros((ns.value, 2), dtype=np.int32)
+        d = np.zeros((nd.value, 4), dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        check(lib.apyib_det_enumeration(no, nf, nv, p(s), None, p(d), None))
+        so, do = orc.det_index_tables(no, nf, nv)
+        assert np.array_equal(s, so) and np.array_equal(d, do)
+        if nd.value:
+            out = np.zeros((nd.value, no), dtype=np.int32)
+            check(lib.apyib_det_index_lists(no, p(d), nd.value, 2, p(out)))
+            want = np.tile(np.arange(no, dtype=np.int32), (nd.value, 1))
+            want[np.arange(nd.value), d[:, 0]] = d[:, 1] + no
+            want[np.arange(nd.value), d[:, 2]] = d[:, 3] + no
+            assert np.array_equal(out, want)
+
+
+def test_so_index_lists_sequential_swaps():
+    from oracle import apyib_oracle as orc
+    from apyib_b200._lib import lib, check
+    nso, nocc = 8, 4
+    tuples = np.array([(i, a, j, b) for i in range(nocc) for a in range(nocc, nso) for j in range(nocc)
+                       for b in range(nocc, nso)], dtype=np.int32)
+    out = np.zeros((len(tuples), nocc), dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    check(lib.apyib_so_index_lists(nso, nocc, p(tuples), len(tuples), 2, p(out)))
+    want = np.array([orc._swap_perm(nso, t)[:nocc] for t in tuples])
+    assert np.array_equal(out, want)
+
+
+def test_argument_errors_are_reported_not_crashed():
+    from apyib_b200._lib import lib
+    rc = lib.apyib_det_outer(None, 4, 40, None, 1, None, 1, None, None)
+    assert rc < 0 and b"null" in lib.apyib_last_error()
+    b = (C.c_int32 * 16)()
+    assert lib.apyib_get_slices(3, 5, 0, 0, b) < 0
+
+
+def test_geometry_round_trip_and_units():
+    from apyib_b200.hostchem import Molecule, BOHR2ANG
+    g = "O 0.0 0.1 0.2\nH 1.0 0.0 -0.5\nno_com\nunits bohr\n"
+    m = Molecule.from_string(g)
+    assert m.natom() == 2 and m.true_atomic_number(0) == 8
+    m2 = Molecule.from_string(m.create_psi4_string_from_molecule())
+    assert np.array_equal(m.geometry(), m2.geometry())
+    a = Molecule.from_string("H 0 0 0\nH 0 0 %r\n" % BOHR2ANG)
+    assert abs(a.geometry()[1, 2] - 1.0) < 1e-14
+
+
+def test_partition_is_balanced_and_deterministic():
+    from apyib_b200.parallel import partition
+    from apyib_b200.fin_diff import aat_points, point_cost
+    pts = aat_points(10)
+    assert len(pts) == 66
+    costs = [point_cost(p[0]) for p in pts]
+    for world in (1, 2, 4, 8):
+        own = partition(pts, costs, world)
+        assert own == partition(pts, costs, world)
+        loads = [sum(c for c, o in zip(costs, own) if o == r) for r in range(world)]
+        assert max(loads) - min(loads) <= 4.0
+        assert sorted(set(own)) == list(range(world))
+
+
+def test_synthetic_provider_is_hermitian_and_smooth():
+    from apyib_b200 import hostchem as hc
+    prov = hc.SyntheticProvider(6, 2, 2, seed=3)
+    p = {"geom": prov.geometry_string(), "basis": "synthetic", "method": "CISD", "freeze_core": False,
+         "F_el": [0.0] * 3, "F_mag": [0.0, 1e-3, 0.0], "provider": prov, "DIIS": True, "max_iterations": 50,
+         "e_convergence": 1e-12, "d_convergence": 1e-12}
+    H = hc.Hamiltonian(p)
+    h = H.T + H.V
+    assert np.abs(h - h.conj().T).max() < 1e-15 and np.iscomplexobj(h)
+    w = hc.hf_wfn(H)
+    E, Cm = w.solve_SCF(p)
+    assert abs(np.imag(E)) < 1e-12
+    assert np.abs(Cm.conj().T @ H.S @ Cm - np.eye(6)).max() < 1e-12

@@ -1,0 +1,133 @@
+"""CPU: pins the oracle (numpy restatement) to (A) outputs of the UNMODIFIED reference on the
+seeded synthetic inputs (tests/golden/synthetic_*.npz, made by make_golden.py) and (B) the
+hard-coded known-answer values of the reference's own tests for its (H2)_2 molecule
+(tests/golden/reference_literals.json)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import apyib_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOLV = np.load(os.path.join(HERE, "golden", "synthetic_solvers.npz"))
+AATG = np.load(os.path.join(HERE, "golden", "synthetic_aat.npz"))
+LIT = json.load(open(os.path.join(HERE, "golden", "reference_literals.json")))
+
+from golden.make_golden import SOLVER_CASES, AAT_SPATIAL, AAT_SO, par   # noqa: E402
+
+
+@pytest.mark.parametrize("name,nbf,no,nf,cplx,seed", SOLVER_CASES)
+def test_solvers_match_reference_outputs(name, nbf, no, nf, cplx, seed):
+    w = orc.rotated_wfn(nbf, no, seed, cplx, nf)
+    ci = orc._CI(par("CISD", nf > 0), w)
+    assert np.abs(ci.F_MO - SOLV[name + "/F_MO"]).max() < 1e-13
+    assert np.abs(ci.ERI_MO - SOLV[name + "/ERI_MO"]).max() < 1e-14
+    for m in ("MP2", "MP2_SO"):
+        E, t2 = getattr(orc, "solve_" + m)(par(m, nf > 0), w)
+        assert abs(E - SOLV["%s/%s/E" % (name, m)]) < 1e-14
+        assert np.abs(t2 - SOLV["%s/%s/t2" % (name, m)]).max() < 1e-14
+    for m in ("CID", "CID_SO", "CISD", "CISD_SO"):
+        res = getattr(orc, "solve_" + m)(par(m, nf > 0), w)
+        assert abs(res[0] - SOLV["%s/%s/E" % (name, m)]) < 1e-13
+        assert np.abs(res[-1] - SOLV["%s/%s/t2" % (name, m)]).max() < 1e-13
+        if len(res) == 3:
+            assert np.abs(res[1] - SOLV["%s/%s/t1" % (name, m)]).max() < 1e-13
+        res = getattr(orc, "solve_" + m)(par(m, nf > 0, maxit=4, conv=0.0), w)
+        assert abs(res[0] - SOLV["%s/%s/E_it4" % (name, m)]) < 1e-13
+        assert np.abs(res[-1] - SOLV["%s/%s/t2_it4" % (name, m)]).max() < 1e-13
+
+
+@pytest.mark.parametrize("nbf,no,nf,seed", [(5, 2, 0, 301), (6, 3, 1, 302), (7, 3, 0, 303)])
+def test_compute_all_dets_bit_exact_layout(nbf, no, nf, seed):
+    A = orc.synthetic_aat_inputs("CISD", nbf, no, nf, 1, seed, h=1e-2)
+    res = orc.compute_all_dets(A.overlap_pp[1][2], no, nf, nbf)
+    for k, v in enumerate(res):
+        g = AATG["dets_%d_%d_%d/%d" % (nbf, no, nf, k)]
+        assert np.asarray(v).shape == g.shape
+        assert np.abs(np.asarray(v) - g).max() < 1e-14
+        assert np.array_equal(np.asarray(v) == 0, g == 0), "zero pattern (index tables) must be identical"
+
+
+@pytest.mark.parametrize("method,nbf,no,nf,seed", AAT_SPATIAL)
+@pytest.mark.parametrize("norm", ["full", "intermediate"])
+def test_spatial_aat_matches_reference_outputs(method, nbf, no, nf, seed, norm):
+    A = orc.synthetic_aat_inputs(method, nbf, no, nf, 1, seed, h=1e-3)
+    got = np.array([[orc.compute_spatial_aats(A, a, b, norm) for b in range(3)] for a in range(3)])
+    want = AATG["spatial/%s_%d_%d_%d_%s" % (method, nbf, no, nf, norm)]
+    assert np.abs(got - want).max() < 1e-9 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("method,nbf,no,nf,seed", AAT_SO)
+@pytest.mark.parametrize("norm", ["full", "intermediate"])
+def test_so_aat_matches_reference_outputs(method, nbf, no, nf, seed, norm):
+    A = orc.synthetic_aat_inputs(method, nbf, no, nf, 1, seed, h=1e-3)
+    got = np.array([orc.compute_SO_aats(A, a, b, norm) for (a, b) in ((0, 0), (1, 2), (2, 1))])
+    want = AATG["so/%s_%d_%d_%d_%s" % (method, nbf, no, nf, norm)]
+    assert np.abs(got - want).max() < 1e-9 * max(1.0, np.abs(want).max())
+
+
+def test_so_det_sequential_swap_semantics():
+    S = AATG["so_det/S"]
+    for js, want in zip(AATG["so_det/idx"], AATG["so_det/vals"]):
+        bra, ket = json.loads(str(js))
+        assert abs(orc.compute_SO_det(S, 4, bra, ket) - want) < 1e-14
+
+
+def test_get_slices_tables():
+    w = orc.synthetic_wfn(9, 4, 1, nfzc=1)
+    C, I = orc.get_slices({"method": "CISD"}, w)
+    assert C == [slice(0, 1), slice(1, 4), slice(4, 9), slice(1, 9)]
+    assert I == [slice(0, 1), slice(0, 3), slice(3, 8), slice(0, 8)]
+    C, I = orc.get_slices({"method": "CISD_SO"}, w)
+    assert I == [slice(0, 2), slice(0, 6), slice(6, 16), slice(0, 16)]
+
+
+# ---- (B) the reference's own known-answer values for (H2)_2 ---------------------------------
+def _energy_case():
+    return [c for c in LIT["cases"] if "psi4_CISD" in c["arrays"]][0]
+
+
+def test_h2_2_cisd_energy_literal():
+    """apyib/tests/test_008_CISD_SO.py:107-130: E_tot = -2.2165136315314133 (1e-11)"""
+    from oracle import fd_pipeline as fp
+    c = _energy_case()
+    for method in ("CISD_SO", "CISD"):
+        p = dict(c["parameters"], geom=LIT["geom"], method=method)
+        E_list = fp.energy(p)[0]
+        assert abs(E_list[0] + E_list[1] + E_list[2] - c["arrays"]["psi4_CISD"]) < 1e-11
+
+
+AAT_CASES = [c for c in LIT["cases"] if "h_R" in c]
+
+
+def _fast(c):
+    return c["parameters"]["method"] in ("MP2", "CISD")
+
+
+@pytest.mark.parametrize("c", [c for c in AAT_CASES if _fast(c)], ids=lambda c: c["file"][5:8] + "-" + c["test"])
+def test_h2_2_aat_literals_spatial(c):
+    _check_aat_case(c)
+
+
+@pytest.mark.parametrize("c", [c for c in AAT_CASES if not _fast(c) and c["file"].startswith("test_013")],
+                         ids=lambda c: c["file"][5:8] + "-" + c["test"])
+def test_h2_2_aat_literals_spin_orbital(c):
+    _check_aat_case(c)
+
+
+def _check_aat_case(c):
+    from oracle import fd_pipeline as fp
+    p = dict(c["parameters"], geom=LIT["geom"], F_el=[0.0] * 3, F_mag=[0.0] * 3)
+    I, T = fp.compute_parallel_aats(p, c["h_R"], c["h_B"], c["normalization"], terms=True)
+    tol = 1e-8 if "mp2" in c["test"] and c["file"].startswith("test_013") and "SO" not in c["test"] else 1e-7
+    assert np.abs(I - np.array(c["arrays"]["aat_ref"])).max() < tol
+    if p["method"].endswith("_SO"):        # the SO route evaluates every term -> term-resolved check
+        for k in ("00", "0D", "D0", "DD"):
+            if "I_%s_ref" % k in c["arrays"]:
+                assert np.abs(T[k] - np.array(c["arrays"]["I_%s_ref" % k])).max() < 1e-8
+    else:
+        for k in ("00", "DD"):
+            if "I_%s_ref" % k in c["arrays"]:
+                assert np.abs(T[k] - np.array(c["arrays"]["I_%s_ref" % k])).max() < 1e-8
