@@ -75,6 +75,41 @@ def _load():
 
 lib = _load()
 
+# ---- launch accounting (bench.py reports `gpu_launches`) -------------------------------------
+# kernels launched per C-ABI call; everything not listed launches nothing on the device
+_KERNELS_PER_CALL = {
+    "apyib_contract": 1, "apyib_gather4": 1, "apyib_gather2": 1, "apyib_mp2_t2_energy": 1, "apyib_ci_update": 1,
+    "apyib_symmetrize_ijab": 1, "apyib_dots": 1, "apyib_diis_push": 1, "apyib_diis_solve": 1,
+    "apyib_lincomb_energy_rms": 1, "apyib_iter_advance": 1, "apyib_copy": 1, "apyib_axpby": 1,
+    "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_pack_doubles": 1,
+}
+LAUNCHES = [0]
+
+
+class _Counted:
+    __slots__ = ("fn", "n")
+
+    def __init__(self, fn, n):
+        self.fn, self.n = fn, n
+
+    def __call__(self, *a):
+        LAUNCHES[0] += self.n
+        return self.fn(*a)
+
+
+class _Lib:
+    """Thin proxy over the CDLL that counts kernel launches."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name in SIGNATURES:
+            fn = getattr(cdll, name)
+            n = _KERNELS_PER_CALL.get(name, 0)
+            setattr(self, name, _Counted(fn, n) if n else fn)
+
+
+lib = _Lib(lib)
+
 
 def check(rc):
     if rc != 0:

@@ -83,13 +83,17 @@ def _det_matvec(S, n, rows, cols, Y):
     for q0 in range(0, nq, 4):
         q1 = min(nq, q0 + 4)
         work = empty((int(lib.apyib_det_matvec_work_len(nrow, ncol, q1 - q0, n)),), _C128)
-        check(lib.apyib_det_matvec(ptr(S), S.shape[0], n, ptr(rows), nrow, ptr(cols), ncol, ptr(Y[q0:q1]), q1 - q0,
-                                   ptr(Z[q0:q1]), ptr(work), stream_ptr()))
+        with config.timed("det_matvec[n=%d,%dx%d]" % (n, nrow, ncol)):
+            check(lib.apyib_det_matvec(ptr(S), S.shape[0], n, ptr(rows), nrow, ptr(cols), ncol, ptr(Y[q0:q1]),
+                                       q1 - q0, ptr(Z[q0:q1]), ptr(work), stream_ptr()))
     return Z
 
 
-def _stack(ts):
-    return torch.stack([to_device(np.asarray(t), _C128) for t in ts])
+def _dev(x):
+    """numpy array / python scalar / CUDA tensor -> complex128 CUDA tensor"""
+    if isinstance(x, torch.Tensor):
+        return to_device(x, _C128)
+    return to_device(np.asarray(x), _C128)
 
 
 def _axpby(alpha, x, beta, y, conj_x=False):
@@ -181,10 +185,10 @@ class AAT(object):
         cisd = m == "CISD_SO"
 
         def N(T):
-            t2 = to_device(np.asarray(T[2]), _C128)
+            t2 = _dev(T[2])
             x = T[0] ** 2 + 0.25 * _vdot(t2, t2)
             if cisd:
-                t1 = to_device(np.asarray(T[1]), _C128)
+                t1 = _dev(T[1])
                 x = x + _vdot(t1, t1)
             return 1 / np.sqrt(x)
 
@@ -245,12 +249,12 @@ class AAT(object):
             cisd = m == "CISD"
 
             def N(T):
-                t2 = to_device(np.asarray(T[2]), _C128)
+                t2 = _dev(T[2])
                 sw = zeros((1,), _C128)
                 contract("ijab,ijba->", t2, t2, sw.view(()), 1.0, 0.0, conj_a=True)
                 x = T[0] + (2 * _vdot(t2, t2) - complex(to_host(sw)[0]))
                 if cisd:
-                    t1 = to_device(np.asarray(T[1]), _C128)
+                    t1 = _dev(T[1])
                     x = x + 2 * _vdot(t1, t1)
                 return 1 / np.sqrt(x)
 
@@ -272,17 +276,17 @@ class AAT(object):
         def build(idx):
             if idx == 1 and not cisd:
                 return None
-            T0 = to_device(np.asarray(self.unperturbed_T[idx]), _C128)
+            T0 = _dev(self.unperturbed_T[idx])
             t = _axpby(N, T0, 0.0, torch.empty_like(T0))
             tc = _axpby(np.conj(N), T0, 0.0, torch.empty_like(T0), conj_x=True)
             dH, dR = [], []
             for b in range(3):
-                x = _axpby(N_mp[b], to_device(np.asarray(self.mag_pos_T[b][idx]), _C128), 0.0, torch.empty_like(T0))
-                dH.append(_axpby(-N_mn[b], to_device(np.asarray(self.mag_neg_T[b][idx]), _C128), 1.0, x))
+                x = _axpby(N_mp[b], _dev(self.mag_pos_T[b][idx]), 0.0, torch.empty_like(T0))
+                dH.append(_axpby(-N_mn[b], _dev(self.mag_neg_T[b][idx]), 1.0, x))
             for a in range(n3):
-                x = _axpby(np.conj(N_np[a]), to_device(np.asarray(self.nuc_pos_T[a][idx]), _C128), 0.0,
+                x = _axpby(np.conj(N_np[a]), _dev(self.nuc_pos_T[a][idx]), 0.0,
                            torch.empty_like(T0), conj_x=True)
-                dR.append(_axpby(-np.conj(N_nn[a]), to_device(np.asarray(self.nuc_neg_T[a][idx]), _C128), 1.0, x,
+                dR.append(_axpby(-np.conj(N_nn[a]), _dev(self.nuc_neg_T[a][idx]), 1.0, x,
                                  conj_x=True))
             return dict(t=t[None], tc=tc[None], dH=torch.stack(dH), dR=torch.stack(dR))
 
@@ -449,7 +453,7 @@ class AAT(object):
         nocc = 2 * self.ndocc
         N, N_np, N_nn, N_mp, N_mn = self.compute_normalization(alpha, beta, normalization)
         L = self._so_lists()
-        dev = lambda S: to_device(np.asarray(S), _C128)
+        dev = _dev
         if m == "RHF":
             sb = lambda S: spin_block_2_dev(dev(S))                      # aats.py:165-169 (not in place)
         else:

@@ -218,6 +218,9 @@ class ci_wfn(object):
 
     def _finish(self, eng, E, singles):
         self.iterations = eng.iterations
+        if config.RETURN_DEVICE:
+            t2 = eng.t2().clone()
+            return (E, eng.t1().clone(), t2) if singles else (E, t2)
         t2 = to_host(eng.t2()).copy()
         if singles:
             return E, to_host(eng.t1()).copy(), t2
@@ -252,7 +255,7 @@ class ci_wfn(object):
 
         E = eng.run(residual, print_level, self.wfn.E_SCF, self.H.E_nuc)
         out = self._finish(eng, E, False)
-        if config.VERBOSE:
+        if config.VERBOSE and not config.RETURN_DEVICE:
             print("t-Amplitude Data:")
             print("Maximum t2: ", np.max(out[1]))
         return out
@@ -384,7 +387,7 @@ class ci_wfn(object):
 
         E = eng.run(residual, print_level, self.wfn.E_SCF, self.H.E_nuc)
         out = self._finish(eng, E, True)
-        if config.VERBOSE:
+        if config.VERBOSE and not config.RETURN_DEVICE:
             print("t-Amplitude Data:")
             print("Maximum t1: ", np.max(out[1]))
             print("Maximum t2: ", np.max(out[2]))

@@ -5,3 +5,27 @@ USE_CUDA_GRAPH = True
 # The reference prints amplitude maxima / timings unconditionally (ci_wfn.py:132-133, 529-531;
 # aats.py:552, 1053).  Kept for drop-in fidelity; benches and tests switch it off.
 VERBOSE = True
+
+# Device-resident mode (bench `value` leg): solver results stay on the GPU as torch tensors
+# instead of being copied back to numpy; AAT accepts either.
+RETURN_DEVICE = False
+# Optional kernel timing hook: dict name -> list of (start_event, end_event); None = off.
+TIMING = None
+TIMING_ONLY = None          # optional name prefix filter for the hook
+
+
+def timed(name):
+    """Context manager recording CUDA events around a launch when TIMING is enabled."""
+    import contextlib
+    if TIMING is None or (TIMING_ONLY is not None and not name.startswith(TIMING_ONLY)):
+        return contextlib.nullcontext()
+    import torch
+
+    @contextlib.contextmanager
+    def _cm():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        TIMING.setdefault(name, []).append((e0, e1))
+    return _cm()

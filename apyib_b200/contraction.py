@@ -13,6 +13,7 @@ import ctypes as C
 import numpy as np
 import torch
 
+from . import config
 from ._lib import lib, check
 from .device import dtype_code, ptr, stream_ptr, device
 
@@ -79,12 +80,20 @@ def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
     assert A.dtype == B.dtype == out.dtype, "mixed dtypes: %s %s %s" % (A.dtype, B.dtype, out.dtype)
     M, N, K, ptrs, a_kfast, b_kfast, _keep = _plan(spec, A, B, out)
     alpha, beta = complex(alpha), complex(beta)
-    check(lib.apyib_contract(dtype_code(A), ptr(A), ptr(B), ptr(out), M, N, K,
+    if config.TIMING is not None:
+        with config.timed("contract[%s %dx%dx%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K)):
+            check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta))
+        return out
+    check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta))
+    return out
+
+
+def _launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta):
+    return (lib.apyib_contract(dtype_code(A), ptr(A), ptr(B), ptr(out), M, N, K,
                              *[C.c_void_p(p) for p in ptrs],
                              a_kfast, b_kfast, int(conj_a), int(conj_b),
                              alpha.real, alpha.imag, beta.real, beta.imag,
                              1, 0, 0, 0, C.c_void_p(0), stream_ptr()))
-    return out
 
 
 def contract_new(spec, A, B, alpha=1.0, conj_a=False, conj_b=False):

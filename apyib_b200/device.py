@@ -6,9 +6,11 @@ import ctypes as C
 import numpy as np
 import torch
 
+from . import _lib
 from ._lib import lib, check, F64, C128, require_cuda
 
 _scratch = {}
+COUNTERS = {"h2d_bytes": 0, "d2h_bytes": 0}     # host<->device traffic of the public API (bench e2e)
 
 
 def device():
@@ -43,10 +45,13 @@ def to_device(x, dtype=None):
         t = torch.from_numpy(a)
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
+    if not t.is_cuda:
+        COUNTERS["h2d_bytes"] += t.numel() * t.element_size()
     return t.to(device(), non_blocking=False).contiguous()
 
 
 def to_host(t):
+    COUNTERS["d2h_bytes"] += t.numel() * t.element_size()
     return t.detach().cpu().numpy()
 
 
@@ -88,6 +93,7 @@ class Graph:
         """Records the launches `fn` enqueues (nothing executes).  The legacy default stream
         cannot be captured, so recording happens on a private side stream; `fn` must only
         launch libapyib_b200 kernels on the *current* stream and must not allocate."""
+        n0 = _lib.LAUNCHES[0]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -99,8 +105,11 @@ class Graph:
                 rc = lib.apyib_graph_end(C.c_void_p(side.cuda_stream), C.byref(h))
         check(rc)
         self._exec = h
+        self._launches = _lib.LAUNCHES[0] - n0
+        _lib.LAUNCHES[0] = n0                       # recorded, not executed
 
     def launch(self):
+        _lib.LAUNCHES[0] += self._launches
         check(lib.apyib_graph_launch(self._exec, stream_ptr()))
 
     def __del__(self):

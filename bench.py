@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- CISD finite-difference AAT time-to-solution per molecule (BASELINE.json metric).
+
+A "step" is one complete pass of the hot path for one molecule: the 6N+7 CISD solves
+(AO->MO transform, Fock build, iterations) + MO overlaps + the determinant-overlap assembly of
+the full (3N,3) AAT tensor.  AO integrals and the complex-HF SCF of every finite-difference point
+are host inputs prepared once, outside the timed region (north star: "stay host-side inputs").
+
+Workload at N=1 (and for every N): BASELINE.json configs[1], H2O2/6-31G *shape* -- nbf=22,
+ndocc=9, 4 atoms, CISD, 30+1 points -- on synthetic integrals (no Psi4 in this image).
+
+  value : seconds per molecule with the per-point AO integrals already resident in HBM and
+          amplitudes kept on the device between the solve and the AAT phase;
+  e2e   : the same through the public drop-in API with host (numpy) buffers in and out:
+          ci_wfn(parameters, wfn).solve_CISD(), AAT(...), compute_spatial_aats(alpha, beta).
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload h2o2|small]
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: nbf, ndocc, natom, nfzc
+    "h2o2": dict(nbf=22, ndocc=9, natom=4, nfzc=0, label="H2O2/6-31G shape (nbf=22, ndocc=9, N=4), CISD FD-AAT, synthetic integrals"),
+    "small": dict(nbf=10, ndocc=4, natom=2, nfzc=0, label="smoke shape (nbf=10, ndocc=4, N=2), CISD FD-AAT, synthetic integrals"),
+}
+H_R = H_B = 1e-4
+METRIC = "cisd_fd_aat_time_to_solution_per_molecule"
+UNIT = "s/molecule"
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# FP64 peak on B200 is not in MEASURED_PEAKS.json (bf16 + HBM only); denominator = own DMMA
+# microbenchmark measured on this pool (profiles/r01_calibration.json), re-measured live when possible.
+FP64_PEAK_TFLOPS_FALLBACK = 37.2
+
+
+# ---------------------------------------------------------------------------------------------
+# host inputs (untimed): SCF + phase fix for every finite-difference point
+# ---------------------------------------------------------------------------------------------
+def prepare(wl):
+    from apyib_b200 import hostchem as hc
+    from apyib_b200.fin_diff import aat_points
+    prov = hc.SyntheticProvider(wl["nbf"], wl["ndocc"], wl["natom"], seed=1000 * 2, nfzc=wl["nfzc"])
+    par = {"geom": prov.geometry_string(), "basis": "synthetic", "method": "CISD", "freeze_core": wl["nfzc"] > 0,
+           "F_el": [0.0] * 3, "F_mag": [0.0] * 3, "provider": prov, "DIIS": True, "max_iterations": 120,
+           "e_convergence": 1e-12, "d_convergence": 1e-12}
+
+    def scf(p):
+        H = hc.Hamiltonian(p)
+        w = hc.hf_wfn(H)
+        w.solve_SCF(p)
+        return w
+
+    w0 = scf(par)
+    mol = hc.Molecule.from_string(par["geom"])
+    geom0 = mol.geometry()
+    pts = {}
+    for pt in aat_points(wl["natom"]):
+        p = copy.deepcopy({k: v for k, v in par.items() if k != "provider"})
+        p["provider"] = prov
+        if pt[0] == "R":
+            g = geom0.copy()
+            g[pt[1] // 3][pt[1] % 3] += pt[2] * H_R
+            mol.set_geometry(g)
+            p["geom"] = mol.create_psi4_string_from_molecule()
+        else:
+            p["F_mag"][pt[1]] += pt[2] * H_B
+        w = scf(p)
+        S = hc.provider_ao_overlap(w0.H.basis_set, w.H.basis_set)
+        d = np.diagonal(w0.C.conj().T @ S @ w.C)
+        w.C = w.C * ((d / np.sqrt(d * np.conj(d))) ** -1)[None, :]          # compute_phase, utils.py:427-446
+        pts[pt] = w
+    return dict(par=par, w0=w0, pts=pts, natom=wl["natom"], prov=prov)
+
+
+def work_items(work, rank, world):
+    from apyib_b200.fin_diff import aat_points, point_cost
+    from apyib_b200.parallel import partition
+    pts = aat_points(work["natom"])
+    own = partition(pts, [point_cost(p[0]) for p in pts], world)
+    return pts, own
+
+
+# ---------------------------------------------------------------------------------------------
+# one step of the product path
+# ---------------------------------------------------------------------------------------------
+def gpu_step(work, rank=0, world=1, dist=None):
+    import torch
+    import apyib_b200
+    from apyib_b200.aats import AAT
+    par, w0, natom = work["par"], work["w0"], work["natom"]
+    pts, own = work_items(work, rank, world)
+    n3 = 3 * natom
+
+    def solve(w):
+        E, t1, t2 = apyib_b200.ci_wfn(par, w).solve_CISD()
+        return [1, t1, t2]
+
+    T0 = solve(w0)                                     # every rank needs the unperturbed amplitudes
+    mine = {p: solve(work["pts"][p]) for p, o in zip(pts, own) if o == rank}
+    if world > 1:
+        # exchange step: every AAT element needs T(R+-alpha), T(B+-beta)  (aats.py:690-711)
+        blob = {p: [1] + [x.cpu().numpy() if hasattr(x, "cpu") else x for x in T[1:]] for p, T in mine.items()}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, blob)
+        for part in gathered:
+            for p, T in part.items():
+                mine.setdefault(p, T)
+    T = lambda k, i, s: mine[(k, i, s)]
+    W = lambda k, i, s: work["pts"][(k, i, s)]
+    A = AAT(par, w0, w0.C, w0.H.basis_set, T0,
+            [W("R", a, +1).C for a in range(n3)], [W("R", a, -1).C for a in range(n3)],
+            [W("R", a, +1).H.basis_set for a in range(n3)], [W("R", a, -1).H.basis_set for a in range(n3)],
+            [T("R", a, +1) for a in range(n3)], [T("R", a, -1) for a in range(n3)],
+            [W("B", b, +1).C for b in range(3)], [W("B", b, -1).C for b in range(3)],
+            [W("B", b, +1).H.basis_set for b in range(3)], [W("B", b, -1).H.basis_set for b in range(3)],
+            [T("B", b, +1) for b in range(3)], [T("B", b, -1) for b in range(3)], H_R, H_B)
+    I = np.zeros((n3, 3))
+    elems = [(a, b) for a in range(n3) for b in range(3)]
+    for k, (a, b) in enumerate(elems):
+        if k % world == rank:
+            I[a, b] = A.compute_spatial_aats(a, b)
+    if world > 1:
+        t = torch.from_numpy(I).cuda()
+        dist.all_reduce(t)                              # disjoint elements: sum == final gather of the tensor
+        I = t.cpu().numpy()
+    return I
+
+
+def drop_device_caches(work):
+    for w in [work["w0"]] + list(work["pts"].values()):
+        w.H._apyib_b200_dev = None
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (numpy restatement of the reference) on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(work, budget_s=20.0):
+    """Times (i) oracle.solve_CISD on finite-difference points and (ii) the substituted-determinant
+    evaluation of compute_all_dets (aats.py:581-618, batched np.linalg.det) on a slice of one
+    overlap, then scales both to the whole molecule.  Returns (seconds_per_molecule, description)."""
+    from oracle import apyib_oracle as orc
+    par, natom = work["par"], work["natom"]
+    w0 = work["w0"]
+    npts = 6 * natom + 7
+    t0 = time.perf_counter()
+    nsolve = 0
+    for w in [w0] + list(work["pts"].values())[:3] + list(work["pts"].values())[-1:]:
+        orc.solve_CISD(par, w)
+        nsolve += 1
+        if time.perf_counter() - t0 > budget_s / 3:
+            break
+    t_solve = (time.perf_counter() - t0) / nsolve
+    no, nv = w0.ndocc, w0.nbf - w0.ndocc
+    sing, doub = orc.det_index_tables(no, par_nfzc(work), nv)
+    S = np.eye(w0.nbf) + 1e-4 * np.random.default_rng(0).standard_normal((w0.nbf, w0.nbf)).astype(complex)
+    d_sub = doub.reshape(-1, 2, 2)
+    P = len(d_sub)
+    nrow = max(1, min(P, int(2.0e5 // max(P, 1)) or 1))
+    t0 = time.perf_counter()
+    ndet = 0
+    while True:
+        orc._batched_sub_dets(S, no, d_sub[:nrow], d_sub)
+        ndet += nrow * P
+        if time.perf_counter() - t0 > budget_s / 2:
+            break
+    t_det = (time.perf_counter() - t0) / ndet
+    n_overlaps = 1 + 6 + 6 * natom + 36 * natom
+    # the reference recomputes compute_all_dets for 9 overlaps per (alpha, beta) element (aats.py:714-1008)
+    n_overlaps_ref = 9 * 9 * natom
+    dets_per_overlap = 1 + 2 * len(sing) + 2 * P + len(sing) ** 2 + 2 * P * len(sing) + P * P
+    total = npts * t_solve + n_overlaps_ref * dets_per_overlap * t_det
+    desc = ("oracle (numpy port of ci_wfn.py:420-574 + aats.py:581-618): %d CISD solves timed (%.3f s each, x%d points) "
+            "+ %d substituted %dx%d determinants timed (%.2f us each, x%.3g dets x %d overlap evaluations as the "
+            "reference recomputes them per element; %d distinct overlaps); contraction of the 8-index tensors not "
+            "included (lower bound)" % (nsolve, t_solve, npts, ndet, no, no, t_det * 1e6, dets_per_overlap,
+                                        n_overlaps_ref, n_overlaps))
+    return total, desc
+
+
+def par_nfzc(work):
+    return work["w0"].H.basis_set.n_frozen_core()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, idx):
+        super().__init__(daemon=True)
+        self.idx, self.samples, self.reasons, self.stop_flag = idx, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def flush_l2(buf):
+    buf.zero_()       # 512 MB write, larger than the 126 MB L2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="h2o2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": wl["label"], "nbf": wl["nbf"], "ndocc": wl["ndocc"], "natom": wl["natom"],
+              "fd_points": 6 * wl["natom"] + 7, "h_R": H_R, "h_B": H_B, "method": "CISD",
+              "l2": "512 MB buffer written between timed steps (flush)", "sharding": "fd-points then tensor elements"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        work = prepare(wl)
+        vals = []
+        for _ in range(max(1, min(args.steps, 2))):
+            v, desc = cpu_sample(work, budget_s=30.0)
+            vals.append(v)
+        v = float(np.median(vals))
+        cores = os.cpu_count()
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
+                          "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64/c128",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import apyib_b200
+    from apyib_b200 import _lib, device as dev
+    apyib_b200.config.VERBOSE = False
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    work = prepare(wl)
+    l2buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(k, device_resident):
+        apyib_b200.config.RETURN_DEVICE = device_resident
+        tot = 0.0
+        res = None
+        for _ in range(k):
+            if not device_resident:
+                drop_device_caches(work)
+            flush_l2(l2buf)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            res = gpu_step(work, rank, world, dist)
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            tot += max(e0.elapsed_time(e1) * 1e-3, wall)       # host-orchestrated step: never below wall clock
+        return tot, res
+
+    sampler = ClockSampler(local_rank)
+    # warm-up (also fills the device-resident AO-integral caches and the offset-table cache)
+    timed_steps(args.warmup, True)
+    sampler.start()
+    apyib_b200.config.TIMING = {}
+    apyib_b200.config.TIMING_ONLY = "det_matvec"
+    _lib.LAUNCHES[0] = 0
+    t_dev, I_dev = timed_steps(args.steps, True)
+    launches = _lib.LAUNCHES[0] // max(args.steps, 1)
+    timing = apyib_b200.config.TIMING
+    apyib_b200.config.TIMING = None
+    dev.COUNTERS["h2d_bytes"] = dev.COUNTERS["d2h_bytes"] = 0
+    t_e2e, I_e2e = timed_steps(args.steps, False)
+    h2d, d2h = dev.COUNTERS["h2d_bytes"] // args.steps, dev.COUNTERS["d2h_bytes"] // args.steps
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if dist is not None:
+        t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    assert np.abs(I_dev - I_e2e).max() < 1e-8 * max(1.0, np.abs(I_e2e).max()), "device-resident and e2e legs disagree"
+
+    # ---- roofline of the dominant kernel: the fused LU determinant kernel, largest shape ----
+    peaks, peak_src = load_peaks()
+    fp64_peak = FP64_PEAK_TFLOPS_FALLBACK
+    try:
+        import ctypes as C
+        fl, ms = C.c_double(), C.c_float()
+        _lib.check(_lib.lib.apyib_peak_fp64(1, 4000, C.byref(fl), C.byref(ms)))
+        fp64_peak = fl.value / 1e12
+    except Exception:
+        pass
+    roof = None
+    if timing:
+        name = max(timing, key=lambda k: sum(a.elapsed_time(b) for a, b in timing[k]))
+        evs = timing[name]
+        avg_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        n = int(name.split("n=")[1].split(",")[0])
+        nrow, ncol = (int(x) for x in name.split(",")[1].rstrip("]").split("x"))
+        flops = nrow * ncol * (8.0 / 3.0) * n ** 3          # (8/3) n^3 real flop per complex LU
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        share = sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / t_dev
+        roof = {"bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                "traffic": None, "kernel": "det_kernel<16,false> " + name, "launches_timed": len(evs),
+                "avg_ms": avg_ms, "share_of_step": share,
+                "note": "FP64 compute roofline (LU on the FP64 FMA pipe); peak = own DMMA microbenchmark measured "
+                        "in this run (MEASURED_PEAKS.json holds only bf16/HBM, %s)" % peak_src}
+    cpu_v, cpu_desc = cpu_sample(work, budget_s=20.0)
+    line = {"metric": METRIC, "value": t_dev / args.steps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64/c128", "data": "synthetic", "config": config,
+            "clocks": sampler.result(),
+            "e2e": {"value": t_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches), "roofline": roof,
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
+            "aat_checksum": float(np.abs(I_dev).sum())}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
