@@ -14,71 +14,89 @@ namespace apyib {
 
 constexpr int kDetThreads = 256;
 
-template <int G>
-__device__ __forceinline__ cplx group_lu_det(cplx (&a)[G], const int n, const int l) {
-    // lanes >= n are padding: never pivot, never updated
-    bool done = (l >= n);
-    cplx det = make_cplx(1.0, 0.0);
-    int parity = 0;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned gbase = lane & ~(unsigned)(G - 1);
+// LU with partial pivoting of an N x N complex matrix spread over a group of N lanes (lane l of
+// the group = matrix row l, in registers, fully unrolled -> static register indexing).
+//   pivot search : one REDUX.MAX on the high word of |re|+|im| (LAPACK izamax metric, 20-bit
+//                  mantissa resolution is plenty for choosing a pivot) + one ballot;
+//   pivot row    : broadcast with shuffles from the owning lane, rows are never moved -- the
+//                  permutation parity comes from a ballot of the not-yet-eliminated rows;
+//   multipliers  : one reciprocal per step instead of a complex division per row.
+// Lanes that belong to no group (32 % N leftovers) run the same instruction stream on a dummy
+// identity row with a single-lane member mask.
+template <int N>
+__device__ __forceinline__ cplx group_lu_det(cplx (&a)[N], const int l, const int g, const int gbase) {
+    constexpr int GPW = 32 / N;
+    constexpr unsigned gm = (N == 32) ? 0xffffffffu : ((1u << N) - 1u);
+    bool done = (g >= GPW);                          // leftover lanes never take part
+    double detx = 1.0, dety = 0.0;
+    unsigned parity = 0;
 #pragma unroll
-    for (int k = 0; k < G; ++k) {
-        if (k < n) {
-            double best = done ? -1.0 : (fabs(a[k].x) + fabs(a[k].y));
-            int who = l;
+    for (int k = 0; k < N; ++k) {
+        const double mag = fabs(a[k].x) + fabs(a[k].y);
+        const unsigned key = done ? 0u : ((unsigned)__double2hiint(mag) + 1u);
+        // per-group maximum with GPW full-warp REDUX ops (a REDUX over sub-warp member masks
+        // would be serialised by the compiler into a loop over the distinct masks)
+        unsigned kmax = 0u;
 #pragma unroll
-            for (int off = G / 2; off > 0; off >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, off, G);
-                const int ow = __shfl_xor_sync(0xffffffffu, who, off, G);
-                if (ob > best || (ob == best && ow < who)) {
-                    best = ob;
-                    who = ow;
-                }
-            }
-            const unsigned undone = (__ballot_sync(0xffffffffu, !done) >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
-            parity ^= __popc(undone & ((1u << who) - 1u)) & 1;
-            cplx pv;
-            pv.x = __shfl_sync(0xffffffffu, a[k].x, who, G);
-            pv.y = __shfl_sync(0xffffffffu, a[k].y, who, G);
-            det = det * pv;
-            if (l == who) done = true;
-            cplx f = make_cplx(0.0, 0.0);
-            if (!done && best > 0.0) f = cdiv(a[k], pv);
+        for (int G = 0; G < GPW; ++G) {
+            const unsigned m = __reduce_max_sync(0xffffffffu, (g == G) ? key : 0u);
+            kmax = (g == G) ? m : kmax;
+        }
+        const unsigned undone = (__ballot_sync(0xffffffffu, !done) >> gbase) & gm;
+        const unsigned cand = (__ballot_sync(0xffffffffu, (!done) && key == kmax) >> gbase) & gm;
+        const int who = cand ? (__ffs(cand) - 1) : 0;          // lowest row among the maxima
+        parity ^= (unsigned)__popc(undone & ((1u << who) - 1u));
+        const int src = gbase + who;
+        const double pvx = __shfl_sync(0xffffffffu, a[k].x, src);
+        const double pvy = __shfl_sync(0xffffffffu, a[k].y, src);
+        const double ndx = detx * pvx - dety * pvy;
+        dety = detx * pvy + dety * pvx;
+        detx = ndx;
+        done = done || (l == who);
+        const double d2 = fma(pvx, pvx, pvy * pvy);
+        const double rinv = (d2 > 0.0) ? __drcp_rn(d2) : 0.0;  // exactly singular column -> det = 0
+        const double ix = pvx * rinv, iy = -pvy * rinv;
+        double fx = fma(a[k].x, ix, -a[k].y * iy), fy = fma(a[k].x, iy, a[k].y * ix);
+        fx = done ? 0.0 : fx;
+        fy = done ? 0.0 : fy;
 #pragma unroll
-            for (int j = k + 1; j < G; ++j) {
-                if (j < n) {
-                    cplx pj;
-                    pj.x = __shfl_sync(0xffffffffu, a[j].x, who, G);
-                    pj.y = __shfl_sync(0xffffffffu, a[j].y, who, G);
-                    a[j].x -= f.x * pj.x - f.y * pj.y;
-                    a[j].y -= f.x * pj.y + f.y * pj.x;
-                }
-            }
+        for (int j = k + 1; j < N; ++j) {
+            const double px = __shfl_sync(0xffffffffu, a[j].x, src);
+            const double py = __shfl_sync(0xffffffffu, a[j].y, src);
+            a[j].x = fma(fy, py, fma(-fx, px, a[j].x));
+            a[j].y = fma(-fy, px, fma(-fx, py, a[j].y));
         }
     }
-    if (parity) det = make_cplx(-det.x, -det.y);
-    return det;
+    const double sgn = (parity & 1u) ? -1.0 : 1.0;
+    return make_cplx(sgn * detx, sgn * dety);
 }
 
-// grid: x = row blocks (kDetThreads/G rows each), y = column chunks.
+// n <= N: the matrix is embedded as blockdiag(M, 1).  Each warp carries 32/N groups; a group owns
+// one row list r and loops over a chunk of column lists.
+// grid: x = row blocks, y = column chunks.
 // OUTER : out[r*ncol + c] = det
 // !OUTER: Zp[(chunk*ny + iy)*nrow + r] = sum_{c in chunk} det(r,c) * Y[iy*ncol + c]
-template <int G, bool OUTER>
-__global__ void __launch_bounds__(kDetThreads)
+template <int N, bool OUTER>
+__global__ void __launch_bounds__(kDetThreads, (N <= 10) ? 3 : 2)
 det_kernel(const cplx *__restrict__ S, int ns, int n, const int32_t *__restrict__ rows, int64_t nrow,
            const int32_t *__restrict__ cols, int64_t ncol, int64_t chunk_len, const cplx *__restrict__ Y, int ny,
            cplx *__restrict__ out) {
-    constexpr int GPB = kDetThreads / G;
-    const int l = threadIdx.x % G;
-    const int64_t r = (int64_t)blockIdx.x * GPB + threadIdx.x / G;
-    const bool rvalid = r < nrow;
+    constexpr int GPW = 32 / N;                       // groups per warp
+    constexpr int GPB = (kDetThreads / 32) * GPW;     // groups per block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / N;
+    const bool in_group = g < GPW;
+    const int l = in_group ? lane - g * N : 0;
+    const int gbase = in_group ? g * N : lane;
+    const int64_t r = (int64_t)blockIdx.x * GPB + warp * GPW + g;
+    const bool rvalid = in_group && r < nrow;
+    const bool real_row = rvalid && l < n;
     const int64_t c0 = (int64_t)blockIdx.y * chunk_len;
     int64_t c1 = c0 + chunk_len;
     if (c1 > ncol) c1 = ncol;
 
     const cplx *Srow = S;
-    if (rvalid && l < n) Srow = S + (int64_t)rows[r * n + l] * ns;
+    if (real_row) Srow = S + (int64_t)rows[r * n + l] * ns;
 
     constexpr int NYMAX = 4;
     cplx z[NYMAX];
@@ -86,16 +104,14 @@ det_kernel(const cplx *__restrict__ S, int ns, int n, const int32_t *__restrict_
     for (int q = 0; q < NYMAX; ++q) z[q] = make_cplx(0.0, 0.0);
 
     for (int64_t c = c0; c < c1; ++c) {
-        cplx a[G];
+        cplx a[N];
         const int32_t *cl = cols + c * n;
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            if (j < n) {
-                if (rvalid && l < n) a[j] = ldg(&Srow[__ldg(&cl[j])]);
-                else a[j] = make_cplx(j == l ? 1.0 : 0.0, 0.0);
-            }
+        for (int j = 0; j < N; ++j) {
+            if (real_row && j < n) a[j] = ldg(&Srow[__ldg(&cl[j])]);
+            else a[j] = make_cplx((j == l && !(real_row)) || (j == l && j >= n) ? 1.0 : 0.0, 0.0);
         }
-        const cplx d = group_lu_det<G>(a, n, l);
+        const cplx d = group_lu_det<N>(a, l, g, gbase);
         if (l == 0 && rvalid) {
             if (OUTER) {
                 out[r * ncol + c] = d;
@@ -140,21 +156,34 @@ pack_doubles_kernel(const cplx *__restrict__ x, int64_t xstride, int nq, int o, 
     }
 }
 
+// instantiated matrix sizes; n is padded up to the next one
+static int padded_size(int n) {
+    static const int sizes[] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 20, 24, 28, 32};
+    for (int s : sizes)
+        if (n <= s) return s;
+    return 32;
+}
+static int64_t groups_per_block(int n) { return (kDetThreads / 32) * (32 / padded_size(n)); }
+
 template <bool OUTER>
-static int launch_det(int G, dim3 grid, cudaStream_t st, const cplx *S, int ns, int n, const int32_t *rows,
-                      int64_t nrow, const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny,
-                      cplx *out) {
-    switch (G) {
-        case 4: det_kernel<4, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
-        case 8: det_kernel<8, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
-        case 16: det_kernel<16, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
-        default: det_kernel<32, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); break;
+static int launch_det(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
+                      const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny, cplx *out) {
+#define APYIB_DET_CASE(NN)                                                                                         \
+    case NN:                                                                                                       \
+        det_kernel<NN, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out); \
+        break;
+    switch (padded_size(n)) {
+        APYIB_DET_CASE(2) APYIB_DET_CASE(3) APYIB_DET_CASE(4) APYIB_DET_CASE(5) APYIB_DET_CASE(6) APYIB_DET_CASE(7)
+        APYIB_DET_CASE(8) APYIB_DET_CASE(9) APYIB_DET_CASE(10) APYIB_DET_CASE(12) APYIB_DET_CASE(14)
+        APYIB_DET_CASE(16) APYIB_DET_CASE(20) APYIB_DET_CASE(24) APYIB_DET_CASE(28)
+        default:
+            det_kernel<32, OUTER><<<grid, kDetThreads, 0, st>>>(S, ns, n, rows, nrow, cols, ncol, chunk_len, Y, ny, out);
+            break;
     }
+#undef APYIB_DET_CASE
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
-
-static int group_size(int n) { return n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : 32)); }
 
 }  // namespace apyib
 
@@ -165,8 +194,7 @@ extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_
     APYIB_REQUIRE(d_S && d_rows && d_cols && d_out, "null pointer");
     APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
     if (nrow == 0 || ncol == 0) return APYIB_OK;
-    const int G = group_size(n);
-    const int64_t gpb = kDetThreads / G;
+    const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     int64_t nchunk = (148 * 8 + rb - 1) / rb;
     if (nchunk > ncol) nchunk = ncol;
@@ -176,15 +204,14 @@ extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_
     nchunk = (ncol + chunk_len - 1) / chunk_len;
     APYIB_REQUIRE(rb <= 2147483647LL, "too many rows");
     dim3 grid((unsigned)rb, (unsigned)nchunk);
-    return launch_det<true>(G, grid, (cudaStream_t)stream, (const cplx *)d_S, ns, n, d_rows, nrow, d_cols, ncol,
+    return launch_det<true>(n, grid, (cudaStream_t)stream, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol,
                             chunk_len, nullptr, 0, (cplx *)d_out);
 }
 
 // Z[iy*nrow + r] = sum_c det(S[rows[r], cols[c]]) * Y[iy*ncol + c]
 // d_work: scratch of apyib_det_matvec_work_len(nrow, ncol, ny, n) complex128 elements.
 extern "C" int64_t apyib_det_matvec_nchunk(int64_t nrow, int64_t ncol, int n) {
-    const int G = group_size(n);
-    const int64_t gpb = kDetThreads / G;
+    const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     int64_t nchunk = (148 * 8 + rb - 1) / rb;
     if (nchunk > ncol) nchunk = ncol;
@@ -210,13 +237,12 @@ extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d
         APYIB_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(cplx) * ny * nrow, st));
         return APYIB_OK;
     }
-    const int G = group_size(n);
-    const int64_t gpb = kDetThreads / G;
+    const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     const int64_t nchunk = apyib_det_matvec_nchunk(nrow, ncol, n);
     const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
     dim3 grid((unsigned)rb, (unsigned)nchunk);
-    int rc = launch_det<false>(G, grid, st, (const cplx *)d_S, ns, n, d_rows, nrow, d_cols, ncol, chunk_len,
+    int rc = launch_det<false>(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
                                (const cplx *)d_Y, ny, (cplx *)d_work);
     if (rc != APYIB_OK) return rc;
     const int64_t len = (int64_t)ny * nrow;

@@ -1,7 +1,7 @@
 """FP64 / HBM calibration on the GPU box -> gpurun_out/calibration.json (copied to profiles/)."""
 import ctypes as C, json, os, sys, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from apyib_b200._lib import lib, check
 
 out = {"gpu": torch.cuda.get_device_name(0)}

@@ -1,0 +1,26 @@
+"""Runs the fused LU determinant kernel on the bench shape (n=9, 2808 x 2808 substituted
+matrices of a 22 x 22 overlap) a few times -- target for `ncu -k regex:det_kernel`."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from apyib_b200.aats import _Tables, _det_matvec
+from apyib_b200.device import to_device
+
+no, nf, nv = int(os.environ.get("NO", 9)), 0, int(os.environ.get("NV", 13))
+nbf = no + nv
+rng = np.random.default_rng(0)
+S = to_device(np.eye(nbf) + 1e-4 * (rng.standard_normal((nbf, nbf)) + 0.1j * rng.standard_normal((nbf, nbf))), torch.complex128)
+T = _Tables.get(no, nf, nv)
+P = T.n2
+Y = to_device(rng.standard_normal((1, P)) + 1j * rng.standard_normal((1, P)), torch.complex128)
+for _ in range(3):
+    Z = _det_matvec(S, no, T.L[2], T.L[2], Y)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+reps = 5
+for _ in range(reps):
+    Z = _det_matvec(S, no, T.L[2], T.L[2], Y)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / reps
+print("n=%d P=%d  %.3f ms/launch  %.3e dets/s  %.2f TFLOP/s (8/3 n^3)" % (no, P, ms, P * P / ms * 1e3, P * P * 8 / 3 * no ** 3 / ms * 1e3 / 1e12))
