@@ -348,8 +348,16 @@ class AAT(object):
             if P:
                 dd["ds1"] = cn("xr,qr->xq", Xh, z21[ny:])
                 dd["sd1"] = cn("xr,qr->xq", X1.reshape(nx, -1), z12)
-        h = {k: to_host(v) for k, v in dd.items()}
-        dSh = complex(to_host(dS)[0, 0])
+        # one device->host copy for all the small result matrices of this block
+        keys = list(dd)
+        flat = torch.cat([dS.reshape(-1)] + [dd[k].reshape(-1) for k in keys])
+        fh = to_host(flat)
+        dSh = complex(fh[0])
+        h, off = {}, 1
+        for k in keys:
+            n_el = dd[k].numel()
+            h[k] = fh[off:off + n_el].reshape(tuple(dd[k].shape))
+            off += n_el
         zero = np.zeros((nx, ny), dtype=np.complex128)
         g = lambda k: h.get(k, zero)
         v1, v2 = g("v1"), g("v2")                                        # [nx,1], [1,ny]

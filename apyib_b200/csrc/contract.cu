@@ -259,8 +259,9 @@ extern "C" int apyib_contract(int dtype, const void *d_A, const void *d_B, void 
     const bool big = big_tiles >= 148;
     if (dtype == APYIB_C128) {
         return big ? launch_contract<true, 64, 64, 8, 32, 32, 3>(a, batch, st)
-                   : launch_contract<true, 32, 32, 8, 16, 16, 3>(a, batch, st);
+                   : launch_contract<true, 32, 32, 16, 16, 16, 4>(a, batch, st);
     }
+    // small problems are latency bound (few CTAs, each walking K alone): deeper pipeline, longer slabs
     return big ? launch_contract<false, 64, 64, 16, 32, 32, 3>(a, batch, st)
-               : launch_contract<false, 32, 32, 16, 16, 16, 3>(a, batch, st);
+               : launch_contract<false, 32, 32, 32, 16, 16, 4>(a, batch, st);
 }

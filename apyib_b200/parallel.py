@@ -47,6 +47,36 @@ def partition(items, costs, world):
     return owner
 
 
+def exchange_points(dist, blob, world):
+    """The one exchange step of the path: every rank contributes {point: payload} for the points
+    it solved and receives the union (every AAT element needs all amplitudes, aats.py:690-711)."""
+    if dist is None or world == 1:
+        return dict(blob)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, blob)
+    out = {}
+    for part in gathered:
+        out.update(part)
+    return out
+
+
+def owned_elements(n3, rank, world):
+    """(alpha, beta) elements of the (3N,3) tensor evaluated by `rank` (round robin)."""
+    return [(a, b) for k, (a, b) in enumerate((a, b) for a in range(n3) for b in range(3)) if k % world == rank]
+
+
+def gather_tensor(dist, I, world):
+    """Final gather of the (3N,3) tensor: ranks fill disjoint elements, the rest is zero, so a
+    sum-all-reduce is the gather (NCCL on GPUs, gloo in the CPU tests)."""
+    if dist is None or world == 1:
+        return I
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(np.ascontiguousarray(I)).to(dev)
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
 def compute_parallel_aats(parameters, nuc_pert_strength, mag_pert_strength, normalization='full', num_processes=4):
     dist, rank, world = _dist()
     E_list, T_list, C, basis = energy(parameters)
@@ -69,15 +99,12 @@ def compute_parallel_aats(parameters, nuc_pert_strength, mag_pert_strength, norm
             i0 = 0 if p[2] > 0 else 1
             grp = 0 if p[0] == "R" else 6
             blob[p] = (lists[grp + i0][p[1]], lists[grp + 4 + i0][p[1]])
-        gathered = [None] * world
-        dist.all_gather_object(gathered, blob)
         lists = [list(x) for x in lists]
-        for part in gathered:
-            for p, (Cp, Tp) in part.items():
-                i0 = 0 if p[2] > 0 else 1
-                grp = 0 if p[0] == "R" else 6
-                lists[grp + i0][p[1]] = Cp
-                lists[grp + 4 + i0][p[1]] = Tp
+        for p, (Cp, Tp) in exchange_points(dist, blob, world).items():
+            i0 = 0 if p[2] > 0 else 1
+            grp = 0 if p[0] == "R" else 6
+            lists[grp + i0][p[1]] = Cp
+            lists[grp + 4 + i0][p[1]] = Tp
         for p in pts:                      # basis handles for points solved elsewhere
             i0 = 0 if p[2] > 0 else 1
             grp = 0 if p[0] == "R" else 6
@@ -96,17 +123,10 @@ def compute_parallel_aats(parameters, nuc_pert_strength, mag_pert_strength, norm
                nuc_pert_strength, mag_pert_strength)
     spatial = parameters['method'] in ('RHF', 'MP2', 'CID', 'CISD')
     fn = AATs.compute_spatial_aats if spatial else AATs.compute_SO_aats
-    rows = [a for a in range(3 * natom) if a % world == rank]
     I = np.zeros((3 * natom, 3))
-    for a in rows:
-        for b in range(3):
-            I[a, b] = fn(a, b, normalization)
-    if world > 1:
-        import torch
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        t = torch.from_numpy(I).to(dev)
-        dist.all_reduce(t)                 # rows are disjoint -> sum == gather of the (3N,3) tensor
-        I = t.cpu().numpy()
+    for a, b in owned_elements(3 * natom, rank, world):
+        I[a, b] = fn(a, b, normalization)
+    I = gather_tensor(dist, I, world)
     if config.VERBOSE and rank == 0:
         print(I, "\n")
     return I

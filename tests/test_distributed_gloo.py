@@ -1,0 +1,75 @@
+"""CPU, world_size = 2, gloo: the N>1 host logic of the sharded finite-difference driver
+(partition of the points, the one amplitude exchange, element partition, final tensor gather)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _code(p):
+    return float(ord(p[0]) + 7 * p[1] + 3 * (p[2] + 1))
+
+
+def _worker(rank, world, port, natom, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from apyib_b200.parallel import partition, exchange_points, owned_elements, gather_tensor, _dist
+        from apyib_b200.fin_diff import aat_points, point_cost
+        d, r, w = _dist()
+        assert (r, w) == (rank, world)
+        pts = aat_points(natom)
+        own = partition(pts, [point_cost(p[0]) for p in pts], world)
+        mine = {p: (rank, np.full((2, 2), _code(p), dtype=np.float64)) for p, o in zip(pts, own) if o == rank}
+        allp = exchange_points(d, mine, world)
+        assert sorted(allp) == sorted(pts)
+        for p, (src, arr) in allp.items():
+            assert src == own[pts.index(p)] and arr[0, 0] == _code(p)
+        n3 = 3 * natom
+        I = np.zeros((n3, 3))
+        for a, b in owned_elements(n3, rank, world):
+            I[a, b] = 100 * a + b + 0.5
+        I = gather_tensor(d, I, world)
+        want = np.array([[100 * a + b + 0.5 for b in range(3)] for a in range(n3)])
+        q.put((rank, bool(np.array_equal(I, want)), len(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_driver_logic_world2():
+    world, natom = 2, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, natom, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=90) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert sum(n for _, _, n in res) == 6 * natom + 6
+    loads = sorted(n for _, _, n in res)
+    assert loads[-1] - loads[0] <= 8          # complex points weigh 4x, counts may differ
+
+
+def test_single_process_degenerates():
+    from apyib_b200.parallel import exchange_points, owned_elements, gather_tensor
+    assert exchange_points(None, {1: 2}, 1) == {1: 2}
+    assert owned_elements(2, 0, 1) == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2)]
+    I = np.ones((2, 3))
+    assert gather_tensor(None, I, 1) is I
