@@ -50,24 +50,37 @@ struct ContractArgs {
 template <bool CPLX> struct elem_t { using type = double; };
 template <> struct elem_t<true> { using type = cplx; };
 
+// Shared-memory tile layouts.  An operand whose k index is the contiguous one in global memory
+// (KF = true) is staged as [row][k] (k contiguous), otherwise as [k][row]; either way consecutive
+// threads of the gather write consecutive shared-memory words (no store conflicts) and read
+// consecutive global elements (coalesced).  Pitches make the DMMA fragment reads
+// (lane -> row = lane/4, k = lane%4) conflict-free:
+//   [k][row]: pitch = 4 (mod 16) doubles / 2 (mod 8) complex
+//   [row][k]: pitch = 4 (mod 16) doubles / 4 (mod 8) complex
+template <bool CPLX, bool KF, int ROWS, int BK> struct TileLayout {
+    static constexpr int pitch = KF ? (BK + 4) : (ROWS + (CPLX ? 2 : 4));
+    static constexpr int size = KF ? ROWS * pitch : BK * pitch;
+    __device__ static __forceinline__ int at(int row, int k) { return KF ? row * pitch + k : k * pitch + row; }
+};
+
 // BM x BN CTA tile, BK slab, warps arranged (BM/WM) x (BN/WN), each warp WM x WN.
-template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES>
+template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES, bool AKF, bool BKF>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
 contract_kernel(const ContractArgs p) {
     using T = typename elem_t<CPLX>::type;
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int EB = CPLX ? 16 : 8;
-    // row pitch: conflict-free fragment reads: pitch = 2 (mod 8) complex, 4 (mod 16) real
-    constexpr int LDA = BM + (CPLX ? 2 : 4);
-    constexpr int LDB = BN + (CPLX ? 2 : 4);
+    using LA = TileLayout<CPLX, AKF, BM, BK>;
+    using LB = TileLayout<CPLX, BKF, BN, BK>;
     constexpr int TM = WM / 8, TN = WN / 8;
-    constexpr int ITA = (BM * BK) / NT, ITB = (BN * BK) / NT;
-    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile/threads mismatch");
+    constexpr int ITA = (BM * BK) / NT, ITB = (BN * BK) / NT;   // elements per thread per slab
+    constexpr int RG = NT / BK;                                 // row groups: threads sharing one k
+    static_assert((BM * BK) % NT == 0 && (BN * BK) % NT == 0 && NT % BK == 0, "tile/threads mismatch");
     static_assert(BK % 4 == 0, "BK must be a multiple of the DMMA k");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *As = reinterpret_cast<T *>(smem_raw);                       // [STAGES][BK][LDA]
-    T *Bs = As + (size_t)STAGES * BK * LDA;                        // [STAGES][BK][LDB]
+    T *As = reinterpret_cast<T *>(smem_raw);                       // [STAGES][LA::size]
+    T *Bs = As + (size_t)STAGES * LA::size;                        // [STAGES][LB::size]
 
     const int z = blockIdx.z;
     if (p.active != nullptr && p.active[z] == 0) return;
@@ -79,43 +92,44 @@ contract_kernel(const ContractArgs p) {
     const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
     const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
 
-    // per-thread gather coordinates (fixed for the whole kernel)
-    int a_mi[ITA], a_ki[ITA], b_ni[ITB], b_ki[ITB];
+    // Gather mapping: every thread owns ONE k of the slab and ITA (ITB) rows, fixed for the whole
+    // kernel -> row offsets live in registers, one k-offset load per operand per slab.
+    const int a_k = AKF ? tid % BK : tid / RG, a_r0 = AKF ? tid / BK : tid % RG;
+    const int b_k = BKF ? tid % BK : tid / RG, b_r0 = BKF ? tid / BK : tid % RG;
     int64_t a_off[ITA], b_off[ITB];
-    bool a_ok[ITA], b_ok[ITB];
+    unsigned a_ok = 0, b_ok = 0;
 #pragma unroll
     for (int i = 0; i < ITA; ++i) {
-        int e = tid + i * NT;
-        a_mi[i] = p.a_kfast ? e / BK : e % BM;
-        a_ki[i] = p.a_kfast ? e % BK : e / BM;
-        a_ok[i] = (m0 + a_mi[i]) < p.M;
-        a_off[i] = a_ok[i] ? p.a_m[m0 + a_mi[i]] : 0;
+        const int64_t m = m0 + a_r0 + i * RG;
+        const bool ok = m < p.M;
+        a_ok |= (ok ? 1u : 0u) << i;
+        a_off[i] = ok ? p.a_m[m] : 0;
     }
 #pragma unroll
     for (int i = 0; i < ITB; ++i) {
-        int e = tid + i * NT;
-        b_ni[i] = p.b_kfast ? e / BK : e % BN;
-        b_ki[i] = p.b_kfast ? e % BK : e / BN;
-        b_ok[i] = (n0 + b_ni[i]) < p.N;
-        b_off[i] = b_ok[i] ? p.b_n[n0 + b_ni[i]] : 0;
+        const int64_t n = n0 + b_r0 + i * RG;
+        const bool ok = n < p.N;
+        b_ok |= (ok ? 1u : 0u) << i;
+        b_off[i] = ok ? p.b_n[n] : 0;
     }
 
-    auto load_slab = [&](int stage, int64_t kbase) {
-        T *as = As + (size_t)stage * BK * LDA;
-        T *bs = Bs + (size_t)stage * BK * LDB;
+    auto k_offsets = [&](int64_t kbase, int64_t &ak, int64_t &bk) {
+        const int64_t ka = kbase + a_k, kb = kbase + b_k;
+        ak = (ka < p.K) ? p.a_k[ka] : -1;       // -1: beyond K -> zero fill
+        bk = (kb < p.K) ? p.b_k[kb] : -1;
+    };
+    auto load_slab = [&](int stage, int64_t ak, int64_t bk) {
+        T *as = As + (size_t)stage * LA::size;
+        T *bs = Bs + (size_t)stage * LB::size;
 #pragma unroll
         for (int i = 0; i < ITA; ++i) {
-            int64_t k = kbase + a_ki[i];
-            bool ok = a_ok[i] && k < p.K;
-            int64_t off = ok ? a_off[i] + p.a_k[k] : 0;
-            cp_async<EB>(as + a_ki[i] * LDA + a_mi[i], A + off, ok);
+            const bool ok = ((a_ok >> i) & 1u) && ak >= 0;
+            cp_async<EB>(as + LA::at(a_r0 + i * RG, a_k), A + (ok ? a_off[i] + ak : 0), ok);
         }
 #pragma unroll
         for (int i = 0; i < ITB; ++i) {
-            int64_t k = kbase + b_ki[i];
-            bool ok = b_ok[i] && k < p.K;
-            int64_t off = ok ? b_off[i] + p.b_k[k] : 0;
-            cp_async<EB>(bs + b_ki[i] * LDB + b_ni[i], B + off, ok);
+            const bool ok = ((b_ok >> i) & 1u) && bk >= 0;
+            cp_async<EB>(bs + LB::at(b_r0 + i * RG, b_k), B + (ok ? b_off[i] + bk : 0), ok);
         }
     };
 
@@ -130,11 +144,16 @@ contract_kernel(const ContractArgs p) {
         }
 
     const int64_t nslab = (p.K + BK - 1) / BK;
+    int64_t ak_next, bk_next;                  // k offsets of the next slab to be issued (prefetched)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < nslab) load_slab(s, (int64_t)s * BK);
+        if (s < nslab) {
+            k_offsets((int64_t)s * BK, ak_next, bk_next);
+            load_slab(s, ak_next, bk_next);
+        }
         cp_async_commit();
     }
+    k_offsets((int64_t)(STAGES - 1) * BK, ak_next, bk_next);
 
     const int fr = lane >> 2, fk = lane & 3;   // fragment row (or col) / k within the 8x4 atom
     const double sa = p.conj_a ? -1.0 : 1.0, sb = p.conj_b ? -1.0 : 1.0;
@@ -143,32 +162,43 @@ contract_kernel(const ContractArgs p) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {   // prefetch slab kt + STAGES - 1 into the stage freed in the previous iteration
-            int64_t nk = kt + STAGES - 1;
-            if (nk < nslab) load_slab((int)(nk % STAGES), nk * BK);
+            const int64_t nk = kt + STAGES - 1;
+            if (nk < nslab) load_slab((int)(nk % STAGES), ak_next, bk_next);
             cp_async_commit();
+            k_offsets((nk + 1) * BK, ak_next, bk_next);
         }
-        const T *as = As + (size_t)(kt % STAGES) * BK * LDA;
-        const T *bs = Bs + (size_t)(kt % STAGES) * BK * LDB;
+        const T *as = As + (size_t)(kt % STAGES) * LA::size;
+        const T *bs = Bs + (size_t)(kt % STAGES) * LB::size;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             T af[TM], bf[TN];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) af[i] = as[(kk + fk) * LDA + wm0 + i * 8 + fr];
+            for (int i = 0; i < TM; ++i) af[i] = as[LA::at(wm0 + i * 8 + fr, kk + fk)];
 #pragma unroll
-            for (int j = 0; j < TN; ++j) bf[j] = bs[(kk + fk) * LDB + wn0 + j * 8 + fr];
+            for (int j = 0; j < TN; ++j) bf[j] = bs[LB::at(wn0 + j * 8 + fr, kk + fk)];
             if constexpr (CPLX) {
+                // four passes so that DMMAs hitting the same accumulator are TM*TN instructions apart
+                double ai[TM], bi[TN];
 #pragma unroll
-                for (int i = 0; i < TM; ++i) {
-                    const double ar = af[i].x, ai = sa * af[i].y, nai = -ai;
+                for (int i = 0; i < TM; ++i) ai[i] = sa * af[i].y;
 #pragma unroll
-                    for (int j = 0; j < TN; ++j) {
-                        const double br = bf[j].x, bi = sb * bf[j].y;
-                        dmma884(cr[i][j][0], cr[i][j][1], ar, br);
-                        dmma884(ci[i][j][0], ci[i][j][1], ar, bi);
-                        dmma884(cr[i][j][0], cr[i][j][1], nai, bi);
-                        dmma884(ci[i][j][0], ci[i][j][1], ai, br);
-                    }
-                }
+                for (int j = 0; j < TN; ++j) bi[j] = sb * bf[j].y;
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) dmma884(cr[i][j][0], cr[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) dmma884(ci[i][j][0], ci[i][j][1], af[i].x, bi[j]);
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) dmma884(cr[i][j][0], cr[i][j][1], -ai[i], bi[j]);
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) dmma884(ci[i][j][0], ci[i][j][1], ai[i], bf[j].x);
             } else {
 #pragma unroll
                 for (int i = 0; i < TM; ++i)
@@ -212,13 +242,12 @@ contract_kernel(const ContractArgs p) {
     }
 }
 
-template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES>
-static int launch_contract(const ContractArgs &a, int batch, cudaStream_t st) {
+template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES, bool AKF, bool BKF>
+static int launch_contract2(const ContractArgs &a, int batch, cudaStream_t st) {
     using T = typename elem_t<CPLX>::type;
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
-    constexpr int LDA = BM + (CPLX ? 2 : 4), LDB = BN + (CPLX ? 2 : 4);
-    constexpr size_t smem = (size_t)STAGES * BK * (LDA + LDB) * sizeof(T);
-    auto kern = contract_kernel<CPLX, BM, BN, BK, WM, WN, STAGES>;
+    constexpr size_t smem = (size_t)STAGES * (TileLayout<CPLX, AKF, BM, BK>::size + TileLayout<CPLX, BKF, BN, BK>::size) * sizeof(T);
+    auto kern = contract_kernel<CPLX, BM, BN, BK, WM, WN, STAGES, AKF, BKF>;
     static bool attr_set = false;
     if (!attr_set) {
         APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -228,6 +257,16 @@ static int launch_contract(const ContractArgs &a, int batch, cudaStream_t st) {
     kern<<<grid, NT, smem, st>>>(a);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
+}
+
+template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES>
+static int launch_contract(const ContractArgs &a, int batch, cudaStream_t st) {
+    if (a.a_kfast) {
+        return a.b_kfast ? launch_contract2<CPLX, BM, BN, BK, WM, WN, STAGES, true, true>(a, batch, st)
+                         : launch_contract2<CPLX, BM, BN, BK, WM, WN, STAGES, true, false>(a, batch, st);
+    }
+    return a.b_kfast ? launch_contract2<CPLX, BM, BN, BK, WM, WN, STAGES, false, true>(a, batch, st)
+                     : launch_contract2<CPLX, BM, BN, BK, WM, WN, STAGES, false, false>(a, batch, st);
 }
 
 }  // namespace apyib
