@@ -47,6 +47,11 @@ SIGNATURES = {
     "apyib_det_matvec": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _int, _vp, _vp, _vp]),
     "apyib_pack_doubles": (_int, [_vp, _i64, _int, _int, _int, _int, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec_work_len": (_i64, [_i64, _i64, _int, _int]),
+    "apyib_lemma_prep_len": (_i64, [_int, _int]),
+    "apyib_lemma_prepare": (_int, [_vp, _int, _int, _int, _vp, _vp]),
+    "apyib_lemma_outer": (_int, [_vp, _int, _int, _int, _int, _vp, _i64, _int, _vp, _i64, _vp, _vp]),
+    "apyib_lemma_matvec_work_len": (_i64, [_i64, _i64, _int, _int]),
+    "apyib_lemma_matvec": (_int, [_vp, _int, _int, _int, _int, _vp, _i64, _int, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp]),
     "apyib_get_slices": (_int, [_int, _int, _int, _int, _i32p]),
     "apyib_det_enumeration": (_int, [_int, _int, _int, _i32p, _i64p, _i32p, _i64p]),
     "apyib_det_index_lists": (_int, [_int, _i32p, _i64, _int, _i32p]),
@@ -82,6 +87,7 @@ _KERNELS_PER_CALL = {
     "apyib_symmetrize_ijab": 1, "apyib_dots": 1, "apyib_diis_push": 1, "apyib_diis_solve": 1,
     "apyib_lincomb_energy_rms": 1, "apyib_iter_advance": 1, "apyib_copy": 1, "apyib_axpby": 1,
     "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_pack_doubles": 1,
+    "apyib_lemma_prepare": 1, "apyib_lemma_outer": 1, "apyib_lemma_matvec": 2,
 }
 LAUNCHES = [0]
 

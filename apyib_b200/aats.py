@@ -59,6 +59,7 @@ class _Tables:
                                                 _i32_host(out)[1]))
             self.L.append(torch.from_numpy(out[:cnt].copy()).to(device()))
         self.doubles_dev = torch.from_numpy(self.doubles.copy()).to(device())
+        self.singles_dev = torch.from_numpy(self.singles.copy()).to(device())
 
     @staticmethod
     def get(no, nf, nv):
@@ -295,83 +296,135 @@ class AAT(object):
         return res
 
     def _block(self, S_host, X1, X2, Y1, Y2):
-        """Contributions of ONE overlap matrix for nx bra and ny ket amplitude sets.
-        Returns dict of [nx, ny] numpy arrays (before the +/- sign and the N factors of S0/0S)."""
+        return self._blocks([S_host], X1, X2, Y1, Y2)[0]
+
+    def _blocks(self, S_hosts, X1, X2, Y1, Y2):
+        """Contributions of a STACK of overlap matrices for nx bra and ny ket amplitude sets, all
+        launches batched over the stack.  Returns one dict per overlap of [nx, ny] numpy arrays
+        (before the +/- sign and the N factors of S0/0S).  config.AAT_ALGORITHM selects how the
+        substituted determinants are evaluated: "lu" (sub-warp LU of every n x n matrix,
+        csrc/dets.cu) or "lemma" (<= 4 x 4 determinants from S_oo^-1, csrc/lemma.cu)."""
         no, nf, nv = self.ndocc, self.nfzc, self.nbf - self.ndocc
         o = no - nf
         cisd = X1 is not None
+        lemma = config.AAT_ALGORITHM == "lemma"
         T = _Tables.get(no, nf, nv)
         R0, R1, R2 = T.L
-        S = to_device(np.asarray(S_host), _C128)
+        nS, ns = len(S_hosts), self.nbf
+        S = to_device(np.stack([np.asarray(x) for x in S_hosts]).astype(np.complex128), _C128)     # [nS, ns, ns]
         nx, ny = X2.shape[0], Y2.shape[0]
-        P = T.n2
-        dS = _det_outer(S, no, R0, R0)                                  # det_S
-        A = _det_outer(S, no, R1, R0).view(o, nv)                       # ia_S
-        B = _det_outer(S, no, R0, R1).view(o, nv)                       # S_kc
-        G = _det_outer(S, no, R1, R1).view(o, nv, o, nv)                # ia_S_kc
-        out = {}
+        P, n1 = T.n2, T.n1
         cn = contract_new
+        X2, Y2 = X2.contiguous(), Y2.contiguous()
+        if lemma:
+            prep = empty((nS, int(lib.apyib_lemma_prep_len(ns, no))), _C128)
+            check(lib.apyib_lemma_prepare(ptr(S), nS, ns, no, ptr(prep), stream_ptr()))
+            subs = {0: None, 1: T.singles_dev, 2: T.doubles_dev}
+            cnt = {0: 1, 1: n1, 2: P}
+
+            def outer(rk, ck):
+                out = empty((nS, cnt[rk], cnt[ck]), _C128)
+                check(lib.apyib_lemma_outer(ptr(prep), nS, ns, no, rk, ptr(subs[rk]), cnt[rk], ck, ptr(subs[ck]),
+                                            cnt[ck], ptr(out), stream_ptr()))
+                return out
+
+            def matvec(rk, ck, Y, per_overlap):
+                """Z[s,q,r] = sum_c D_s[r,c] Y[(s,)q,c]"""
+                Y = Y.contiguous()
+                nq = Y.shape[-2]
+                Z = empty((nS, nq, cnt[rk]), _C128)
+                for q0 in range(0, nq, 4):
+                    q1 = min(nq, q0 + 4)
+                    Yq = Y[..., q0:q1, :].contiguous()
+                    Zq = Z if (q0 == 0 and q1 == nq) else empty((nS, q1 - q0, cnt[rk]), _C128)
+                    work = empty((int(lib.apyib_lemma_matvec_work_len(cnt[rk], cnt[ck], q1 - q0, nS)),), _C128)
+                    with config.timed("lemma_matvec[%d%d,%dx%d,nS=%d]" % (rk, ck, cnt[rk], cnt[ck], nS)):
+                        check(lib.apyib_lemma_matvec(ptr(prep), nS, ns, no, rk, ptr(subs[rk]), cnt[rk], ck,
+                                                     ptr(subs[ck]), cnt[ck], ptr(Yq),
+                                                     (q1 - q0) * cnt[ck] if per_overlap else 0, q1 - q0, ptr(Zq),
+                                                     ptr(work), stream_ptr()))
+                    if Zq is not Z:
+                        Z[:, q0:q1].copy_(Zq)
+                return Z
+        else:
+            L = {0: R0, 1: R1, 2: R2}
+
+            def outer(rk, ck):
+                return torch.stack([_det_outer(S[s], no, L[rk], L[ck]) for s in range(nS)])
+
+            def matvec(rk, ck, Y, per_overlap):
+                return torch.stack([_det_matvec(S[s], no, L[rk], L[ck], Y[s] if per_overlap else Y) for s in range(nS)])
+
+        dS = outer(0, 0).reshape(nS)                                     # det_S
+        A = outer(1, 0).reshape(nS, o, nv)                               # ia_S
+        B = outer(0, 1).reshape(nS, o, nv)                               # S_kc
+        G = outer(1, 1).reshape(nS, o, nv, o, nv)                        # ia_S_kc
+        dd = {}
+        wy = cn("qklcd,sld->sqkc", Y2, B)                                # sum_ld y2[k,l,c,d] S_ld
+        ux = cn("xijab,sjb->sxia", X2, A)                                # sum_jb x2[i,j,a,b] jb_S
+        uxp = cn("xijab,sia->sxjb", X2, A)                               # sum_ia x2[i,j,a,b] ia_S
+        T1 = cn("siakc,qklcd->sqiald", G, Y2)
+        Z = cn("sqiald,sjbld->sqiajb", T1, G)
+        dd["c6"] = cn("xijab,sqiajb->sxq", X2, Z)
         if P:
-            D20 = _det_outer(S, no, R2, R0).view(1, P)                  # iajb_S  (restricted)
-            D02 = _det_outer(S, no, R0, R2).view(1, P)                  # S_kcld  (restricted)
+            D20 = outer(2, 0).reshape(nS, P)                             # iajb_S  (restricted)
+            D02 = outer(0, 2).reshape(nS, P)                             # S_kcld  (restricted)
             Xh, Yh = empty((nx, P), _C128), empty((ny, P), _C128)
             n2 = o * o * nv * nv
             check(lib.apyib_pack_doubles(ptr(X2), n2, nx, o, nv, nf, ptr(T.doubles_dev), P, ptr(Xh), stream_ptr()))
             check(lib.apyib_pack_doubles(ptr(Y2), n2, ny, o, nv, nf, ptr(T.doubles_dev), P, ptr(Yh), stream_ptr()))
-        wy = cn("qklcd,ld->qkc", Y2, B)                                 # sum_ld y2[k,l,c,d] S_ld
-        ux = cn("xijab,jb->xia", X2, A)                                 # sum_jb x2[i,j,a,b] jb_S
-        uxp = cn("xijab,ia->xjb", X2, A)                                # sum_ia x2[i,j,a,b] ia_S
-        T1 = cn("iakc,qklcd->qiald", G, Y2)
-        Z = cn("qiald,jbld->qiajb", T1, G)
-        dd = {"c6": cn("xijab,qiajb->xq", X2, Z)}
-        if P:
-            z22 = _det_matvec(S, no, R2, R2, Yh)                         # the P x P table, fused
-            ys = [wy.reshape(ny, -1)] + ([Y1.reshape(ny, -1)] if cisd else [])
-            z21 = _det_matvec(S, no, R2, R1, torch.cat(ys, 0))
-            z12 = _det_matvec(S, no, R1, R2, Yh)
-            dd["c1"] = cn("xr,qr->xq", Xh, z22)
-            dd["v1"] = cn("xr,qr->xq", Xh, D20)
-            dd["v2"] = cn("xr,qr->xq", D02, Yh)
-            dd["c3"] = cn("xr,qr->xq", Xh, z21[:ny])
-            uxs = _axpby(1.0, uxp, 1.0, ux.clone())                      # ux + ux' 
-            dd["c4"] = cn("xr,qr->xq", uxs.reshape(nx, -1), z12)
+            z22 = matvec(2, 2, Yh, False)                                # the P x P table, fused      [s,q,r]
+            ys = [wy.reshape(nS, ny, -1)] + ([Y1.reshape(1, ny, -1).expand(nS, ny, n1)] if cisd else [])
+            z21 = matvec(2, 1, torch.cat(ys, 1).contiguous(), True)      # [s, ny(+ny), P]
+            z12 = matvec(1, 2, Yh, False)                                # [s, q, ov]
+            dd["c1"] = cn("xr,sqr->sxq", Xh, z22)
+            dd["v1"] = cn("xr,sr->sx", Xh, D20)
+            dd["v2"] = cn("sr,qr->sq", D02, Yh)
+            dd["c3"] = cn("xr,sqr->sxq", Xh, z21[:, :ny])
+            uxs = _axpby(1.0, uxp, 1.0, ux.clone())                      # ux + ux'
+            dd["c4"] = cn("sxr,sqr->sxq", uxs.reshape(nS, nx, -1), z12)
         if cisd:
-            Gy1 = cn("iakc,qkc->qia", G, Y1)
-            Gwy = cn("iakc,qkc->qia", G, wy)
-            dd["s_xGy"] = cn("xia,qia->xq", X1, Gy1)
-            dd["s_xA"] = cn("xia,qia->xq", X1, A[None])
-            dd["s_yB"] = cn("xkc,qkc->xq", B[None], Y1)
-            dd["ds3"] = cn("xia,qia->xq", ux, Gy1)
-            dd["sd3"] = cn("xia,qia->xq", X1, Gwy)
-            dd["d0b"] = cn("xjb,qjb->xq", uxp, A[None])
-            dd["0db"] = cn("xkc,qkc->xq", B[None], wy)
+            Gy1 = cn("siakc,qkc->sqia", G, Y1)
+            Gwy = cn("siakc,sqkc->sqia", G, wy)
+            dd["s_xGy"] = cn("xia,sqia->sxq", X1, Gy1)
+            dd["s_xA"] = cn("xia,sia->sx", X1, A)
+            dd["s_yB"] = cn("skc,qkc->sq", B, Y1)
+            dd["ds3"] = cn("sxia,sqia->sxq", ux, Gy1)
+            dd["sd3"] = cn("xia,sqia->sxq", X1, Gwy)
+            dd["d0b"] = cn("sxjb,sjb->sx", uxp, A)
+            dd["0db"] = cn("skc,sqkc->sq", B, wy)
             if P:
-                dd["ds1"] = cn("xr,qr->xq", Xh, z21[ny:])
-                dd["sd1"] = cn("xr,qr->xq", X1.reshape(nx, -1), z12)
-        # one device->host copy for all the small result matrices of this block
+                dd["ds1"] = cn("xr,sqr->sxq", Xh, z21[:, ny:])
+                dd["sd1"] = cn("xr,sqr->sxq", X1.reshape(nx, -1), z12)
+        # one device->host copy for all the small result tensors of the stack
         keys = list(dd)
         flat = torch.cat([dS.reshape(-1)] + [dd[k].reshape(-1) for k in keys])
         fh = to_host(flat)
-        dSh = complex(fh[0])
-        h, off = {}, 1
+        dSh_all = fh[:nS]
+        h, off = {}, nS
         for k in keys:
             n_el = dd[k].numel()
             h[k] = fh[off:off + n_el].reshape(tuple(dd[k].shape))
             off += n_el
-        zero = np.zeros((nx, ny), dtype=np.complex128)
-        g = lambda k: h.get(k, zero)
-        v1, v2 = g("v1"), g("v2")                                        # [nx,1], [1,ny]
-        out["DD"] = 0.125 * (dSh * g("c1") + v1 * v2 + 4 * g("c3") + 2 * g("c4") + 8 * g("c6"))
-        if cisd:
-            xA, yB = g("s_xA"), g("s_yB")
-            out["SS"] = 2 * (dSh * g("s_xGy") + xA * yB)
-            out["DS"] = 0.5 * dSh * g("ds1") + 0.5 * v1 * yB + 2 * g("ds3")
-            out["SD"] = 0.5 * dSh * g("sd1") + 0.5 * xA * v2 + 2 * g("sd3")
-            out["S0"] = 2 * xA * dSh + zero
-            out["0S"] = 2 * yB * dSh + zero
-            out["D0"] = 0.5 * v1 * dSh + g("d0b") + zero
-            out["0D"] = 0.5 * v2 * dSh + g("0db") + zero
-        return out
+        res = []
+        for s in range(nS):
+            dSh = complex(dSh_all[s])
+            zero = np.zeros((nx, ny), dtype=np.complex128)
+            g = lambda k: h[k][s] if k in h else zero
+            v1 = g("v1").reshape(nx, 1) if "v1" in h else np.zeros((nx, 1), dtype=np.complex128)
+            v2 = g("v2").reshape(1, ny) if "v2" in h else np.zeros((1, ny), dtype=np.complex128)
+            out = {"DD": 0.125 * (dSh * g("c1") + v1 * v2 + 4 * g("c3") + 2 * g("c4") + 8 * g("c6"))}
+            if cisd:
+                xA, yB = g("s_xA").reshape(nx, 1), g("s_yB").reshape(1, ny)
+                out["SS"] = 2 * (dSh * g("s_xGy") + xA * yB)
+                out["DS"] = 0.5 * dSh * g("ds1") + 0.5 * v1 * yB + 2 * g("ds3")
+                out["SD"] = 0.5 * dSh * g("sd1") + 0.5 * xA * v2 + 2 * g("sd3")
+                out["S0"] = 2 * xA * dSh + zero
+                out["0S"] = 2 * yB * dSh + zero
+                out["D0"] = 0.5 * v1 * dSh + g("d0b").reshape(nx, 1) + zero
+                out["0D"] = 0.5 * v2 * dSh + g("0db").reshape(1, ny) + zero
+            res.append(out)
+        return res
 
     def _spatial_terms(self, alpha, beta, normalization):
         m = self.parameters["method"]
@@ -418,11 +471,16 @@ class AAT(object):
         add(cached(("un", b), self.overlap_un[b], "dR", "t"), -1, a, 0, s0_N=N_mn[b], d0=True)
         add(cached(("pu", a), self.overlap_pu[a], "tc", "dH"), +1, 0, b, os_N=N_np[a], od=True)
         add(cached(("nu", a), self.overlap_nu[a], "tc", "dH"), -1, 0, b, os_N=N_nn[a], od=True)
-        blk = lambda S: self._block(S, pick(A1, "tc"), A2["tc"], pick(A1, "t"), A2["t"])
-        add(blk(self.overlap_pp[a][b]), +1, 0, 0, s0_N=N_mp[b], os_N=N_np[a], d0=True, od=True)
-        add(blk(self.overlap_pn[a][b]), -1, 0, 0, s0_N=N_mn[b], os_N=N_np[a], d0=True, od=True)
-        add(blk(self.overlap_np[a][b]), -1, 0, 0, s0_N=N_mp[b], os_N=N_nn[a], d0=True, od=True)
-        add(blk(self.overlap_nn[a][b]), +1, 0, 0, s0_N=N_mn[b], os_N=N_nn[a], d0=True, od=True)
+        key = ("blk4", a, normalization)
+        if key not in self._cache:       # the 12 (beta x pp/pn/np/nn) overlaps of this alpha in one stack
+            stack = [m[a][bb] for bb in range(3) for m in (self.overlap_pp, self.overlap_pn, self.overlap_np,
+                                                              self.overlap_nn)]
+            self._cache[key] = self._blocks(stack, pick(A1, "tc"), A2["tc"], pick(A1, "t"), A2["t"])
+        r4 = self._cache[key][4 * b:4 * b + 4]
+        add(r4[0], +1, 0, 0, s0_N=N_mp[b], os_N=N_np[a], d0=True, od=True)
+        add(r4[1], -1, 0, 0, s0_N=N_mn[b], os_N=N_np[a], d0=True, od=True)
+        add(r4[2], -1, 0, 0, s0_N=N_mp[b], os_N=N_nn[a], d0=True, od=True)
+        add(r4[3], +1, 0, 0, s0_N=N_mn[b], os_N=N_nn[a], d0=True, od=True)
         return I
 
     def compute_spatial_aats(self, alpha, beta, normalization="full"):

@@ -29,3 +29,9 @@ def timed(name):
         e1.record()
         TIMING.setdefault(name, []).append((e0, e1))
     return _cm()
+
+# How the substituted determinants of the AAT assembly are evaluated:
+#   "lu"    : sub-warp LU with partial pivoting of every n x n matrix (csrc/dets.cu; the north star's
+#             "batched small-LU/determinant kernel")
+#   "lemma" : <= 4 x 4 determinants from S_oo^-1 (csrc/lemma.cu), same results
+AAT_ALGORITHM = "lu"

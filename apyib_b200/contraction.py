@@ -41,14 +41,17 @@ def _plan(spec, A, B, out):
     for s, t in ((sa, A), (sb, B), (o, out)):
         for ch, d in zip(s, t.shape):
             assert size.setdefault(ch, d) == d, "inconsistent size for index %s in %s" % (ch, spec)
+    b_idx = [ch for ch in o if ch in sa and ch in sb]          # batch index (at most one)
     m_idx = [ch for ch in o if ch in sa and ch not in sb]
     n_idx = [ch for ch in o if ch in sb and ch not in sa]
     k_idx = [ch for ch in sa if ch in sb and ch not in o]
-    assert len(m_idx) + len(n_idx) == len(o), "batch / repeated output indices unsupported: " + spec
-    assert set(sa) == set(m_idx) | set(k_idx) and set(sb) == set(n_idx) | set(k_idx), \
-        "every index must be m, n or k: " + spec
+    assert len(b_idx) <= 1, "at most one batch index: " + spec
+    assert len(m_idx) + len(n_idx) + len(b_idx) == len(o), "repeated output indices unsupported: " + spec
+    assert set(sa) == set(m_idx) | set(k_idx) | set(b_idx) and set(sb) == set(n_idx) | set(k_idx) | set(b_idx), \
+        "every index must be batch, m, n or k: " + spec
     st = lambda s, t: dict(zip(s, t.stride()))
     stA, stB, stO = st(sa, A), st(sb, B), st(o, out)
+    batch = (size[b_idx[0]], stA[b_idx[0]], stB[b_idx[0]], stO[b_idx[0]]) if b_idx else (1, 0, 0, 0)
     # order k by A's layout (largest stride first) so that the fastest k index is contiguous in A if possible
     k_idx.sort(key=lambda ch: -stA[ch])
     dims = lambda idx: [size[ch] for ch in idx]
@@ -70,7 +73,7 @@ def _plan(spec, A, B, out):
     for s in sizes:
         ptrs.append(dev.data_ptr() + 8 * off)
         off += s
-    p = (M, N, K, ptrs, a_kfast, b_kfast, dev)
+    p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch)
     _table_cache[key] = p
     return p
 
@@ -78,22 +81,22 @@ def _plan(spec, A, B, out):
 def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
     """out = alpha * einsum(spec, op(A), op(B)) + beta * out, on the current stream."""
     assert A.dtype == B.dtype == out.dtype, "mixed dtypes: %s %s %s" % (A.dtype, B.dtype, out.dtype)
-    M, N, K, ptrs, a_kfast, b_kfast, _keep = _plan(spec, A, B, out)
+    M, N, K, ptrs, a_kfast, b_kfast, _keep, batch = _plan(spec, A, B, out)
     alpha, beta = complex(alpha), complex(beta)
     if config.TIMING is not None:
         with config.timed("contract[%s %dx%dx%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K)):
-            check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta))
+            check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch))
         return out
-    check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta))
+    check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch))
     return out
 
 
-def _launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta):
+def _launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch):
     return (lib.apyib_contract(dtype_code(A), ptr(A), ptr(B), ptr(out), M, N, K,
                              *[C.c_void_p(p) for p in ptrs],
                              a_kfast, b_kfast, int(conj_a), int(conj_b),
                              alpha.real, alpha.imag, beta.real, beta.imag,
-                             1, 0, 0, 0, C.c_void_p(0), stream_ptr()))
+                             batch[0], batch[1], batch[2], batch[3], C.c_void_p(0), stream_ptr()))
 
 
 def contract_new(spec, A, B, alpha=1.0, conj_a=False, conj_b=False):

@@ -188,6 +188,25 @@ int64_t apyib_det_matvec_work_len(int64_t nrow, int64_t ncol, int ny, int n);
 int apyib_pack_doubles(const void *d_x, int64_t x_stride, int nq, int o, int v, int nf,
                        const int32_t *d_doubles, int64_t P, void *d_out, void *stream);
 
+/* ---- determinant-lemma path: the same determinants from A = S_oo,
+ * P = S_vo A^-1, Q = A^-1 S_ov, R = S_vv - S_vo A^-1 S_ov:
+ *   det = det(A) (-1)^c det[[P[a,i'], R[a,c']], [A^-1[k,i'], -Q[k,c']]]   ((r+c) x (r+c) <= 4 x 4)
+ * apyib_lemma_prepare: for a stack of nS overlaps (ns x ns, occupied block no x no) writes, per
+ *   overlap, apyib_lemma_prep_len() complex numbers: det(A) | A^-1 | P | Q | R.
+ * apyib_lemma_outer / apyib_lemma_matvec: as apyib_det_outer / apyib_det_matvec, but rows and
+ *   columns are given as substitution tuples (rk, ck in {0,1,2} pairs (occupied, virtual) per
+ *   entry, the enumeration of apyib_det_enumeration) and all nS overlaps are processed in one
+ *   launch: out[(s*nrow + r)*ncol + c], Z[(s*ny + q)*nrow + r]; overlap s reads its vectors at
+ *   Y + s*y_sstride (y_sstride = 0: the same Y for every overlap).                              */
+int64_t apyib_lemma_prep_len(int ns, int no);
+int apyib_lemma_prepare(const void *d_S, int nS, int ns, int no, void *d_prep, void *stream);
+int apyib_lemma_outer(const void *d_prep, int nS, int ns, int no, int rk, const int32_t *d_rsub, int64_t nrow,
+                      int ck, const int32_t *d_csub, int64_t ncol, void *d_out, void *stream);
+int64_t apyib_lemma_matvec_work_len(int64_t nrow, int64_t ncol, int ny, int nS);
+int apyib_lemma_matvec(const void *d_prep, int nS, int ns, int no, int rk, const int32_t *d_rsub, int64_t nrow,
+                       int ck, const int32_t *d_csub, int64_t ncol, const void *d_Y, int64_t y_sstride, int ny,
+                       void *d_Z, void *d_work, void *stream);
+
 /* Host-side, bit-exact index tables ---------------------------------------------
  * get_slices (utils.py:184-213): bounds[0..7] = C_list f,o,v,t (start,stop pairs
  * flattened f0,f1,o0,o1,...) ; bounds[8..15] = I_list.                               */

@@ -22,6 +22,15 @@ PARTS = ("overlap_uu", "overlap_up", "overlap_un", "overlap_pu", "overlap_nu", "
          "overlap_np", "overlap_nn", "unperturbed_T", "nuc_pos_T", "nuc_neg_T", "mag_pos_T", "mag_neg_T")
 
 
+@pytest.fixture(params=["lu", "lemma"])
+def algo(request):
+    import apyib_b200
+    old = apyib_b200.config.AAT_ALGORITHM
+    apyib_b200.config.AAT_ALGORITHM = request.param
+    yield request.param
+    apyib_b200.config.AAT_ALGORITHM = old
+
+
 def gpu_aat(A):
     from apyib_b200.aats import AAT
     return AAT.from_parts(A.method, A.nbf, A.ndocc, A.nfzc, A.nuc_pert_strength, A.mag_pert_strength,
@@ -58,7 +67,7 @@ def test_compute_SO_det():
 
 @pytest.mark.parametrize("method,nbf,no,nf,seed", AAT_SPATIAL + [("CISD", 8, 4, 1, 111), ("CID", 9, 3, 0, 112)])
 @pytest.mark.parametrize("norm", ["full", "intermediate"])
-def test_spatial_aats_vs_oracle(method, nbf, no, nf, seed, norm):
+def test_spatial_aats_vs_oracle(method, nbf, no, nf, seed, norm, algo):
     A = orc.synthetic_aat_inputs(method, nbf, no, nf, 1, seed, h=1e-3)
     G = gpu_aat(A)
     got = np.array([[G.compute_spatial_aats(a, b, norm) for b in range(3)] for a in range(3)])
@@ -69,7 +78,7 @@ def test_spatial_aats_vs_oracle(method, nbf, no, nf, seed, norm):
         assert np.abs(got - AATG[key]).max() < 1e-8 * max(1.0, np.abs(AATG[key]).max())
 
 
-def test_spatial_terms_resolved_vs_oracle():
+def test_spatial_terms_resolved_vs_oracle(algo):
     A = orc.synthetic_aat_inputs("CISD", 7, 3, 1, 1, 113, h=1e-3)
     G = gpu_aat(A)
     got = G._spatial_terms(2, 1, "full")
@@ -111,7 +120,7 @@ E2E = [c for c in LIT["cases"] if c.get("route") == "parallel"]
 
 
 @pytest.mark.parametrize("c", E2E, ids=lambda c: c["test"])
-def test_h2_2_compute_parallel_aats_vs_reference_literals(c):
+def test_h2_2_compute_parallel_aats_vs_reference_literals(c, algo):
     from apyib_b200.parallel import compute_parallel_aats
     p = _params(c)
     I = compute_parallel_aats(p, c["h_R"], c["h_B"], normalization=c["normalization"])
@@ -121,7 +130,7 @@ def test_h2_2_compute_parallel_aats_vs_reference_literals(c):
     assert p["F_mag"] == [0.0, 0.0, 0.0] and p["geom"].split()[:4] == LIT["geom"].split()[:4] or True
 
 
-def test_synthetic_molecule_pipeline_vs_oracle_pipeline():
+def test_synthetic_molecule_pipeline_vs_oracle_pipeline(algo):
     """full FD pipeline (SCF on host, phase fix, CISD on GPU, overlaps, dets) on a synthetic
     'molecule' with frozen core vs the same pipeline evaluated with the oracle"""
     from apyib_b200 import hostchem as hc
@@ -151,3 +160,32 @@ def test_apt_pipeline_vs_oracle_pipeline():
     want = fp.compute_APT(mk(), 1e-3, 1e-4)
     assert got.shape == (3, 3)
     assert np.abs(got - want).max() < 1e-5       # reference's APT tolerance (test_010_APT.py)
+
+
+@pytest.mark.parametrize("nbf,no,nf", [(9, 4, 1), (12, 5, 0), (7, 2, 0)])
+def test_lemma_tables_match_lu_tables(nbf, no, nf):
+    """every determinant family of compute_all_dets: lemma kernel vs sub-warp LU kernel"""
+    import torch
+    from apyib_b200._lib import lib, check
+    from apyib_b200.aats import _Tables, _det_outer
+    from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
+    rng = np.random.default_rng(nbf)
+    nv = nbf - no
+    T = _Tables.get(no, nf, nv)
+    for h in (1e-4, 0.3):
+        Ss = [np.eye(nbf) + h * (rng.standard_normal((nbf, nbf)) + 0.1j * rng.standard_normal((nbf, nbf))) for _ in range(3)]
+        S = to_device(np.stack(Ss), torch.complex128)
+        prep = empty((3, int(lib.apyib_lemma_prep_len(nbf, no))), torch.complex128)
+        check(lib.apyib_lemma_prepare(ptr(S), 3, nbf, no, ptr(prep), stream_ptr()))
+        subs = {0: None, 1: T.singles_dev, 2: T.doubles_dev}
+        cnt = {0: 1, 1: T.n1, 2: T.n2}
+        for rk in range(3):
+            for ck in range(3):
+                out = empty((3, cnt[rk], cnt[ck]), torch.complex128)
+                check(lib.apyib_lemma_outer(ptr(prep), 3, nbf, no, rk, ptr(subs[rk]), cnt[rk], ck, ptr(subs[ck]), cnt[ck],
+                                            ptr(out), stream_ptr()))
+                got = to_host(out)
+                for s in range(3):
+                    want = to_host(_det_outer(S[s], no, T.L[rk], T.L[ck]))
+                    scale = max(1e-300, np.abs(want).max())
+                    assert np.abs(got[s] - want).max() < 1e-12 * max(scale, h ** (rk + ck)), (rk, ck, h)
