@@ -114,29 +114,44 @@ mp2_kernel(const T *eri, int64_t n, int64_t o, const double *eps, T *t2, double 
 // --------------------------------------------------------------------------------------
 // CI update  r <- r - E t ; t <- t + r / D
 // --------------------------------------------------------------------------------------
+// Streaming kernels keep U independent 16-byte loads per array and thread in flight: the loaded
+// HBM latency on B200 is ~2 us, so one load per thread (32 KB per SM at full occupancy) caps a
+// kernel at ~2.7 TB/s of reads (measured, profiles/r01_streaming_roofline_v1.json).
+constexpr int kUnroll = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-ci_update_kernel(T *r, T *t, const double *E, const double *eps_o, const double *eps_v, int64_t o, int64_t v,
-                 int64_t n1, int64_t n2, int sh) {
+ci_update_kernel(T *__restrict__ r, T *__restrict__ t, const double *__restrict__ E, const double *__restrict__ eps_o,
+                 const double *__restrict__ eps_v, int64_t o, int64_t v, int64_t n1, int64_t n2, int sh) {
     const T Ec = scalar<T>::make(E[0], E[1]);
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        double D;
-        if (idx < n1) {
-            const int64_t a = idx % v, i = idx / v;
-            D = eps_o[i >> sh] - eps_v[a >> sh];
-        } else {
-            int64_t q = idx - n1;
-            const int64_t b = q % v; q /= v;
-            const int64_t a = q % v; q /= v;
-            const int64_t j = q % o;
-            const int64_t i = q / o;
-            D = eps_o[i >> sh] + eps_o[j >> sh] - eps_v[a >> sh] - eps_v[b >> sh];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, len = n1 + n2;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += kUnroll * stride) {
+        T tv[kUnroll], rv[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + u * stride;
+            if (idx < len) { tv[u] = t[idx]; rv[u] = r[idx]; }
         }
-        const T tv = t[idx];
-        const T rv = r[idx] - Ec * tv;
-        r[idx] = rv;
-        t[idx] = tv + scalar<T>::div_real(rv, D);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t idx = base + u * stride;
+            if (idx >= len) continue;
+            double D;
+            if (idx < n1) {
+                const int64_t a = idx % v, i = idx / v;
+                D = eps_o[i >> sh] - eps_v[a >> sh];
+            } else {
+                int64_t q = idx - n1;
+                const int64_t b = q % v; q /= v;
+                const int64_t a = q % v; q /= v;
+                const int64_t j = q % o;
+                const int64_t i = q / o;
+                D = eps_o[i >> sh] + eps_o[j >> sh] - eps_v[a >> sh] - eps_v[b >> sh];
+            }
+            const T rn = rv[u] - Ec * tv[u];
+            r[idx] = rn;
+            t[idx] = tv[u] + scalar<T>::div_real(rn, D);
+        }
     }
 }
 
@@ -159,23 +174,52 @@ __global__ void __launch_bounds__(kThreads) symmetrize_kernel(const T *h, T *out
 // --------------------------------------------------------------------------------------
 constexpr int kMaxVec = 8;
 
+// single-vector dot (energies, norms): 2 accumulators, 8 independent element pairs in flight
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-dots_kernel(const T *x, int64_t xs, int nvec, const T *y, int64_t len, int conj_x, double *out, double *partials) {
+dot1_kernel(const T *__restrict__ x, const T *__restrict__ y, int64_t len, int conj_x, double *out, double *partials) {
+    double acc[2] = {0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 8;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += U * stride) {
+        T xv[U], yv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * stride;
+            xv[u] = (i < len) ? x[i] : scalar<T>::zero();
+            yv[u] = (i < len) ? y[i] : scalar<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const T p = (conj_x ? scalar<T>::cj(xv[u]) : xv[u]) * yv[u];
+            acc[0] += scalar<T>::re(p);
+            acc[1] += scalar<T>::im(p);
+        }
+    }
+    grid_sum_finish<2, kThreads>(acc, partials, [&](double(&tot)[2]) {
+        out[0] = tot[0];
+        out[1] = tot[1];
+    });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+dots_kernel(const T *__restrict__ x, int64_t xs, int nvec, const T *__restrict__ y, int64_t len, int conj_x,
+            double *out, double *partials) {
     double acc[2 * kMaxVec];
 #pragma unroll
     for (int k = 0; k < 2 * kMaxVec; ++k) acc[k] = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
         const T yv = y[i];
+        T xv[kMaxVec];
+#pragma unroll
+        for (int j = 0; j < kMaxVec; ++j) xv[j] = (j < nvec) ? x[(int64_t)j * xs + i] : scalar<T>::zero();
 #pragma unroll
         for (int j = 0; j < kMaxVec; ++j) {
-            if (j < nvec) {
-                T xv = x[(int64_t)j * xs + i];
-                if (conj_x) xv = scalar<T>::cj(xv);
-                const T p = xv * yv;
-                acc[2 * j] += scalar<T>::re(p);
-                acc[2 * j + 1] += scalar<T>::im(p);
-            }
+            const T p = (conj_x ? scalar<T>::cj(xv[j]) : xv[j]) * yv;
+            acc[2 * j] += scalar<T>::re(p);
+            acc[2 * j + 1] += scalar<T>::im(p);
         }
     }
     grid_sum_finish<2 * kMaxVec, kThreads>(acc, partials, [&](double(&tot)[2 * kMaxVec]) {
@@ -191,23 +235,39 @@ dots_kernel(const T *x, int64_t xs, int nvec, const T *y, int64_t len, int conj_
 // iteration, only one row/column actually changes).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-diis_push_kernel(const T *r, const T *t, T *hist_e, T *hist_t, int64_t len, const int *iter, double *B,
-                 double *partials) {
+diis_push_kernel(const T *__restrict__ r, const T *__restrict__ t, T *__restrict__ hist_e, T *__restrict__ hist_t,
+                 int64_t len, const int *iter, double *B, double *partials) {
     const int it = *iter;
     const int slot = (it - 1) % kMaxVec;
     const int m = it < kMaxVec ? it : kMaxVec;
     double acc[2 * kMaxVec];
 #pragma unroll
     for (int k = 0; k < 2 * kMaxVec; ++k) acc[k] = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
-        const T rv = r[i];
-        hist_e[(int64_t)slot * len + i] = rv;
-        hist_t[(int64_t)slot * len + i] = t[i];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 2;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += U * stride) {
+        T rv[U], tv[U], ev[U][kMaxVec];
 #pragma unroll
-        for (int j = 0; j < kMaxVec; ++j) {
-            if (j < m) {
-                const T ev = (j == slot) ? rv : hist_e[(int64_t)j * len + i];
-                const T p = scalar<T>::cj(ev) * rv;     // <e_j | e_slot>
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * stride;
+            const bool ok = i < len;
+            rv[u] = ok ? r[i] : scalar<T>::zero();
+            tv[u] = ok ? t[i] : scalar<T>::zero();
+#pragma unroll
+            for (int j = 0; j < kMaxVec; ++j)
+                ev[u][j] = (ok && j < m && j != slot) ? hist_e[(int64_t)j * len + i] : scalar<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * stride;
+            if (i < len) {
+                hist_e[(int64_t)slot * len + i] = rv[u];
+                hist_t[(int64_t)slot * len + i] = tv[u];
+            }
+#pragma unroll
+            for (int j = 0; j < kMaxVec; ++j) {
+                const T e = (j == slot) ? rv[u] : ev[u][j];
+                const T p = scalar<T>::cj(e) * rv[u];     // <e_j | e_slot>
                 acc[2 * j] += scalar<T>::re(p);
                 acc[2 * j + 1] += scalar<T>::im(p);
             }
@@ -285,25 +345,42 @@ lincomb_kernel(const T *hist, int64_t hs, const int *iter, int m_fixed, const do
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) cj[j] = (j < m) ? scalar<T>::make(c[2 * j], c[2 * j + 1]) : scalar<T>::zero();
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
-        T tv;
-        if (m > 0) {
-            tv = scalar<T>::zero();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 2;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += U * stride) {
+        T hv[U][kMaxVec], wv[U], ov[U], tcur[U];
 #pragma unroll
-            for (int j = 0; j < kMaxVec; ++j)
-                if (j < m) tv = tv + cj[j] * hist[(int64_t)j * hs + i];
-            t[i] = tv;
-        } else {
-            tv = t[i];
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * stride;
+            const bool ok = i < len;
+#pragma unroll
+            for (int j = 0; j < kMaxVec; ++j) hv[u][j] = (ok && j < m) ? hist[(int64_t)j * hs + i] : scalar<T>::zero();
+            wv[u] = ok ? w[i] : scalar<T>::zero();
+            ov[u] = ok ? t_old[i] : scalar<T>::zero();
+            tcur[u] = (ok && m == 0) ? t[i] : scalar<T>::zero();
         }
-        const T e = w[i] * tv;
-        acc[0] += scalar<T>::re(e);
-        acc[1] += scalar<T>::im(e);
-        const T d = t_old[i] - tv;
-        const T d2 = d * d;
-        const int k = (i < n1) ? 2 : 4;
-        acc[k] += scalar<T>::re(d2);
-        acc[k + 1] += scalar<T>::im(d2);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * stride;
+            if (i >= len) continue;
+            T tv;
+            if (m > 0) {
+                tv = scalar<T>::zero();
+#pragma unroll
+                for (int j = 0; j < kMaxVec; ++j) tv = tv + cj[j] * hv[u][j];
+                t[i] = tv;
+            } else {
+                tv = tcur[u];
+            }
+            const T e = wv[u] * tv;
+            acc[0] += scalar<T>::re(e);
+            acc[1] += scalar<T>::im(e);
+            const T d = ov[u] - tv;
+            const T d2 = d * d;
+            const int k = (i < n1) ? 2 : 4;
+            acc[k] += scalar<T>::re(d2);
+            acc[k + 1] += scalar<T>::im(d2);
+        }
     }
     grid_sum_finish<6, kThreads>(acc, partials, [&](double(&tot)[6]) {
 #pragma unroll
@@ -315,9 +392,18 @@ __global__ void iter_advance_kernel(int *iter) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *iter += 1;
 }
 
-template <typename T> __global__ void __launch_bounds__(kThreads) copy_kernel(T *dst, const T *src, int64_t len) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = src[i];
+template <typename T>
+__global__ void __launch_bounds__(kThreads) copy_kernel(T *__restrict__ dst, const T *__restrict__ src, int64_t len) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += kUnroll * stride) {
+        T v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + u * stride < len) v[u] = src[base + u * stride];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + u * stride < len) dst[base + u * stride] = v[u];
+    }
 }
 
 // y <- alpha * op(x) + beta * y   (beta == 0: y is write-only)
@@ -465,6 +551,14 @@ extern "C" int apyib_dots(int dtype, const void *d_x, int64_t x_stride, int nvec
     APYIB_REQUIRE(nvec >= 1 && nvec <= kMaxVec, "nvec");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = stream_grid(len);
+    if (nvec == 1) {
+        if (dtype == APYIB_C128)
+            dot1_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_x, (const cplx *)d_y, len, conj_x, d_out, d_partials);
+        else
+            dot1_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_x, (const double *)d_y, len, conj_x, d_out, d_partials);
+        APYIB_LAUNCH_CHECK();
+        return APYIB_OK;
+    }
     if (dtype == APYIB_C128)
         dots_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_x, x_stride, nvec, (const cplx *)d_y, len, conj_x, d_out, d_partials);
     else
