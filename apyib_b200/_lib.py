@@ -34,12 +34,12 @@ SIGNATURES = {
     "apyib_gather2": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _vp]),
     "apyib_mp2_t2_energy": (_int, [_int, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp]),
     "apyib_reduce_scratch_len": (_i64, []),
-    "apyib_ci_update": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _vp]),
+    "apyib_ci_update": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
     "apyib_symmetrize_ijab": (_int, [_int, _vp, _vp, _i64, _i64, _vp]),
     "apyib_dots": (_int, [_int, _vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp]),
-    "apyib_diis_push": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
-    "apyib_diis_solve": (_int, [_int, _vp, _int, _int, _vp, _vp, _vp]),
-    "apyib_lincomb_energy_rms": (_int, [_int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "apyib_diis_push": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _int, _vp, _vp]),
+    "apyib_diis_solve": (_int, [_int, _vp, _int, _int, _vp, _vp, _int, _vp, _vp]),
+    "apyib_lincomb_energy_rms": (_int, [_int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
     "apyib_iter_advance": (_int, [_vp, _vp]),
     "apyib_copy": (_int, [_int, _vp, _vp, _i64, _vp]),
     "apyib_axpby": (_int, [_int, _i64, _dbl, _dbl, _vp, _int, _dbl, _dbl, _vp, _vp]),

@@ -9,8 +9,14 @@ solve methods and return shapes.  Everything between "integrals are on the devic
   * `r -= E t; t += r/D`, the DIIS Gram row, the bordered solve, the extrapolation, the new energy
     and both rms sums are streaming / tiny kernels with deterministic reductions;
   * the iteration counter, energy and DIIS state live on the device, so one captured CUDA graph
-    replays every iteration; the host only reads back 6 doubles per iteration for the
-    convergence test (which keeps the reference's exact semantics, ci_wfn.py:123-130).
+    replays every iteration; the host only reads back 6 doubles per point and iteration for the
+    convergence test (which keeps the reference's exact semantics, ci_wfn.py:123-130);
+  * BATCHED SOLVES: `solve_batch` advances many finite-difference points (same shapes and
+    dtype, each with its own integrals) with the same launches -- every tensor carries a leading
+    point index that the contraction kernel treats as its batch dimension.  A point that meets
+    the reference's convergence test is frozen by a device-side `active` flag, i.e. it stops
+    exactly where the reference's loop `break`s.  The finite-difference driver uses this to fill the
+    GPU with the 6N+7 tiny solves of one molecule.
 """
 from __future__ import annotations
 
@@ -22,14 +28,13 @@ import torch
 from . import config
 from ._lib import lib, check
 from .contraction import contract
-from .device import (to_device, to_host, empty, zeros, dtype_code, ptr, stream_ptr, reduce_scratch, i32, i64,
-                     Graph)
+from .device import (to_device, to_host, empty, zeros, ptr, stream_ptr, Graph)
 from .utils import (get_slices, compute_F_MO_dev, compute_ERI_MO_dev, spin_block_2_dev, gather4)
 
 _NULL = C.c_void_p(0)
 
 
-def w_block(E, labels, out_labels, space, bounds, spin=0, c1=1.0, c2=0.0):
+def w_block(E, labels, out_labels, space, bounds, spin=0, c1=1.0, c2=0.0, out=None):
     """Dense block of the physicists' integrals W[p,q,r,s] = (pr|qs) built from the chemists'
     tensor E (optionally spin-blocked on the fly):
         out[out_labels] = c1 * W[labels] + c2 * W[labels with the last two swapped]
@@ -40,90 +45,111 @@ def w_block(E, labels, out_labels, space, bounds, spin=0, c1=1.0, c2=0.0):
     shape = [bounds[space[ch]][1] - bounds[space[ch]][0] for ch in out_labels]
     perm = lambda src: [out_labels.index(ch) for ch in src]
     start = lambda src: [bounds[space[ch]][0] for ch in src]
-    return gather4(E, spin, shape, perm(src1), start(src1), c1, perm(src2), start(src2), c2)
+    return gather4(E, spin, shape, perm(src1), start(src1), c1, perm(src2), start(src2), c2, out=out)
+
+
+class _Point:
+    """MO integrals of one finite-difference point on the device (what ci_wfn.__init__ builds)."""
+
+    def __init__(self, F, ERI, eps_o, eps_v, E_SCF=0.0, E_nuc=0.0):
+        self.F, self.ERI, self.eps_o, self.eps_v, self.E_SCF, self.E_nuc = F, ERI, eps_o, eps_v, E_SCF, E_nuc
 
 
 class _Engine:
-    """Device-resident Jacobi/DIIS iteration shared by the four solvers."""
+    """Device-resident Jacobi/DIIS iteration shared by the four solvers, for nb points at once."""
 
-    def __init__(self, parameters, dtype, O, V, has_singles, spin_orbital, eps_o, eps_v, symmetrize=False):
+    def __init__(self, parameters, dtype, nb, O, V, has_singles, spin_orbital, eps_o, eps_v, symmetrize=False):
         self.p = parameters
-        self.dtype, self.O, self.V = dtype, O, V
+        self.dtype, self.nb, self.O, self.V = dtype, nb, O, V
         self.n1 = O * V if has_singles else 0
         self.n2 = O * O * V * V
         self.len = self.n1 + self.n2
         self.has_singles, self.so, self.symmetrize = has_singles, int(spin_orbital), symmetrize
         self.code = 1 if dtype == torch.complex128 else 0
-        self.eps_o = to_device(np.asarray(eps_o).real.astype(np.float64))
-        self.eps_v = to_device(np.asarray(eps_v).real.astype(np.float64))
-        z = lambda n: zeros((n,), dtype)
-        self.t, self.r, self.t_old, self.w, self.r0 = z(self.len), z(self.len), z(self.len), z(self.len), z(self.len)
-        self.r_half = z(self.n2) if symmetrize else None
-        self.out6 = zeros((6,), torch.float64)        # E(re,im), S1(re,im), S2(re,im)
+        self.eps_o = to_device(np.ascontiguousarray(np.real(eps_o), dtype=np.float64))       # [nb, o_spatial]
+        self.eps_v = to_device(np.ascontiguousarray(np.real(eps_v), dtype=np.float64))
+        z = lambda *s: zeros(s, dtype)
+        L = self.len
+        self.t, self.r, self.t_old, self.w, self.r0 = z(nb, L), z(nb, L), z(nb, L), z(nb, L), z(nb, L)
+        self.r_half = z(nb, self.n2) if symmetrize else None
+        self.out6 = zeros((nb, 6), torch.float64)        # E(re,im), S1(re,im), S2(re,im) per point
+        self.active = torch.ones((nb,), dtype=torch.int32, device=self.t.device)
         self.diis = bool(parameters["DIIS"])
         if self.diis:
-            self.hist_e = zeros((8, self.len), dtype)
-            self.hist_t = zeros((8, self.len), dtype)
-            self.B = zeros((8 * 8 * 2,), torch.float64)
-            self.c = zeros((16,), torch.float64)
+            self.hist_e = z(nb, 8, L)
+            self.hist_t = z(nb, 8, L)
+            self.B = zeros((nb, 8 * 8 * 2), torch.float64)
+            self.c = zeros((nb, 16), torch.float64)
             self.iter = torch.ones((1,), dtype=torch.int32, device=self.t.device)
-        self.scratch = reduce_scratch()
+        self.scratch = zeros((nb, int(lib.apyib_reduce_scratch_len())), torch.float64)
+        self.iterations = [0] * nb
 
     # views into the concatenated vectors
     def t1(self, x=None):
         x = self.t if x is None else x
-        return x[:self.n1].view(self.O, self.V)
+        return x[:, :self.n1].view(self.nb, self.O, self.V)
 
     def t2(self, x=None):
         x = self.t if x is None else x
-        return x[self.n1:].view(self.O, self.O, self.V, self.V)
+        return x[:, self.n1:].view(self.nb, self.O, self.O, self.V, self.V)
 
     def _update(self):
         check(lib.apyib_ci_update(self.code, ptr(self.r), ptr(self.t), ptr(self.out6), ptr(self.eps_o),
-                                  ptr(self.eps_v), self.O, self.V, int(self.has_singles), self.so, stream_ptr()))
+                                  ptr(self.eps_v), self.O, self.V, int(self.has_singles), self.so, self.nb,
+                                  ptr(self.active), stream_ptr()))
 
     def _energy_rms(self, use_diis):
         if use_diis:
             check(lib.apyib_lincomb_energy_rms(self.code, ptr(self.hist_t), self.len, 0, ptr(self.iter), ptr(self.c),
                                                ptr(self.t), ptr(self.t_old), ptr(self.w), self.n1, self.len,
-                                               ptr(self.out6), ptr(self.scratch), stream_ptr()))
+                                               ptr(self.out6), ptr(self.scratch), self.nb, ptr(self.active),
+                                               stream_ptr()))
         else:
             check(lib.apyib_lincomb_energy_rms(self.code, _NULL, 0, 0, _NULL, _NULL, ptr(self.t), ptr(self.t_old),
                                                ptr(self.w), self.n1, self.len, ptr(self.out6), ptr(self.scratch),
-                                               stream_ptr()))
+                                               self.nb, ptr(self.active), stream_ptr()))
 
-    def _copy(self, dst, src, n):
-        check(lib.apyib_copy(self.code, ptr(dst), ptr(src), n, stream_ptr()))
+    def _copy(self, dst, src):
+        """dense copy of equally shaped tensors via the copy kernel (per point if strided)"""
+        if dst.is_contiguous() and src.is_contiguous():
+            check(lib.apyib_copy(self.code, ptr(dst), ptr(src), dst.numel(), stream_ptr()))
+        else:
+            for s in range(self.nb):
+                check(lib.apyib_copy(self.code, ptr(dst[s]), ptr(src[s]), dst[s].numel(), stream_ptr()))
 
     def initial_guess(self):
         """t = r0 / D, E = w.t   (ci_wfn.py:66-70, 193-197, 286-293, 435-442)."""
         self.out6.zero_()
         self.t.zero_()
-        self._copy(self.r, self.r0, self.len)
+        self._copy(self.r, self.r0)
         if self.symmetrize:                   # CID spatial keeps 0.5*K in r0 (ci_wfn.py:83); guess uses K
-            check(lib.apyib_axpby(self.code, self.n2, 2.0, 0.0, ptr(self.r0[self.n1:]), 0, 0.0, 0.0,
-                                  ptr(self.r[self.n1:]), stream_ptr()))
+            for s in range(self.nb):
+                check(lib.apyib_axpby(self.code, self.n2, 2.0, 0.0, ptr(self.r0[s, self.n1:]), 0, 0.0, 0.0,
+                                      ptr(self.r[s, self.n1:]), stream_ptr()))
         self._update()
-        self._copy(self.t_old, self.t, self.len)
+        self._copy(self.t_old, self.t)
         self._energy_rms(False)
 
     def iteration(self, residual):
-        """One trip of the reference's while-loop body, enqueued on the current stream."""
-        self._copy(self.t_old, self.t, self.len)
+        """One trip of the reference's while-loop body for all active points, on the current stream."""
+        self._copy(self.t_old, self.t)
         if self.symmetrize:
-            self._copy(self.r[:self.n1], self.r0[:self.n1], self.n1)
-            self._copy(self.r_half, self.r0[self.n1:], self.n2)
+            self._copy(self.r, self.r0)                      # (the r2 part is overwritten by the symmetrisation)
+            self._copy(self.r_half, self.r0[:, self.n1:])
             residual(self.r_half)
-            check(lib.apyib_symmetrize_ijab(self.code, ptr(self.r_half), ptr(self.r[self.n1:]), self.O, self.V,
-                                            stream_ptr()))
+            for s in range(self.nb):
+                check(lib.apyib_symmetrize_ijab(self.code, ptr(self.r_half[s]), ptr(self.r[s, self.n1:]), self.O,
+                                                self.V, stream_ptr()))
         else:
-            self._copy(self.r, self.r0, self.len)
+            self._copy(self.r, self.r0)
             residual(None)
         self._update()
         if self.diis:
             check(lib.apyib_diis_push(self.code, ptr(self.r), ptr(self.t), ptr(self.hist_e), ptr(self.hist_t),
-                                      self.len, ptr(self.iter), ptr(self.B), ptr(self.scratch), stream_ptr()))
-            check(lib.apyib_diis_solve(self.code, ptr(self.B), 8, 0, ptr(self.iter), ptr(self.c), stream_ptr()))
+                                      self.len, ptr(self.iter), ptr(self.B), ptr(self.scratch), self.nb,
+                                      ptr(self.active), stream_ptr()))
+            check(lib.apyib_diis_solve(self.code, ptr(self.B), 8, 0, ptr(self.iter), ptr(self.c), self.nb,
+                                       ptr(self.active), stream_ptr()))
             self._energy_rms(True)
             check(lib.apyib_iter_advance(ptr(self.iter), stream_ptr()))
         else:
@@ -132,20 +158,21 @@ class _Engine:
     def read(self):
         h = to_host(self.out6)
         if self.code:
-            return (np.complex128(complex(h[0], h[1])), np.complex128(complex(h[2], h[3])),
-                    np.complex128(complex(h[4], h[5])))
-        return np.float64(h[0]), np.float64(h[2]), np.float64(h[4])
+            c = h[:, 0::2] + 1j * h[:, 1::2]
+            return [tuple(np.complex128(x) for x in row) for row in c]
+        return [tuple(np.float64(x) for x in row[0::2]) for row in h]
 
     def run(self, residual, print_level=0, E_SCF=0.0, E_nuc=0.0):
-        """The reference's iteration control (ci_wfn.py:76-130 etc.), verbatim semantics."""
-        p = self.p
+        """The reference's iteration control (ci_wfn.py:76-130 etc.), verbatim semantics, applied to
+        every point of the batch independently."""
+        p, nb = self.p, self.nb
         self.initial_guess()
-        E, _, _ = self.read()
+        E = [x[0] for x in self.read()]
         graph = None
         iteration = 1
-        self.iterations = 0
-        while iteration <= p["max_iterations"]:
-            E_old = E
+        active = [True] * nb
+        while iteration <= p["max_iterations"] and any(active):
+            E_old = list(E)
             if iteration == 1 or not config.USE_CUDA_GRAPH:
                 self.iteration(residual)              # eager: also builds/caches the offset tables
             else:
@@ -153,26 +180,254 @@ class _Engine:
                     graph = Graph()
                     graph.capture(lambda: self.iteration(residual))
                 graph.launch()
-            E, S1, S2 = self.read()
-            rms_t1, rms_t2 = np.sqrt(S1), np.sqrt(S2)
-            delta_E = E_old - E
-            self.iterations = iteration
-            if print_level > 0:
-                E_tot = E_SCF + E + E_nuc
-                print(" %02d %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f" % (
-                    iteration, np.real(E), np.imag(E), np.real(E_tot), np.real(delta_E), np.imag(delta_E),
-                    np.real(rms_t1), np.imag(rms_t1), np.real(rms_t2), np.imag(rms_t2)))
-            if iteration > 1:
-                conv = abs(delta_E) < p["e_convergence"] and rms_t2 < p["d_convergence"]
-                if self.has_singles:
-                    conv = conv and rms_t1 < p["d_convergence"]
-                if conv:
-                    break
-            if iteration == p["max_iterations"]:
-                if abs(delta_E) > p["e_convergence"] or rms_t2 > p["d_convergence"]:
-                    print("Not converged.")
+            vals = self.read()
+            changed = False
+            for s in range(nb):
+                if not active[s]:
+                    continue
+                E[s], S1, S2 = vals[s]
+                rms_t1, rms_t2 = np.sqrt(S1), np.sqrt(S2)
+                delta_E = E_old[s] - E[s]
+                self.iterations[s] = iteration
+                if print_level > 0 and nb == 1:
+                    E_tot = E_SCF + E[s] + E_nuc
+                    print(" %02d %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f %20.12f" % (
+                        iteration, np.real(E[s]), np.imag(E[s]), np.real(E_tot), np.real(delta_E), np.imag(delta_E),
+                        np.real(rms_t1), np.imag(rms_t1), np.real(rms_t2), np.imag(rms_t2)))
+                if iteration > 1:
+                    conv = abs(delta_E) < p["e_convergence"] and rms_t2 < p["d_convergence"]
+                    if self.has_singles:
+                        conv = conv and rms_t1 < p["d_convergence"]
+                    if conv:
+                        active[s] = False
+                        changed = True
+                        continue
+                if iteration == p["max_iterations"]:
+                    if abs(delta_E) > p["e_convergence"] or rms_t2 > p["d_convergence"]:
+                        print("Not converged.")
+            if changed and any(active):
+                self.active.copy_(torch.tensor([1 if a else 0 for a in active], dtype=torch.int32))
             iteration += 1
         return E
+
+
+# -------------------------------------------------------------------------------------------------
+# the four residuals, written for a stack of points (leading index s)
+# -------------------------------------------------------------------------------------------------
+def _sizes(points, so):
+    n = points[0].F.shape[0]
+    o = len(points[0].eps_o)
+    f = 2 if so else 1
+    O, V = f * o, f * (n - o)
+    return O, V, {"o": (0, O), "v": (O, O + V)}
+
+
+def _stack(points, fn, shape, dtype):
+    out = empty((len(points),) + tuple(shape), dtype)
+    for s, pt in enumerate(points):
+        fn(pt, out[s])
+    return out
+
+
+def _make_engine(parameters, points, has_singles, so, symmetrize=False):
+    O, V, bd = _sizes(points, so)
+    eps_o = np.stack([np.asarray(pt.eps_o) for pt in points])
+    eps_v = np.stack([np.asarray(pt.eps_v) for pt in points])
+    eng = _Engine(parameters, points[0].ERI.dtype, len(points), O, V, has_singles, so, eps_o, eps_v, symmetrize)
+    return eng, O, V, bd
+
+
+def _blocks(points, sp, bd, dt, spin):
+    """returns blk(labels, out_labels=None, c1=1, c2=0): stacked [nb, ...] block of W (or <pq||rs>)"""
+    def blk(lab, outl=None, c1=1.0, c2=0.0):
+        ol = outl or lab
+        return _stack(points, lambda pt, out: w_block(pt.ERI, lab, ol, sp, bd, spin, c1, c2, out=out),
+                      [bd[sp[ch]][1] - bd[sp[ch]][0] for ch in ol], dt)
+    return blk
+
+
+def _solve_CID(parameters, points, print_level):
+    """Spatial-orbital CID (ci_wfn.py:51-167)."""
+    eng, O, V, bd = _make_engine(parameters, points, False, False, symmetrize=True)
+    dt, nb = eng.dtype, eng.nb
+    sp = dict(i="o", j="o", m="o", n="o", a="v", b="v", e="v", f="v")
+    blk = _blocks(points, sp, bd, dt, 0)
+    eng.r0.copy_(blk("abij", "ijab", 0.5).reshape(nb, -1))              # 0.5 <ab|ij>     ci_wfn.py:83
+    eng.w.copy_(blk("ijab", None, 2.0, -1.0).reshape(nb, -1))           # 2<ij|ab>-<ij|ba> ci_wfn.py:70
+    Woooo, Wvvvv = blk("mnij"), blk("abef")
+    Wovvo, Wovov = blk("mbej"), blk("mbie")
+    Lovvo = blk("mbej", None, 1.0, -1.0)                                # <mb|ej>-<mb|je>  ci_wfn.py:89
+    F = torch.stack([pt.F for pt in points])
+    Foo, Fvv = F[:, :O, :O], F[:, O:, O:]
+
+    def residual(r):
+        t2 = eng.t2()
+        r = r.view(nb, O, O, V, V)
+        contract("sijae,sbe->sijab", t2, Fvv, r, 1.0, 1.0)              # ci_wfn.py:84
+        contract("simab,smj->sijab", t2, Foo, r, -1.0, 1.0)             # :85
+        contract("smnab,smnij->sijab", t2, Woooo, r, 0.5, 1.0)          # :86
+        contract("sijef,sabef->sijab", t2, Wvvvv, r, 0.5, 1.0)          # :87
+        contract("simae,smbej->sijab", t2, Wovvo, r, 1.0, 1.0)          # :88  (t2 - t2.swapaxes(2,3)) . W
+        contract("simea,smbej->sijab", t2, Wovvo, r, -1.0, 1.0)
+        contract("simae,smbej->sijab", t2, Lovvo, r, 1.0, 1.0)          # :89
+        contract("smjae,smbie->sijab", t2, Wovov, r, -1.0, 1.0)         # :90
+
+    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    return eng, E
+
+
+def _solve_CID_SO(parameters, points, print_level):
+    """Spin-orbital CID (ci_wfn.py:171-259)."""
+    eng, O, V, bd = _make_engine(parameters, points, False, True)
+    dt, nb = eng.dtype, eng.nb
+    sp = dict(i="o", j="o", m="o", n="o", a="v", b="v", e="v", f="v")
+    blk = _blocks(points, sp, bd, dt, 1)
+    A = lambda lab, outl=None, sc=1.0: blk(lab, outl, sc, -sc)            # <pq||rs>
+    F = torch.stack([spin_block_2_dev(pt.F) for pt in points])             # compute_F_SO, ci_wfn.py:185
+    eng.r0.copy_(A("abij", "ijab").reshape(nb, -1))                       # ci_wfn.py:210
+    eng.w.copy_(A("ijab", None, 0.25).reshape(nb, -1))                    # ci_wfn.py:197
+    Aoooo, Avvvv, Aovvo = A("mnij"), A("abef"), A("mbej")
+    Foo, Fvv = F[:, :O, :O], F[:, O:, O:]
+
+    def residual(_):
+        t2, r = eng.t2(), eng.t2(eng.r)
+        contract("sijae,sbe->sijab", t2, Fvv, r, 1.0, 1.0)                # :211
+        contract("sijeb,sae->sijab", t2, Fvv, r, 1.0, 1.0)
+        contract("simab,smj->sijab", t2, Foo, r, -1.0, 1.0)               # :212
+        contract("smjab,smi->sijab", t2, Foo, r, -1.0, 1.0)
+        contract("smnab,smnij->sijab", t2, Aoooo, r, 0.5, 1.0)            # :213
+        contract("sijef,sabef->sijab", t2, Avvvv, r, 0.5, 1.0)            # :214
+        contract("simae,smbej->sijab", t2, Aovvo, r, 1.0, 1.0)            # :215
+        contract("smjae,smbei->sijab", t2, Aovvo, r, 1.0, 1.0)            # :216
+        contract("simeb,smaej->sijab", t2, Aovvo, r, 1.0, 1.0)            # :217
+        contract("smjeb,smaei->sijab", t2, Aovvo, r, 1.0, 1.0)            # :218
+
+    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    return eng, E
+
+
+def _solve_CISD_SO(parameters, points, print_level):
+    """Spin-orbital CISD (ci_wfn.py:263-416)."""
+    eng, O, V, bd = _make_engine(parameters, points, True, True)
+    dt, nb, n1 = eng.dtype, eng.nb, eng.n1
+    sp = dict(i="o", j="o", k="o", l="o", a="v", b="v", c="v", d="v")
+    blk = _blocks(points, sp, bd, dt, 1)
+    A = lambda lab, outl=None, sc=1.0: blk(lab, outl, sc, -sc)
+    F = torch.stack([spin_block_2_dev(pt.F) for pt in points])
+    Foo, Fvv, Fov = F[:, :O, :O], F[:, O:, O:], F[:, :O, O:].contiguous()
+    eng.r0[:, :n1].copy_(F[:, O:, :O].transpose(1, 2).reshape(nb, -1))     # F_ai as [i,a]   ci_wfn.py:309
+    eng.r0[:, n1:].copy_(A("abij", "ijab").reshape(nb, -1))               # :319
+    eng.w[:, :n1].copy_(Fov.reshape(nb, -1))                              # :355
+    eng.w[:, n1:].copy_(A("ijab", None, 0.25).reshape(nb, -1))
+    Aovvo, Avovv, Aooov = A("jabi"), A("ajcb"), A("kjib")
+    Aovoo, Avooo, Avvvo, Avvov = A("kbij"), A("akij"), A("abcj"), A("abic")
+    Aoooo, Avvvv = A("klij"), A("abcd")
+
+    def residual(_):
+        t1, t2 = eng.t1(), eng.t2()
+        r1, r2 = eng.t1(eng.r), eng.t2(eng.r)
+        contract("sji,sja->sia", Foo, t1, r1, -1.0, 1.0)                  # :310
+        contract("sab,sib->sia", Fvv, t1, r1, 1.0, 1.0)                   # :311
+        contract("sjabi,sjb->sia", Aovvo, t1, r1, 1.0, 1.0)               # :312
+        contract("sjb,sijab->sia", Fov, t2, r1, 1.0, 1.0)                 # :313
+        contract("sajcb,sijcb->sia", Avovv, t2, r1, 0.5, 1.0)             # :314
+        contract("skjib,skjab->sia", Aooov, t2, r1, -0.5, 1.0)            # :315
+        contract("skbij,ska->sijab", Aovoo, t1, r2, -1.0, 1.0)            # :320
+        contract("sakij,skb->sijab", Avooo, t1, r2, -1.0, 1.0)            # :321
+        contract("sabcj,sic->sijab", Avvvo, t1, r2, 1.0, 1.0)             # :322
+        contract("sabic,sjc->sijab", Avvov, t1, r2, 1.0, 1.0)             # :323
+        contract("sbc,sijac->sijab", Fvv, t2, r2, 1.0, 1.0)               # :324
+        contract("sac,sijcb->sijab", Fvv, t2, r2, 1.0, 1.0)               # :325
+        contract("skj,sikab->sijab", Foo, t2, r2, -1.0, 1.0)              # :326
+        contract("ski,skjab->sijab", Foo, t2, r2, -1.0, 1.0)              # :327
+        contract("sklij,sklab->sijab", Aoooo, t2, r2, 0.5, 1.0)           # :328
+        contract("sabcd,sijcd->sijab", Avvvv, t2, r2, 0.5, 1.0)           # :329
+        contract("skbcj,sikac->sijab", Aovvo, t2, r2, 1.0, 1.0)           # :330
+        contract("skbci,skjac->sijab", Aovvo, t2, r2, 1.0, 1.0)           # :331
+        contract("skacj,sikcb->sijab", Aovvo, t2, r2, 1.0, 1.0)           # :332
+        contract("skaci,skjcb->sijab", Aovvo, t2, r2, 1.0, 1.0)           # :333
+
+    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    return eng, E
+
+
+def _solve_CISD(parameters, points, print_level):
+    """Spatial-orbital CISD (ci_wfn.py:420-574)."""
+    eng, O, V, bd = _make_engine(parameters, points, True, False)
+    dt, nb, n1 = eng.dtype, eng.nb, eng.n1
+    sp = dict(i="o", j="o", k="o", l="o", a="v", b="v", c="v", d="v")
+    blk = _blocks(points, sp, bd, dt, 0)
+    F = torch.stack([pt.F for pt in points])
+    Foo, Fvv, Fov = F[:, :O, :O], F[:, O:, O:], F[:, :O, O:].contiguous()
+    eng.r0[:, :n1].copy_(F[:, O:, :O].transpose(1, 2).reshape(nb, -1))     # ci_wfn.py:457
+    eng.r0[:, n1:].copy_(blk("abij", "ijab").reshape(nb, -1))             # :466
+    w1 = empty((nb, n1), dt)
+    check(lib.apyib_axpby(eng.code, nb * n1, 2.0, 0.0, ptr(Fov), 0, 0.0, 0.0, ptr(w1), stream_ptr()))   # 2 F_ov  :504
+    eng.w[:, :n1].copy_(w1)
+    eng.w[:, n1:].copy_(blk("ijab", None, 2.0, -1.0).reshape(nb, -1))
+    Wovvo, Wovov = blk("kbcj"), blk("kbic")
+    Lovvo = blk("jabi", None, 2.0, -1.0)                                  # 2<ja|bi>-<ja|ib>  :460,478,481
+    Lvovv = blk("ajbc", None, 2.0, -1.0)                                  # :462
+    Looov = blk("kjib", None, 2.0, -1.0)                                  # :463
+    Wvvvo, Wvvov, Wovoo, Wvooo = blk("abcj"), blk("abic"), blk("kbij"), blk("akij")
+    Woooo, Wvvvv = blk("klij"), blk("abcd")
+
+    def residual(_):
+        t1, t2 = eng.t1(), eng.t2()
+        r1, r2 = eng.t1(eng.r), eng.t2(eng.r)
+        contract("sji,sja->sia", Foo, t1, r1, -1.0, 1.0)                  # :458
+        contract("sab,sib->sia", Fvv, t1, r1, 1.0, 1.0)                   # :459
+        contract("sjabi,sjb->sia", Lovvo, t1, r1, 1.0, 1.0)               # :460
+        contract("sjb,sijab->sia", Fov, t2, r1, 2.0, 1.0)                 # :461  F.(2 t2 - t2^T)
+        contract("sjb,sijba->sia", Fov, t2, r1, -1.0, 1.0)
+        contract("sajbc,sijbc->sia", Lvovv, t2, r1, 1.0, 1.0)             # :462
+        contract("skjib,skjab->sia", Looov, t2, r1, -1.0, 1.0)            # :463
+        contract("sabcj,sic->sijab", Wvvvo, t1, r2, 1.0, 1.0)             # :467
+        contract("sabic,sjc->sijab", Wvvov, t1, r2, 1.0, 1.0)             # :468
+        contract("skbij,ska->sijab", Wovoo, t1, r2, -1.0, 1.0)            # :469
+        contract("sakij,skb->sijab", Wvooo, t1, r2, -1.0, 1.0)            # :470
+        contract("sac,sijcb->sijab", Fvv, t2, r2, 1.0, 1.0)               # :471
+        contract("sbc,sijac->sijab", Fvv, t2, r2, 1.0, 1.0)               # :472
+        contract("ski,skjab->sijab", Foo, t2, r2, -1.0, 1.0)              # :473
+        contract("skj,sikab->sijab", Foo, t2, r2, -1.0, 1.0)              # :474
+        contract("sklij,sklab->sijab", Woooo, t2, r2, 1.0, 1.0)           # :475
+        contract("sabcd,sijcd->sijab", Wvvvv, t2, r2, 1.0, 1.0)           # :476
+        contract("skbcj,sikca->sijab", Wovvo, t2, r2, -1.0, 1.0)          # :477
+        contract("skaci,skjcb->sijab", Lovvo, t2, r2, 1.0, 1.0)           # :478
+        contract("skbic,skjac->sijab", Wovov, t2, r2, -1.0, 1.0)          # :479
+        contract("skaci,skjbc->sijab", Wovvo, t2, r2, -1.0, 1.0)          # :480
+        contract("skbcj,sikac->sijab", Lovvo, t2, r2, 1.0, 1.0)           # :481
+        contract("skajc,sikcb->sijab", Wovov, t2, r2, -1.0, 1.0)          # :482
+
+    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    return eng, E
+
+
+_SOLVERS = {"CID": (_solve_CID, False), "CID_SO": (_solve_CID_SO, False),
+            "CISD": (_solve_CISD, True), "CISD_SO": (_solve_CISD_SO, True)}
+
+
+def solve_batch(method, parameters, points, print_level=0):
+    """Solve `method` for a list of _Point objects (identical shapes and dtype) with shared
+    launches.  Returns (results, iterations): results[s] = (E, t2) or (E, t1, t2) exactly as the
+    single-point methods return them."""
+    fn, singles = _SOLVERS[method]
+    eng, E = fn(parameters, points, print_level)
+    res = []
+    dev_out = config.RETURN_DEVICE
+    t1s = eng.t1() if singles else None
+    t2s = eng.t2()
+    if not dev_out:
+        t2h = to_host(t2s)
+        t1h = to_host(t1s) if singles else None
+    for s in range(eng.nb):
+        if dev_out:
+            t2 = t2s[s].clone()
+            res.append((E[s], t1s[s].clone(), t2) if singles else (E[s], t2))
+        else:
+            t2 = t2h[s].copy()
+            res.append((E[s], t1h[s].copy(), t2) if singles else (E[s], t2))
+    return res, list(eng.iterations)
 
 
 class ci_wfn(object):
@@ -208,187 +463,53 @@ class ci_wfn(object):
             self._ERI_host = to_host(self._ERI_dev)
         return self._ERI_host
 
-    # ---------------------------------------------------------------------------------------
-    def _sizes(self, so):
-        n = self._F_dev.shape[0]
-        o = len(self.eps_o)
-        f = 2 if so else 1
-        O, V = f * o, f * (n - o)
-        return O, V, {"o": (0, O), "v": (O, O + V)}
+    def point(self):
+        """Device-side integrals of this wavefunction, for solve_batch."""
+        return _Point(self._F_dev, self._ERI_dev, self.eps_o, self.eps_v, self.wfn.E_SCF, self.H.E_nuc)
 
-    def _finish(self, eng, E, singles):
-        self.iterations = eng.iterations
-        if config.RETURN_DEVICE:
-            t2 = eng.t2().clone()
-            return (E, eng.t1().clone(), t2) if singles else (E, t2)
-        t2 = to_host(eng.t2()).copy()
-        if singles:
-            return E, to_host(eng.t1()).copy(), t2
-        return E, t2
+    def _solve(self, method, print_level):
+        res, its = solve_batch(method, self.parameters, [self.point()], print_level)
+        self.iterations = its[0]
+        return res[0]
 
-    # ---------------------------------------------------------------------------------------
     def solve_CID(self, print_level=0):
         """Spatial-orbital CID (ci_wfn.py:51-167).  Returns (E_CID, t2)."""
-        O, V, bd = self._sizes(False)
-        E4, F = self._ERI_dev, self._F_dev
-        sp = dict(i="o", j="o", m="o", n="o", a="v", b="v", e="v", f="v")
-        eng = _Engine(self.parameters, E4.dtype, O, V, False, False, self.eps_o, self.eps_v, symmetrize=True)
-        blk = lambda lab, out=None, c1=1.0, c2=0.0: w_block(E4, lab, out or lab, sp, bd, 0, c1, c2)
-        eng.r0.copy_(blk("abij", "ijab", 0.5).reshape(-1))                  # 0.5 <ab|ij>     ci_wfn.py:83
-        eng.w.copy_(blk("ijab", None, 2.0, -1.0).reshape(-1))               # 2<ij|ab>-<ij|ba> ci_wfn.py:70
-        Woooo, Wvvvv = blk("mnij"), blk("abef")
-        Wovvo, Wovov = blk("mbej"), blk("mbie")
-        Lovvo = blk("mbej", None, 1.0, -1.0)                                # <mb|ej>-<mb|je>  ci_wfn.py:89
-        Foo, Fvv = F[:O, :O], F[O:, O:]
-
-        def residual(r):
-            t2 = eng.t2()
-            r = r.view(O, O, V, V)
-            contract("ijae,be->ijab", t2, Fvv, r, 1.0, 1.0)                 # ci_wfn.py:84
-            contract("imab,mj->ijab", t2, Foo, r, -1.0, 1.0)                # :85
-            contract("mnab,mnij->ijab", t2, Woooo, r, 0.5, 1.0)             # :86
-            contract("ijef,abef->ijab", t2, Wvvvv, r, 0.5, 1.0)             # :87
-            contract("imae,mbej->ijab", t2, Wovvo, r, 1.0, 1.0)             # :88  (t2 - t2.swapaxes(2,3)) . W
-            contract("imea,mbej->ijab", t2, Wovvo, r, -1.0, 1.0)
-            contract("imae,mbej->ijab", t2, Lovvo, r, 1.0, 1.0)             # :89
-            contract("mjae,mbie->ijab", t2, Wovov, r, -1.0, 1.0)            # :90
-
-        E = eng.run(residual, print_level, self.wfn.E_SCF, self.H.E_nuc)
-        out = self._finish(eng, E, False)
+        out = self._solve("CID", print_level)
         if config.VERBOSE and not config.RETURN_DEVICE:
             print("t-Amplitude Data:")
             print("Maximum t2: ", np.max(out[1]))
         return out
 
-    # ---------------------------------------------------------------------------------------
     def solve_CID_SO(self, print_level=0):
         """Spin-orbital CID (ci_wfn.py:171-259).  Returns (E_CID, t2) in the spin-orbital basis."""
-        O, V, bd = self._sizes(True)
-        E4 = self._ERI_dev
-        F = spin_block_2_dev(self._F_dev)                                   # compute_F_SO, ci_wfn.py:185
-        sp = dict(i="o", j="o", m="o", n="o", a="v", b="v", e="v", f="v")
-        eng = _Engine(self.parameters, E4.dtype, O, V, False, True, self.eps_o, self.eps_v)
-        A = lambda lab, out=None, s=1.0: w_block(E4, lab, out or lab, sp, bd, 1, s, -s)     # <pq||rs>
-        eng.r0.copy_(A("abij", "ijab").reshape(-1))                         # ci_wfn.py:210
-        eng.w.copy_(A("ijab", None, 0.25).reshape(-1))                      # ci_wfn.py:197
-        Aoooo, Avvvv, Aovvo = A("mnij"), A("abef"), A("mbej")
-        Foo, Fvv = F[:O, :O], F[O:, O:]
+        return self._solve("CID_SO", print_level)
 
-        def residual(_):
-            t2, r = eng.t2(), eng.t2(eng.r)
-            contract("ijae,be->ijab", t2, Fvv, r, 1.0, 1.0)                 # :211
-            contract("ijeb,ae->ijab", t2, Fvv, r, 1.0, 1.0)
-            contract("imab,mj->ijab", t2, Foo, r, -1.0, 1.0)                # :212
-            contract("mjab,mi->ijab", t2, Foo, r, -1.0, 1.0)
-            contract("mnab,mnij->ijab", t2, Aoooo, r, 0.5, 1.0)             # :213
-            contract("ijef,abef->ijab", t2, Avvvv, r, 0.5, 1.0)             # :214
-            contract("imae,mbej->ijab", t2, Aovvo, r, 1.0, 1.0)             # :215
-            contract("mjae,mbei->ijab", t2, Aovvo, r, 1.0, 1.0)             # :216
-            contract("imeb,maej->ijab", t2, Aovvo, r, 1.0, 1.0)             # :217
-            contract("mjeb,maei->ijab", t2, Aovvo, r, 1.0, 1.0)             # :218
-
-        E = eng.run(residual, print_level, self.wfn.E_SCF, self.H.E_nuc)
-        return self._finish(eng, E, False)
-
-    # ---------------------------------------------------------------------------------------
     def solve_CISD_SO(self, print_level=0):
         """Spin-orbital CISD (ci_wfn.py:263-416).  Returns (E_CISD, t1, t2)."""
-        O, V, bd = self._sizes(True)
-        E4 = self._ERI_dev
-        F = spin_block_2_dev(self._F_dev)
-        sp = dict(i="o", j="o", k="o", l="o", a="v", b="v", c="v", d="v")
-        eng = _Engine(self.parameters, E4.dtype, O, V, True, True, self.eps_o, self.eps_v)
-        A = lambda lab, out=None, s=1.0: w_block(E4, lab, out or lab, sp, bd, 1, s, -s)
-        n1 = eng.n1
-        Foo, Fvv, Fov = F[:O, :O], F[O:, O:], F[:O, O:]
-        eng.r0[:n1].copy_(F[O:, :O].transpose(0, 1).reshape(-1))            # F_ai as [i,a]   ci_wfn.py:309
-        eng.r0[n1:].copy_(A("abij", "ijab").reshape(-1))                    # :319
-        eng.w[:n1].copy_(Fov.reshape(-1))                                   # :355
-        eng.w[n1:].copy_(A("ijab", None, 0.25).reshape(-1))
-        Aovvo, Avovv, Aooov = A("jabi"), A("ajcb"), A("kjib")
-        Aovoo, Avooo, Avvvo, Avvov = A("kbij"), A("akij"), A("abcj"), A("abic")
-        Aoooo, Avvvv = A("klij"), A("abcd")
-        Fov_c = Fov.contiguous()
+        return self._solve("CISD_SO", print_level)
 
-        def residual(_):
-            t1, t2 = eng.t1(), eng.t2()
-            r1, r2 = eng.t1(eng.r), eng.t2(eng.r)
-            contract("ji,ja->ia", Foo, t1, r1, -1.0, 1.0)                   # :310
-            contract("ab,ib->ia", Fvv, t1, r1, 1.0, 1.0)                    # :311
-            contract("jabi,jb->ia", Aovvo, t1, r1, 1.0, 1.0)                # :312
-            contract("jb,ijab->ia", Fov_c, t2, r1, 1.0, 1.0)                # :313
-            contract("ajcb,ijcb->ia", Avovv, t2, r1, 0.5, 1.0)              # :314
-            contract("kjib,kjab->ia", Aooov, t2, r1, -0.5, 1.0)             # :315
-            contract("kbij,ka->ijab", Aovoo, t1, r2, -1.0, 1.0)             # :320
-            contract("akij,kb->ijab", Avooo, t1, r2, -1.0, 1.0)             # :321
-            contract("abcj,ic->ijab", Avvvo, t1, r2, 1.0, 1.0)              # :322
-            contract("abic,jc->ijab", Avvov, t1, r2, 1.0, 1.0)              # :323
-            contract("bc,ijac->ijab", Fvv, t2, r2, 1.0, 1.0)                # :324
-            contract("ac,ijcb->ijab", Fvv, t2, r2, 1.0, 1.0)                # :325
-            contract("kj,ikab->ijab", Foo, t2, r2, -1.0, 1.0)               # :326
-            contract("ki,kjab->ijab", Foo, t2, r2, -1.0, 1.0)               # :327
-            contract("klij,klab->ijab", Aoooo, t2, r2, 0.5, 1.0)            # :328
-            contract("abcd,ijcd->ijab", Avvvv, t2, r2, 0.5, 1.0)            # :329
-            contract("kbcj,ikac->ijab", Aovvo, t2, r2, 1.0, 1.0)            # :330
-            contract("kbci,kjac->ijab", Aovvo, t2, r2, 1.0, 1.0)            # :331
-            contract("kacj,ikcb->ijab", Aovvo, t2, r2, 1.0, 1.0)            # :332
-            contract("kaci,kjcb->ijab", Aovvo, t2, r2, 1.0, 1.0)            # :333
-
-        E = eng.run(residual, print_level, self.wfn.E_SCF, self.H.E_nuc)
-        return self._finish(eng, E, True)
-
-    # ---------------------------------------------------------------------------------------
     def solve_CISD(self, print_level=0):
         """Spatial-orbital CISD (ci_wfn.py:420-574).  Returns (E_CISD, t1, t2)."""
-        O, V, bd = self._sizes(False)
-        E4, F = self._ERI_dev, self._F_dev
-        sp = dict(i="o", j="o", k="o", l="o", a="v", b="v", c="v", d="v")
-        eng = _Engine(self.parameters, E4.dtype, O, V, True, False, self.eps_o, self.eps_v)
-        blk = lambda lab, out=None, c1=1.0, c2=0.0: w_block(E4, lab, out or lab, sp, bd, 0, c1, c2)
-        n1 = eng.n1
-        Foo, Fvv, Fov = F[:O, :O], F[O:, O:], F[:O, O:].contiguous()
-        eng.r0[:n1].copy_(F[O:, :O].transpose(0, 1).reshape(-1))            # ci_wfn.py:457
-        eng.r0[n1:].copy_(blk("abij", "ijab").reshape(-1))                  # :466
-        check(lib.apyib_axpby(eng.code, n1, 2.0, 0.0, ptr(Fov), 0, 0.0, 0.0, ptr(eng.w), stream_ptr()))  # 2 F_ov  :504
-        eng.w[n1:].copy_(blk("ijab", None, 2.0, -1.0).reshape(-1))
-        Wovvo, Wovov = blk("kbcj"), blk("kbic")
-        Lovvo = blk("jabi", None, 2.0, -1.0)                                # 2<ja|bi>-<ja|ib>  :460,478,481
-        Lvovv = blk("ajbc", None, 2.0, -1.0)                                # :462
-        Looov = blk("kjib", None, 2.0, -1.0)                                # :463
-        Wvvvo, Wvvov, Wovoo, Wvooo = blk("abcj"), blk("abic"), blk("kbij"), blk("akij")
-        Woooo, Wvvvv = blk("klij"), blk("abcd")
-
-        def residual(_):
-            t1, t2 = eng.t1(), eng.t2()
-            r1, r2 = eng.t1(eng.r), eng.t2(eng.r)
-            contract("ji,ja->ia", Foo, t1, r1, -1.0, 1.0)                   # :458
-            contract("ab,ib->ia", Fvv, t1, r1, 1.0, 1.0)                    # :459
-            contract("jabi,jb->ia", Lovvo, t1, r1, 1.0, 1.0)                # :460
-            contract("jb,ijab->ia", Fov, t2, r1, 2.0, 1.0)                  # :461  F.(2 t2 - t2^T)
-            contract("jb,ijba->ia", Fov, t2, r1, -1.0, 1.0)
-            contract("ajbc,ijbc->ia", Lvovv, t2, r1, 1.0, 1.0)              # :462
-            contract("kjib,kjab->ia", Looov, t2, r1, -1.0, 1.0)             # :463
-            contract("abcj,ic->ijab", Wvvvo, t1, r2, 1.0, 1.0)              # :467
-            contract("abic,jc->ijab", Wvvov, t1, r2, 1.0, 1.0)              # :468
-            contract("kbij,ka->ijab", Wovoo, t1, r2, -1.0, 1.0)             # :469
-            contract("akij,kb->ijab", Wvooo, t1, r2, -1.0, 1.0)             # :470
-            contract("ac,ijcb->ijab", Fvv, t2, r2, 1.0, 1.0)                # :471
-            contract("bc,ijac->ijab", Fvv, t2, r2, 1.0, 1.0)                # :472
-            contract("ki,kjab->ijab", Foo, t2, r2, -1.0, 1.0)               # :473
-            contract("kj,ikab->ijab", Foo, t2, r2, -1.0, 1.0)               # :474
-            contract("klij,klab->ijab", Woooo, t2, r2, 1.0, 1.0)            # :475
-            contract("abcd,ijcd->ijab", Wvvvv, t2, r2, 1.0, 1.0)            # :476
-            contract("kbcj,ikca->ijab", Wovvo, t2, r2, -1.0, 1.0)           # :477
-            contract("kaci,kjcb->ijab", Lovvo, t2, r2, 1.0, 1.0)            # :478
-            contract("kbic,kjac->ijab", Wovov, t2, r2, -1.0, 1.0)           # :479
-            contract("kaci,kjbc->ijab", Wovvo, t2, r2, -1.0, 1.0)           # :480
-            contract("kbcj,ikac->ijab", Lovvo, t2, r2, 1.0, 1.0)            # :481
-            contract("kajc,ikcb->ijab", Wovov, t2, r2, -1.0, 1.0)           # :482
-
-        E = eng.run(residual, print_level, self.wfn.E_SCF, self.H.E_nuc)
-        out = self._finish(eng, E, True)
+        out = self._solve("CISD", print_level)
         if config.VERBOSE and not config.RETURN_DEVICE:
             print("t-Amplitude Data:")
             print("Maximum t1: ", np.max(out[1]))
             print("Maximum t2: ", np.max(out[2]))
         return out
+
+
+def solve_many(method, parameters, wfns, print_level=0):
+    """Batched counterpart of `[ci_wfn(parameters, w).solve_<method>() for w in wfns]`: the points
+    are grouped by dtype (real nuclear-displacement points / complex field points) and each group
+    is solved with shared launches.  Returns the per-point result tuples in input order."""
+    cis = [ci_wfn(parameters, w) for w in wfns]
+    groups = {}
+    for k, c in enumerate(cis):
+        groups.setdefault((c._ERI_dev.dtype, tuple(c._ERI_dev.shape), len(c.eps_o)), []).append(k)
+    out = [None] * len(cis)
+    for idx in groups.values():
+        res, its = solve_batch(method, parameters, [cis[k].point() for k in idx], print_level)
+        for k, r, it in zip(idx, res, its):
+            out[k] = r
+            cis[k].iterations = it
+    return out

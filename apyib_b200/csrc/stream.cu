@@ -122,9 +122,13 @@ constexpr int kUnroll = 4;
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 ci_update_kernel(T *__restrict__ r, T *__restrict__ t, const double *__restrict__ E, const double *__restrict__ eps_o,
-                 const double *__restrict__ eps_v, int64_t o, int64_t v, int64_t n1, int64_t n2, int sh) {
-    const T Ec = scalar<T>::make(E[0], E[1]);
+                 const double *__restrict__ eps_v, int64_t o, int64_t v, int64_t n1, int64_t n2, int sh,
+                 const int32_t *__restrict__ active) {
+    const int z = blockIdx.y;                      // finite-difference point of a batched solve
+    if (active != nullptr && active[z] == 0) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, len = n1 + n2;
+    r += z * len; t += z * len; E += z * 6; eps_o += z * (o >> sh); eps_v += z * (v >> sh);
+    const T Ec = scalar<T>::make(E[0], E[1]);
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += kUnroll * stride) {
         T tv[kUnroll], rv[kUnroll];
 #pragma unroll
@@ -236,7 +240,11 @@ dots_kernel(const T *__restrict__ x, int64_t xs, int nvec, const T *__restrict__
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 diis_push_kernel(const T *__restrict__ r, const T *__restrict__ t, T *__restrict__ hist_e, T *__restrict__ hist_t,
-                 int64_t len, const int *iter, double *B, double *partials) {
+                 int64_t len, const int *iter, double *B, double *partials, const int32_t *__restrict__ active) {
+    const int z = blockIdx.y;
+    if (active != nullptr && active[z] == 0) return;
+    r += z * len; t += z * len; hist_e += (int64_t)z * kMaxVec * len; hist_t += (int64_t)z * kMaxVec * len;
+    B += z * 2 * kMaxVec * kMaxVec; partials += (int64_t)z * (kReduceMaxBlocks * kReduceMaxVals + 2);
     const int it = *iter;
     const int slot = (it - 1) % kMaxVec;
     const int m = it < kMaxVec ? it : kMaxVec;
@@ -286,8 +294,12 @@ diis_push_kernel(const T *__restrict__ r, const T *__restrict__ t, T *__restrict
 
 // Bordered system  [B -1; -1 0] c = (0,..,0,-1)  with partial pivoting (np.linalg.solve,
 // utils.py:122-135).  m <= 8 -> at most 9x9; one thread is plenty.
-__global__ void diis_solve_kernel(const double *B, int ldb, const int *iter, int m_fixed, double *c) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void diis_solve_kernel(const double *B, int ldb, const int *iter, int m_fixed, double *c,
+                                  const int32_t *__restrict__ active) {
+    if (threadIdx.x != 0) return;
+    const int z = blockIdx.x;
+    if (active != nullptr && active[z] == 0) return;
+    B += z * 2 * kMaxVec * kMaxVec; c += z * 2 * kMaxVec;
     int m = m_fixed;
     if (iter != nullptr) m = (*iter < kMaxVec) ? *iter : kMaxVec;
     const int n = m + 1;
@@ -338,7 +350,11 @@ __global__ void diis_solve_kernel(const double *B, int ldb, const int *iter, int
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 lincomb_kernel(const T *hist, int64_t hs, const int *iter, int m_fixed, const double *c, T *t, const T *t_old,
-               const T *w, int64_t n1, int64_t len, double *out, double *partials) {
+               const T *w, int64_t n1, int64_t len, double *out, double *partials, const int32_t *__restrict__ active) {
+    const int z = blockIdx.y;
+    if (active != nullptr && active[z] == 0) return;
+    hist += (int64_t)z * kMaxVec * hs; c += z * 2 * kMaxVec; t += z * len; t_old += z * len; w += z * len;
+    out += z * 6; partials += (int64_t)z * (kReduceMaxBlocks * kReduceMaxVals + 2);
     int m = m_fixed;
     if (iter != nullptr) m = (*iter < kMaxVec) ? *iter : kMaxVec;
     T cj[kMaxVec];
@@ -514,18 +530,19 @@ extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, i
 
 extern "C" int apyib_ci_update(int dtype, void *d_r, void *d_t, const double *d_E, const double *d_eps_o,
                                const double *d_eps_v, int64_t o, int64_t v, int has_singles, int spin_orbital,
-                               void *stream) {
+                               int nb, const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(nb >= 1 && nb <= 65535, "batch");
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(d_r && d_t && d_E && d_eps_o && d_eps_v, "null pointer");
     const int64_t n1 = has_singles ? o * v : 0, n2 = o * o * v * v;
     if (n1 + n2 == 0) return APYIB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = stream_grid(n1 + n2);
+    const dim3 grid(stream_grid(n1 + n2), nb);
     const int sh = spin_orbital ? 1 : 0;
     if (dtype == APYIB_C128)
-        ci_update_kernel<cplx><<<grid, kThreads, 0, st>>>((cplx *)d_r, (cplx *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh);
+        ci_update_kernel<cplx><<<grid, kThreads, 0, st>>>((cplx *)d_r, (cplx *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh, d_active);
     else
-        ci_update_kernel<double><<<grid, kThreads, 0, st>>>((double *)d_r, (double *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh);
+        ci_update_kernel<double><<<grid, kThreads, 0, st>>>((double *)d_r, (double *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh, d_active);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
@@ -568,25 +585,28 @@ extern "C" int apyib_dots(int dtype, const void *d_x, int64_t x_stride, int nvec
 }
 
 extern "C" int apyib_diis_push(int dtype, const void *d_r, const void *d_t, void *d_hist_e, void *d_hist_t,
-                               int64_t len, const int32_t *d_iter, double *d_B, double *d_partials, void *stream) {
+                               int64_t len, const int32_t *d_iter, double *d_B, double *d_partials, int nb,
+                               const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(nb >= 1 && nb <= 65535, "batch");
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(d_r && d_t && d_hist_e && d_hist_t && d_iter && d_B && d_partials, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = stream_grid(len);
+    const dim3 grid(stream_grid(len), nb);
     if (dtype == APYIB_C128)
-        diis_push_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_r, (const cplx *)d_t, (cplx *)d_hist_e, (cplx *)d_hist_t, len, d_iter, d_B, d_partials);
+        diis_push_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_r, (const cplx *)d_t, (cplx *)d_hist_e, (cplx *)d_hist_t, len, d_iter, d_B, d_partials, d_active);
     else
-        diis_push_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_r, (const double *)d_t, (double *)d_hist_e, (double *)d_hist_t, len, d_iter, d_B, d_partials);
+        diis_push_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_r, (const double *)d_t, (double *)d_hist_e, (double *)d_hist_t, len, d_iter, d_B, d_partials, d_active);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
 
 extern "C" int apyib_diis_solve(int dtype, const double *d_B, int ldb, int m, const int32_t *d_iter, double *d_c,
-                                void *stream) {
+                                int nb, const int32_t *d_active, void *stream) {
     (void)dtype;
+    APYIB_REQUIRE(nb >= 1 && nb <= 65535 && (nb == 1 || ldb == kMaxVec), "batch (batched B must be 8x8 blocks)");
     APYIB_REQUIRE(d_B && d_c, "null pointer");
     APYIB_REQUIRE(d_iter != nullptr || (m >= 1 && m <= kMaxVec), "m");
-    diis_solve_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_B, ldb, d_iter, m, d_c);
+    diis_solve_kernel<<<nb, 32, 0, (cudaStream_t)stream>>>(d_B, ldb, d_iter, m, d_c, d_active);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
@@ -594,17 +614,18 @@ extern "C" int apyib_diis_solve(int dtype, const double *d_B, int ldb, int m, co
 extern "C" int apyib_lincomb_energy_rms(int dtype, const void *d_hist, int64_t hist_stride, int m,
                                         const int32_t *d_iter, const double *d_c, void *d_t, const void *d_t_old,
                                         const void *d_w, int64_t n1, int64_t len, double *d_out, double *d_partials,
-                                        void *stream) {
+                                        int nb, const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(nb >= 1 && nb <= 65535, "batch");
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(d_t && d_t_old && d_w && d_out && d_partials, "null pointer");
     APYIB_REQUIRE(m >= 0 && m <= kMaxVec, "m");
     APYIB_REQUIRE((m == 0 && d_iter == nullptr) || (d_hist && d_c), "history");
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = stream_grid(len);
+    const dim3 grid(stream_grid(len), nb);
     if (dtype == APYIB_C128)
-        lincomb_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_hist, hist_stride, d_iter, m, d_c, (cplx *)d_t, (const cplx *)d_t_old, (const cplx *)d_w, n1, len, d_out, d_partials);
+        lincomb_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_hist, hist_stride, d_iter, m, d_c, (cplx *)d_t, (const cplx *)d_t_old, (const cplx *)d_w, n1, len, d_out, d_partials, d_active);
     else
-        lincomb_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_hist, hist_stride, d_iter, m, d_c, (double *)d_t, (const double *)d_t_old, (const double *)d_w, n1, len, d_out, d_partials);
+        lincomb_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_hist, hist_stride, d_iter, m, d_c, (double *)d_t, (const double *)d_t_old, (const double *)d_w, n1, len, d_out, d_partials, d_active);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }

@@ -29,6 +29,29 @@ def _correlated(parameters, wfn, print_level):
     return E, [t0, t1, t2]
 
 
+def scf_point(parameters, unperturbed_basis=None, unperturbed_C=None, print_level=0):
+    """Host part of one finite-difference point: AO integrals, SCF and (optionally) the MO phase
+    fix of energy.py:104.  Returns the hf_wfn-like object the correlated solvers consume."""
+    H = Hamiltonian(parameters)
+    wfn = hf_wfn(H)
+    wfn.solve_SCF(parameters, print_level)
+    if unperturbed_basis is not None:
+        wfn.C = compute_phase(wfn.ndocc, wfn.nbf, unperturbed_basis, unperturbed_C, H.basis_set, wfn.C,
+                              ao_overlap=provider_ao_overlap(unperturbed_basis, H.basis_set))
+    return wfn
+
+
+def correlated_many(parameters, wfns, print_level=0):
+    """Device part for a list of points: [(E, [t0, t1, t2]), ...] in input order.  CI methods
+    are solved with shared launches (ci_wfn.solve_many); MP2 is one streaming kernel per point."""
+    from .ci_wfn import solve_many
+    m = parameters["method"]
+    if m in ("CID", "CISD", "CID_SO", "CISD_SO"):
+        res = solve_many(m, parameters, wfns, print_level)
+        return [(r[0], [1, r[1], r[2]] if len(r) == 3 else [1, 0, r[1]]) for r in res]
+    return [_correlated(parameters, w, print_level) for w in wfns]
+
+
 def _report(parameters, E_SCF, E, E_nuc):
     print("Method: ", parameters["method"])
     print("Electronic Hartree-Fock Energy: ", E_SCF)

@@ -12,7 +12,7 @@ import copy
 
 import numpy as np
 
-from .energy import energy, phase_corrected_energy
+from .energy import energy, phase_corrected_energy, scf_point, correlated_many
 from .hostchem import Molecule
 
 
@@ -51,29 +51,39 @@ class finite_difference(object):
         self.molecule.set_geometry(self.geom)
         self.parameters["geom"] = self.molecule.create_psi4_string_from_molecule()
 
-    def solve_aat_point(self, point, h_R, h_B):
+    def scf_aat_point(self, point, h_R, h_B):
+        """Host SCF (+ MO phase fix) of one displaced / field point; `parameters` is mutated and
+        restored like in the reference (fin_diff.py:292-307, 336-351)."""
         kind, idx, sign = point
         if kind == "R":
             self.parameters["geom"] = self._displaced([(idx, sign * h_R)])
-            out = phase_corrected_energy(self.parameters, self.unperturbed_basis, self.unperturbed_C)
+            wfn = scf_point(self.parameters, self.unperturbed_basis, self.unperturbed_C)
             self._reset()
         else:
             self.parameters["F_mag"][idx] += sign * h_B
-            out = phase_corrected_energy(self.parameters, self.unperturbed_basis, self.unperturbed_C)
+            wfn = scf_point(self.parameters, self.unperturbed_basis, self.unperturbed_C)
             self.parameters["F_mag"][idx] -= sign * h_B
-        return out
+        return wfn
+
+    def solve_aat_point(self, point, h_R, h_B):
+        wfn = self.scf_aat_point(point, h_R, h_B)
+        E, T_list = correlated_many(self.parameters, [wfn])[0]
+        return [wfn.E_SCF, E, wfn.H.E_nuc], T_list, wfn.C, wfn.H.basis_set
 
     # -- fin_diff.py:267-372 ------------------------------------------------------------------
     def compute_AAT(self, nuc_pert_strength, mag_pert_strength, points=None):
         """Returns the reference's 12-tuple of lists.  `points` (optional) restricts the work to a
-        subset (sharding); entries not computed are left as None."""
+        subset (sharding); entries not computed are left as None.  All host SCFs run first, then the
+        correlated solves of all points go to the GPU together (batched launches)."""
         n3 = 3 * self.natom
         res = {("R", +1): ([None] * n3, [None] * n3, [None] * n3), ("R", -1): ([None] * n3, [None] * n3, [None] * n3),
                ("B", +1): ([None] * 3, [None] * 3, [None] * 3), ("B", -1): ([None] * 3, [None] * 3, [None] * 3)}
-        for pt in (aat_points(self.natom) if points is None else points):
-            E_list, T_list, C, basis = self.solve_aat_point(pt, nuc_pert_strength, mag_pert_strength)
+        pts = list(aat_points(self.natom) if points is None else points)
+        wfns = [self.scf_aat_point(pt, nuc_pert_strength, mag_pert_strength) for pt in pts]
+        solved = correlated_many(self.parameters, wfns) if pts else []
+        for pt, wfn, (E, T_list) in zip(pts, wfns, solved):
             Cs, Bs, Ts = res[(pt[0], pt[2])]
-            Cs[pt[1]], Bs[pt[1]], Ts[pt[1]] = C, basis, T_list
+            Cs[pt[1]], Bs[pt[1]], Ts[pt[1]] = wfn.C, wfn.H.basis_set, T_list
         (npC, npB, npT), (nnC, nnB, nnT) = res[("R", +1)], res[("R", -1)]
         (mpC, mpB, mpT), (mnC, mnB, mnT) = res[("B", +1)], res[("B", -1)]
         return npC, nnC, npB, nnB, npT, nnT, mpC, mnC, mpB, mnB, mpT, mnT

@@ -135,10 +135,12 @@ def spin_block_2_dev(X):
     return out
 
 
-def gather4(src, spin, out_shape, perm1, start1, c1=1.0, perm2=None, start2=None, c2=0.0):
+def gather4(src, spin, out_shape, perm1, start1, c1=1.0, perm2=None, start2=None, c2=0.0, out=None):
     """out[x] = c1*G(start1 + x[perm1]) + c2*G(start2 + x[perm2]) -- see include/apyib_b200.h."""
     assert src.is_contiguous()
-    out = empty(tuple(out_shape), src.dtype)
+    if out is None:
+        out = empty(tuple(out_shape), src.dtype)
+    assert out.is_contiguous() and tuple(out.shape) == tuple(out_shape)
     p2 = i32(perm2) if perm2 is not None else i32(perm1)
     s2 = i64(start2) if start2 is not None else i64(start1)
     check(lib.apyib_gather4(dtype_code(src), ptr(src), i64(src.shape), int(spin), ptr(out), i64(out_shape),

@@ -112,12 +112,12 @@ def gpu_step(work, rank=0, world=1, dist=None):
     pts, own = work_items(work, rank, world)
     n3 = 3 * natom
 
-    def solve(w):
-        E, t1, t2 = apyib_b200.ci_wfn(par, w).solve_CISD()
-        return [1, t1, t2]
-
-    T0 = solve(w0)                                     # every rank needs the unperturbed amplitudes
-    mine = {p: solve(work["pts"][p]) for p, o in zip(pts, own) if o == rank}
+    from apyib_b200.ci_wfn import solve_many
+    my_pts = [p for p, o in zip(pts, own) if o == rank]
+    # every rank needs the unperturbed amplitudes; all points of the rank are solved together
+    sols = solve_many("CISD", par, [w0] + [work["pts"][p] for p in my_pts])
+    T0 = [1, sols[0][1], sols[0][2]]
+    mine = {p: [1, r[1], r[2]] for p, r in zip(my_pts, sols[1:])}
     if world > 1:
         # exchange step: every AAT element needs T(R+-alpha), T(B+-beta)  (aats.py:690-711)
         blob = {p: [1] + [x.cpu().numpy() if hasattr(x, "cpu") else x for x in T[1:]] for p, T in mine.items()}

@@ -112,11 +112,16 @@ int64_t apyib_reduce_scratch_len(void);
  * (spin_orbital: eps index p/2).  n1 = o*v (0 for CID), n2 = o*o*v*v, in the
  * solver's own (O,V) sizes.  d_E holds (re,im) of the current energy.
  * symmetrize: CID spatial only, r <- r + r^T(ij)(ab) is applied first
- * (ci_wfn.py:92; out-of-place into d_r from d_r_half).                              */
+ * (ci_wfn.py:92; out-of-place into d_r from d_r_half).
+ * Batched solves: nb finite-difference points are advanced by one launch; every per-point
+ * array is the single-point array with a leading [nb] dimension (vectors [nb][len], energies
+ * [nb][6], eps_o [nb][o_spatial], eps_v [nb][v_spatial], DIIS history [nb][8][len], Gram matrices
+ * [nb][8][8], coefficients [nb][8], reduction scratch [nb][apyib_reduce_scratch_len()]); d_active
+ * (nullable, int32[nb]) freezes converged points exactly where the reference `break`s.        */
 int apyib_ci_update(int dtype, void *d_r, void *d_t, const double *d_E,
                     const double *d_eps_o, const double *d_eps_v,
                     int64_t o, int64_t v, int has_singles, int spin_orbital,
-                    void *stream);
+                    int nb, const int32_t *d_active, void *stream);
 int apyib_symmetrize_ijab(int dtype, const void *d_half, void *d_out, int64_t o, int64_t v,
                           void *stream);
 
@@ -144,13 +149,14 @@ int apyib_dots(int dtype, const void *d_x, int64_t x_stride, int nvec, const voi
  *   d_out = { E.re, E.im, S1.re, S1.im, S2.re, S2.im },  S1 = sum_{i<n1} (t_old-t)^2, S2 = rest.
  *   m == 0 with d_iter == NULL keeps t (DIIS disabled).                                       */
 int apyib_diis_push(int dtype, const void *d_r, const void *d_t, void *d_hist_e, void *d_hist_t,
-                    int64_t len, const int32_t *d_iter, double *d_B, double *d_partials, void *stream);
+                    int64_t len, const int32_t *d_iter, double *d_B, double *d_partials,
+                    int nb, const int32_t *d_active, void *stream);
 int apyib_diis_solve(int dtype, const double *d_B, int ldb, int m, const int32_t *d_iter, double *d_c,
-                     void *stream);
+                     int nb, const int32_t *d_active, void *stream);
 int apyib_lincomb_energy_rms(int dtype, const void *d_hist, int64_t hist_stride, int m,
                              const int32_t *d_iter, const double *d_c, void *d_t, const void *d_t_old,
                              const void *d_w, int64_t n1, int64_t len, double *d_out,
-                             double *d_partials, void *stream);
+                             double *d_partials, int nb, const int32_t *d_active, void *stream);
 int apyib_iter_advance(int32_t *d_iter, void *stream);
 /* y <- alpha*op(x) + beta*y: the scaled amplitude combinations t2_dH = N_mp*T(B+) - N_mn*T(B-),
  * conj(N_np*T(R+) - N_nn*T(R-)) of aats.py:690-711 and the 2*F_ov energy weights (ci_wfn.py:504). */

@@ -109,3 +109,23 @@ def test_ci_attributes_match_reference_layout():
     assert np.abs(ci.F_MO - o.F_MO).max() < 1e-12
     assert np.abs(ci.ERI_MO - o.ERI_MO).max() < 1e-13
     assert np.array_equal(ci.D_ia, o.D_ia) and np.array_equal(ci.D_ijab, o.D_ijab)
+
+
+@pytest.mark.parametrize("method", ["CID", "CID_SO", "CISD", "CISD_SO"])
+def test_batched_solve_equals_single_solves(method):
+    """solve_many (shared launches, per-point freeze at convergence) == one solve per point"""
+    import apyib_b200
+    from apyib_b200.ci_wfn import solve_many
+    # different points converge after different iteration counts (scales differ)
+    ws = [orc.rotated_wfn(7, 3, 300 + k, False, 0, scale=sc) for k, sc in enumerate((0.005, 0.02, 0.01))]
+    ws += [orc.rotated_wfn(7, 3, 310 + k, True, 0, scale=sc) for k, sc in enumerate((0.02, 0.008))]
+    p = par(method)
+    got = solve_many(method, p, ws)
+    for w, g in zip(ws, got):
+        want = getattr(orc, "solve_" + method)(p, w)
+        assert abs(g[0] - want[0]) < E_TOL
+        for a, b in zip(g[1:], want[1:]):
+            assert a.dtype == b.dtype and np.abs(a - b).max() < T_TOL
+        single = getattr(apyib_b200.ci_wfn(p, w), "solve_" + method)()
+        for a, b in zip(g, single):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), "batched and single solves must be bit-identical"

@@ -38,13 +38,13 @@ E = zeros((6,), torch.float64)
 eps_o = torch.linspace(-2, -1, O // 2, dtype=torch.float64, device="cuda")
 eps_v = torch.linspace(1, 3, V // 2, dtype=torch.float64, device="cuda")
 timeit("copy (t_old = t)", lambda: check(lib.apyib_copy(1, ptr(told), ptr(t), n, stream_ptr())), 2 * n * 16)
-timeit("ci_update (r -= E t; t += r/D)", lambda: check(lib.apyib_ci_update(1, ptr(r), ptr(t), ptr(E), ptr(eps_o), ptr(eps_v), O, V, 1, 1, stream_ptr())), 4 * n * 16)
+timeit("ci_update (r -= E t; t += r/D)", lambda: check(lib.apyib_ci_update(1, ptr(r), ptr(t), ptr(E), ptr(eps_o), ptr(eps_v), O, V, 1, 1, 1, None, stream_ptr())), 4 * n * 16)
 hist_e, hist_t = rnd(8, n), rnd(8, n)
 B = zeros((128,), torch.float64); c = zeros((16,), torch.float64)
 it = torch.full((1,), 8, dtype=torch.int32, device="cuda")
-timeit("diis_push (m=8: copy r,t + 8 dots)", lambda: check(lib.apyib_diis_push(1, ptr(r), ptr(t), ptr(hist_e), ptr(hist_t), n, ptr(it), ptr(B), ptr(scr), stream_ptr())), (2 + 2 + 7) * n * 16)
+timeit("diis_push (m=8: copy r,t + 8 dots)", lambda: check(lib.apyib_diis_push(1, ptr(r), ptr(t), ptr(hist_e), ptr(hist_t), n, ptr(it), ptr(B), ptr(scr), 1, None, stream_ptr())), (2 + 2 + 7) * n * 16)
 c[0] = 1.0
-timeit("lincomb+energy+rms (m=8)", lambda: check(lib.apyib_lincomb_energy_rms(1, ptr(hist_t), n, 0, ptr(it), ptr(c), ptr(t), ptr(told), ptr(w), n1, n, ptr(E), ptr(scr), stream_ptr())), (8 + 1 + 2) * n * 16)
+timeit("lincomb+energy+rms (m=8)", lambda: check(lib.apyib_lincomb_energy_rms(1, ptr(hist_t), n, 0, ptr(it), ptr(c), ptr(t), ptr(told), ptr(w), n1, n, ptr(E), ptr(scr), 1, None, stream_ptr())), (8 + 1 + 2) * n * 16)
 o2 = zeros((2,), torch.float64)
 timeit("dots (1 vector)", lambda: check(lib.apyib_dots(1, ptr(r), 0, 1, ptr(t), n, 1, ptr(o2), ptr(scr), stream_ptr())), 2 * n * 16)
 timeit("axpby", lambda: check(lib.apyib_axpby(1, n, 0.5, 0.1, ptr(r), 1, 1.0, 0.0, ptr(t), stream_ptr())), 3 * n * 16)
