@@ -61,8 +61,10 @@ def exchange_points(dist, blob, world):
 
 
 def owned_elements(n3, rank, world):
-    """(alpha, beta) elements of the (3N,3) tensor evaluated by `rank` (round robin)."""
-    return [(a, b) for k, (a, b) in enumerate((a, b) for a in range(n3) for b in range(3)) if k % world == rank]
+    """(alpha, beta) elements of the (3N,3) tensor evaluated by `rank`: whole rows alpha, round
+    robin.  All determinant families that depend on alpha (pu/nu[alpha], pp/pn/np/nn[alpha][:]) are
+    then private to one rank; only the 7 alpha-independent overlaps (uu, up/un) are recomputed."""
+    return [(a, b) for a in range(n3) if a % world == rank for b in range(3)]
 
 
 def gather_tensor(dist, I, world):

@@ -135,11 +135,10 @@ def gpu_step(work, rank=0, world=1, dist=None):
             [W("B", b, +1).C for b in range(3)], [W("B", b, -1).C for b in range(3)],
             [W("B", b, +1).H.basis_set for b in range(3)], [W("B", b, -1).H.basis_set for b in range(3)],
             [T("B", b, +1) for b in range(3)], [T("B", b, -1) for b in range(3)], H_R, H_B)
+    from apyib_b200.parallel import owned_elements
     I = np.zeros((n3, 3))
-    elems = [(a, b) for a in range(n3) for b in range(3)]
-    for k, (a, b) in enumerate(elems):
-        if k % world == rank:
-            I[a, b] = A.compute_spatial_aats(a, b)
+    for a, b in owned_elements(n3, rank, world):
+        I[a, b] = A.compute_spatial_aats(a, b)
     if world > 1:
         t = torch.from_numpy(I).cuda()
         dist.all_reduce(t)                              # disjoint elements: sum == final gather of the tensor
@@ -251,7 +250,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": wl["label"], "nbf": wl["nbf"], "ndocc": wl["ndocc"], "natom": wl["natom"],
               "fd_points": 6 * wl["natom"] + 7, "h_R": H_R, "h_B": H_B, "method": "CISD",
-              "l2": "512 MB buffer written between timed steps (flush)", "sharding": "fd-points then tensor elements"}
+              "l2": "512 MB buffer written between timed steps (flush)", "sharding": "fd-points, then tensor rows alpha"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -372,6 +371,16 @@ def main():
                         "microbenchmark in this run (MEASURED_PEAKS.json has bf16/HBM only, %s). With "
                         "--aat-algorithm lemma the kernel executes ~7x fewer flops than it is credited with "
                         "here, so frac is a speed-up measure, not a pipe utilisation." % peak_src}
+    # the algorithmic fast path (determinant lemma) on the same workload, as an extra leg
+    alt = None
+    if args.aat_algorithm == "lu" and world == 1:
+        apyib_b200.config.AAT_ALGORITHM = "lemma"
+        timed_steps(1, True)
+        ta, Ia = timed_steps(args.steps, True)
+        te, Ie = timed_steps(args.steps, False)
+        apyib_b200.config.AAT_ALGORITHM = "lu"
+        alt = {"aat_algorithm": "lemma", "value": ta / args.steps, "e2e": te / args.steps, "unit": UNIT,
+               "max_abs_diff_vs_lu": float(np.abs(Ia - I_dev).max())}
     cpu_v, cpu_desc = cpu_sample(work, budget_s=20.0)
     line = {"metric": METRIC, "value": t_dev / args.steps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": False,
@@ -380,7 +389,7 @@ def main():
             "e2e": {"value": t_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "roofline": roof,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc},
-            "aat_checksum": float(np.abs(I_dev).sum())}
+            "alt": alt, "aat_checksum": float(np.abs(I_dev).sum())}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

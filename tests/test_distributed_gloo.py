@@ -71,5 +71,6 @@ def test_single_process_degenerates():
     from apyib_b200.parallel import exchange_points, owned_elements, gather_tensor
     assert exchange_points(None, {1: 2}, 1) == {1: 2}
     assert owned_elements(2, 0, 1) == [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2)]
+    assert owned_elements(3, 1, 2) == [(1, 0), (1, 1), (1, 2)]
     I = np.ones((2, 3))
     assert gather_tensor(None, I, 1) is I
