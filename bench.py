@@ -154,14 +154,39 @@ def drop_device_caches(work):
 # ---------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (numpy restatement of the reference) on a bounded sample
 # ---------------------------------------------------------------------------------------------
+def _det_worker(args):
+    """One host process of the CPU baseline: batched np.linalg.det over a slice of the substituted
+    matrices of one overlap (the arithmetic of aats.py:581-618), for `budget` seconds."""
+    nbf, no, nf, budget, seed = args
+    from oracle import apyib_oracle as orc
+    nv = nbf - no
+    sing, doub = orc.det_index_tables(no, nf, nv)
+    S = np.eye(nbf) + 1e-4 * np.random.default_rng(seed).standard_normal((nbf, nbf)).astype(complex)
+    d_sub = doub.reshape(-1, 2, 2)
+    P = len(d_sub)
+    nrow = max(1, min(P, int(2.0e5 // max(P, 1)) or 1))
+    t0 = time.perf_counter()
+    ndet = 0
+    while True:
+        orc._batched_sub_dets(S, no, d_sub[:nrow], d_sub)
+        ndet += nrow * P
+        if time.perf_counter() - t0 > budget:
+            break
+    return ndet, time.perf_counter() - t0
+
+
 def cpu_sample(work, budget_s=20.0):
-    """Times (i) oracle.solve_CISD on finite-difference points and (ii) the substituted-determinant
-    evaluation of compute_all_dets (aats.py:581-618, batched np.linalg.det) on a slice of one
-    overlap, then scales both to the whole molecule.  Returns (seconds_per_molecule, description)."""
+    """CPU baseline on ALL host cores: (i) oracle.solve_CISD on finite-difference points (numpy/BLAS
+    threads) and (ii) the substituted-determinant evaluation of compute_all_dets (aats.py:581-618,
+    batched np.linalg.det) on a slice of one overlap, run concurrently in one process per core (the
+    reference fans elements out over a multiprocessing.Pool, parallel.py:32-42); both are scaled to the
+    whole molecule by the unit counts of SURVEY 8(d).  Returns (seconds_per_molecule, description)."""
+    import multiprocessing as mp
     from oracle import apyib_oracle as orc
     par, natom = work["par"], work["natom"]
     w0 = work["w0"]
     npts = 6 * natom + 7
+    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     nsolve = 0
     for w in [w0] + list(work["pts"].values())[:3] + list(work["pts"].values())[-1:]:
@@ -172,28 +197,22 @@ def cpu_sample(work, budget_s=20.0):
     t_solve = (time.perf_counter() - t0) / nsolve
     no, nv = w0.ndocc, w0.nbf - w0.ndocc
     sing, doub = orc.det_index_tables(no, par_nfzc(work), nv)
-    S = np.eye(w0.nbf) + 1e-4 * np.random.default_rng(0).standard_normal((w0.nbf, w0.nbf)).astype(complex)
-    d_sub = doub.reshape(-1, 2, 2)
-    P = len(d_sub)
-    nrow = max(1, min(P, int(2.0e5 // max(P, 1)) or 1))
-    t0 = time.perf_counter()
-    ndet = 0
-    while True:
-        orc._batched_sub_dets(S, no, d_sub[:nrow], d_sub)
-        ndet += nrow * P
-        if time.perf_counter() - t0 > budget_s / 2:
-            break
-    t_det = (time.perf_counter() - t0) / ndet
+    P = len(doub)
+    with mp.get_context("spawn").Pool(cores) as pool:      # spawn: never fork a CUDA-initialised process
+        res = pool.map(_det_worker, [(w0.nbf, no, par_nfzc(work), budget_s / 2, k) for k in range(cores)])
+    ndet = sum(r[0] for r in res)
+    t_det = max(r[1] for r in res) / ndet                 # aggregate seconds per determinant on all cores
     n_overlaps = 1 + 6 + 6 * natom + 36 * natom
     # the reference recomputes compute_all_dets for 9 overlaps per (alpha, beta) element (aats.py:714-1008)
     n_overlaps_ref = 9 * 9 * natom
     dets_per_overlap = 1 + 2 * len(sing) + 2 * P + len(sing) ** 2 + 2 * P * len(sing) + P * P
     total = npts * t_solve + n_overlaps_ref * dets_per_overlap * t_det
-    desc = ("oracle (numpy port of ci_wfn.py:420-574 + aats.py:581-618): %d CISD solves timed (%.3f s each, x%d points) "
-            "+ %d substituted %dx%d determinants timed (%.2f us each, x%.3g dets x %d overlap evaluations as the "
-            "reference recomputes them per element; %d distinct overlaps); contraction of the 8-index tensors not "
-            "included (lower bound)" % (nsolve, t_solve, npts, ndet, no, no, t_det * 1e6, dets_per_overlap,
-                                        n_overlaps_ref, n_overlaps))
+    desc = ("oracle (numpy port of ci_wfn.py:420-574 + aats.py:581-618) on %d host cores: %d CISD solves timed "
+            "(%.3f s each, x%d points) + %d substituted %dx%d determinants timed in %d concurrent processes "
+            "(%.3f us each aggregate, x%.3g dets x %d overlap evaluations as the reference recomputes them per "
+            "element; %d distinct overlaps); contraction of the 8-index tensors not included (lower bound)"
+            % (cores, nsolve, t_solve, npts, ndet, no, no, cores, t_det * 1e6, dets_per_overlap, n_overlaps_ref,
+               n_overlaps))
     return total, desc
 
 
