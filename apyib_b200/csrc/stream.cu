@@ -71,44 +71,152 @@ gather2_kernel(const T *src, T *out, int64_t s0, int64_t s1, int64_t o0, int64_t
 
 // --------------------------------------------------------------------------------------
 // MP2  (mp2_wfn.py:42-59, 64-87)
+//
+// t2[i,j,a,b] = (ai|bj)/D is a transpose of the MO integrals: a one-thread-per-output kernel
+// reads 16-byte elements at stride n (half of every 32-byte sector wasted, 29 % of HBM peak
+// measured).  The tiled kernels below read only runs that are contiguous in the source
+// (>= o elements = 192 B at o = 12), transpose through shared memory and write t2 in runs of v
+// elements.  The exchange part of the energy is relabelled (dummy indices a <-> b, exact):
+//     E = sum (2<ij|ab> - <ij|ba>) t_ijab = sum_ijab (ia|jb) (2 t_ijab - t_ijba)
+// so that every integral read is contiguous as well.
 // --------------------------------------------------------------------------------------
-template <typename T, bool SO>
-__global__ void __launch_bounds__(kThreads)
-mp2_kernel(const T *eri, int64_t n, int64_t o, const double *eps, T *t2, double *E_out, double *partials) {
-    const int64_t O = SO ? 2 * o : o, V = SO ? 2 * (n - o) : (n - o);
-    const int64_t total = O * O * V * V;
-    const int64_t sd[4] = {n, n, n, n};
+constexpr int kMp2Threads = 256;
+
+// spatial: one CTA per (i, a); (j, b) tiles staged in shared memory.
+//   s1[b][j] = (a i | b j)   -> t_ijab        s2[b][j] = (b i | a j) -> t_ijba
+// SO_ENERGY: accumulate the spin-orbital energy 1/4 sum <IJ||AB> t_IJAB instead, spin-summed analytically
+// and relabelled so that all reads stay contiguous:
+//     E_SO = sum_ijab [ t_ijab ((ia|jb) - 1/2 (ja|ib)) + t_ijba ((ja|ib) - 1/2 (ia|jb)) ]
+template <typename T, bool SO_ENERGY>
+__global__ void __launch_bounds__(kMp2Threads)
+mp2_spatial_kernel(const T *__restrict__ eri, int64_t n, int64_t o, const double *__restrict__ eps, T *__restrict__ t2,
+                   double *E_out, double *partials, int bt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int64_t v = n - o;
+    const int oi = (int)o;
+    const int ld = oi | 1;                               // odd pitch: conflict-free transposed reads
+    T *s1 = reinterpret_cast<T *>(smem_raw), *s2 = s1 + (size_t)bt * ld;
     double acc[2] = {0.0, 0.0};
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = idx;
-        const int64_t b = r % V; r /= V;
-        const int64_t a = r % V; r /= V;
-        const int64_t j = r % O;
-        const int64_t i = r / O;
-        const int64_t A = O + a, B = O + b;
-        double D;
-        T num, L;
-        if (SO) {
-            D = eps[i >> 1] + eps[j >> 1] - eps[A >> 1] - eps[B >> 1];
-            // <ab||ij> = (ai|bj) - (aj|bi) ;  <ij||ab> = (ia|jb) - (ib|ja)
-            num = fetch4<T>(eri, sd, 1, A, i, B, j) - fetch4<T>(eri, sd, 1, A, j, B, i);
-            L = 0.25 * (fetch4<T>(eri, sd, 1, i, A, j, B) - fetch4<T>(eri, sd, 1, i, B, j, A));
-        } else {
-            D = eps[i] + eps[j] - eps[A] - eps[B];
-            num = fetch4<T>(eri, sd, 0, A, i, B, j);
-            L = 2.0 * fetch4<T>(eri, sd, 0, i, A, j, B) - fetch4<T>(eri, sd, 0, i, B, j, A);
+    // element e of a tile is (e / o, e % o) in the load phase and (e / nb, e % nb) in the compute phase;
+    // both are advanced incrementally (no integer divisions in the loops)
+    const int l_db = kMp2Threads / oi, l_dj = kMp2Threads % oi;
+    for (int64_t blk = blockIdx.x; blk < o * v; blk += gridDim.x) {
+        const int64_t i = blk / v, a = blk % v, A = o + a;
+        const T *row1 = eri + ((A * n + i) * n + o) * n;          // + b*n + j : (a i | b j)
+        const T *row2 = eri + (o * n + i) * n * n + A * n;         // + b*n^3 + j : (b i | a j)
+        const T *rowg = eri + ((i * n + A) * n) * n + o;           // + j*n + b : (i a | j b)
+        const T *rowh = eri + A * n * n + i * n + o;               // + j*n^3 + b : (j a | i b)
+        const double Dia = eps[i] - eps[A];
+        for (int64_t b0 = 0; b0 < v; b0 += bt) {
+            const int nb = (int)((v - b0 < bt) ? (v - b0) : bt);
+            const int total = nb * oi;
+            {
+                int b = threadIdx.x / oi, j = threadIdx.x % oi;
+                for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMp2Threads) {
+                    T x1[4], x2[4];
+                    int bb[4], jj[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {                              // 8 independent loads in flight
+                        bb[u] = b; jj[u] = j;
+                        if (e0 + u * kMp2Threads < total) {
+                            x1[u] = row1[(b0 + b) * n + j];
+                            x2[u] = row2[(b0 + b) * n * n * n + j];
+                        }
+                        b += l_db; j += l_dj;
+                        if (j >= oi) { j -= oi; ++b; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (e0 + u * kMp2Threads < total) {
+                            s1[bb[u] * ld + jj[u]] = x1[u];
+                            s2[bb[u] * ld + jj[u]] = x2[u];
+                        }
+                }
+            }
+            __syncthreads();
+            {
+                const int c_dj = kMp2Threads / nb, c_db = kMp2Threads % nb;
+                int j = threadIdx.x / nb, b = threadIdx.x % nb;
+                for (int e0 = threadIdx.x; e0 < total; e0 += 4 * kMp2Threads) {    // b fastest: runs of nb
+                    T g[4], g2[4];
+                    int bb[4], jj[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {                                  // integral loads first (MLP)
+                        bb[u] = b; jj[u] = j;
+                        if (e0 + u * kMp2Threads < total) {
+                            g[u] = rowg[(int64_t)j * n + b0 + b];                  // (ia|jb), contiguous in b
+                            if (SO_ENERGY) g2[u] = rowh[(int64_t)j * n * n * n + b0 + b];   // (ja|ib)
+                        }
+                        j += c_dj; b += c_db;
+                        if (b >= nb) { b -= nb; ++j; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (e0 + u * kMp2Threads >= total) continue;
+                        const int64_t B = b0 + bb[u];
+                        const double rD = 1.0 / (Dia + eps[jj[u]] - eps[o + B]);
+                        const T t = rD * s1[bb[u] * ld + jj[u]];
+                        const T tx = rD * s2[bb[u] * ld + jj[u]];
+                        t2[((i * o + jj[u]) * v + a) * v + B] = t;
+                        T ev;
+                        if (SO_ENERGY) ev = t * (g[u] - 0.5 * g2[u]) + tx * (g2[u] - 0.5 * g[u]);
+                        else ev = g[u] * (2.0 * t - tx);
+                        acc[0] += scalar<T>::re(ev);
+                        acc[1] += scalar<T>::im(ev);
+                    }
+                }
+            }
+            __syncthreads();
         }
-        const T t = scalar<T>::div_real(num, D);
-        t2[idx] = t;
-        const T e = L * t;
-        acc[0] += scalar<T>::re(e);
-        acc[1] += scalar<T>::im(e);
     }
-    grid_sum_finish<2, kThreads>(acc, partials, [&](double(&tot)[2]) {
+    grid_sum_finish<2, kMp2Threads>(acc, partials, [&](double(&tot)[2]) {
         E_out[0] = tot[0];
         E_out[1] = tot[1];
     });
+}
+
+// spin-orbital amplitudes from the spatial ones (one CTA per (I, J), B fastest):
+//   t_IJAB = [(AI|BJ) - (AJ|BI)]/D = [sA==sI][sB==sJ] t_ijab - [sA==sJ][sB==sI] t_jiab
+// with (PQ|RS) = (pq|rs)[sP==sQ][sR==sS] (utils.py:317-365; alpha = even, beta = odd).  Pure
+// streaming: 16 o^2 v^2 elements written in runs of V, the spatial t2 is read in runs of v.
+template <typename T> struct pair_t { T lo, hi; };
+template <typename T>
+__global__ void __launch_bounds__(kMp2Threads)
+mp2_so_expand_kernel(const T *__restrict__ ts, int o, int v, T *__restrict__ t2) {
+    const int O = 2 * o, V = 2 * v;
+    const int d_a = kMp2Threads / v, d_b = kMp2Threads % v;
+    for (int pr = blockIdx.x; pr < O * O; pr += gridDim.x) {
+        const int I = pr / O, J = pr - I * O;
+        const int i = I >> 1, si = I & 1, j = J >> 1, sj = J & 1;
+        const T *tij = ts + ((int64_t)i * o + j) * v * v, *tji = ts + ((int64_t)j * o + i) * v * v;
+        T *out = t2 + ((int64_t)I * O + J) * V * V;
+        // every thread turns one spatial (a, b) into its four spin components: two 2-element stores
+        const double c1 = 1.0, c2 = -1.0;
+        int a = threadIdx.x / v, b = threadIdx.x % v;
+        for (int e = threadIdx.x; e < v * v; e += kMp2Threads) {
+            const T x1 = tij[e], x2 = tji[e];
+            // value(sa, sb) = [sa==si][sb==sj] x1 - [sa==sj][sb==si] x2
+            T val[2][2];
+#pragma unroll
+            for (int sa = 0; sa < 2; ++sa)
+#pragma unroll
+                for (int sb = 0; sb < 2; ++sb) {
+                    T r = scalar<T>::zero();
+                    if (sa == si && sb == sj) r = r + c1 * x1;
+                    if (sa == sj && sb == si) r = r + c2 * x2;
+                    val[sa][sb] = r;
+                }
+#pragma unroll
+            for (int sa = 0; sa < 2; ++sa) {
+                pair_t<T> p;
+                p.lo = val[sa][0];
+                p.hi = val[sa][1];
+                *reinterpret_cast<pair_t<T> *>(out + (int64_t)(2 * a + sa) * V + 2 * b) = p;
+            }
+            a += d_a; b += d_b;
+            if (b >= v) { b -= v; ++a; }
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------
@@ -508,16 +616,37 @@ extern "C" int apyib_gather2(int dtype, const void *d_src, const int64_t src_dim
 }
 
 extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, int64_t o, const double *d_eps,
-                                   int spin_orbital, void *d_t2, double *d_E, double *d_partials, void *stream) {
+                                   int spin_orbital, void *d_t2, double *d_E, double *d_partials, void *d_work,
+                                   void *stream) {
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(d_eri_mo && d_eps && d_t2 && d_E && d_partials, "null pointer");
     APYIB_REQUIRE(n > 0 && o >= 0 && o <= n, "sizes");
-    const int64_t O = spin_orbital ? 2 * o : o, V = spin_orbital ? 2 * (n - o) : (n - o);
-    const int64_t total = O * O * V * V;
-    const int grid = stream_grid(total);
+    APYIB_REQUIRE(!spin_orbital || d_work, "spin-orbital MP2 needs a workspace of o*o*v*v elements");
     cudaStream_t st = (cudaStream_t)stream;
-#define MP2_LAUNCH(T, SO) \
-    mp2_kernel<T, SO><<<grid, kThreads, 0, st>>>((const T *)d_eri_mo, n, o, d_eps, (T *)d_t2, d_E, d_partials)
+    const int64_t v = n - o;
+    if (o == 0 || v == 0) {
+        APYIB_CUDA_CHECK(cudaMemsetAsync(d_E, 0, 2 * sizeof(double), st));
+        return APYIB_OK;
+    }
+    APYIB_REQUIRE(4 * v * v < 2147483647LL && 4 * o * o < 2147483647LL, "index range");
+    const size_t es = dtype == APYIB_C128 ? 16 : 8;
+    const int ld = (int)o | 1;
+    const size_t budget = 24 * 1024;      // small slabs -> many CTAs per SM -> enough loads in flight
+    int bt = (int)(budget / (2 * (size_t)ld * es));
+    if (bt > v) bt = (int)v;
+    if (bt < 1) bt = 1;
+    const size_t smem = 2 * (size_t)bt * ld * es;
+    APYIB_REQUIRE(smem <= 200 * 1024, "too many occupied orbitals for the shared-memory slab");
+    const int64_t work = o * v;
+    int grid = (int)(work < kReduceMaxBlocks ? work : kReduceMaxBlocks);
+    void *t_spatial = spin_orbital ? d_work : d_t2;
+#define MP2_LAUNCH(T, SOE)                                                                                        \
+    do {                                                                                                          \
+        APYIB_CUDA_CHECK(cudaFuncSetAttribute(mp2_spatial_kernel<T, SOE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              200 * 1024));                                                       \
+        mp2_spatial_kernel<T, SOE><<<grid, kMp2Threads, smem, st>>>((const T *)d_eri_mo, n, o, d_eps, (T *)t_spatial, \
+                                                                    d_E, d_partials, bt);                         \
+    } while (0)
     if (dtype == APYIB_C128) {
         if (spin_orbital) MP2_LAUNCH(cplx, true); else MP2_LAUNCH(cplx, false);
     } else {
@@ -525,6 +654,15 @@ extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, i
     }
 #undef MP2_LAUNCH
     APYIB_LAUNCH_CHECK();
+    if (spin_orbital) {
+        const int64_t pairs = 4 * o * o;
+        const int g2 = (int)(pairs < 148 * 16 ? pairs : 148 * 16);
+        if (dtype == APYIB_C128)
+            mp2_so_expand_kernel<cplx><<<g2, kMp2Threads, 0, st>>>((const cplx *)d_work, (int)o, (int)v, (cplx *)d_t2);
+        else
+            mp2_so_expand_kernel<double><<<g2, kMp2Threads, 0, st>>>((const double *)d_work, (int)o, (int)v, (double *)d_t2);
+        APYIB_LAUNCH_CHECK();
+    }
     return APYIB_OK;
 }
 

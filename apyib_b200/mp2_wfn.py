@@ -38,8 +38,9 @@ class mp2_wfn(object):
         O, V = (2 * o, 2 * (n - o)) if spin_orbital else (o, n - o)
         t2 = empty((O, O, V, V), ERI_MO.dtype)
         E = zeros((2,), torch.float64)
+        work = empty((o, o, n - o, n - o), ERI_MO.dtype) if spin_orbital else None
         check(lib.apyib_mp2_t2_energy(dtype_code(ERI_MO), ptr(ERI_MO), n, o, ptr(eps), int(spin_orbital),
-                                      ptr(t2), ptr(E), ptr(reduce_scratch()), stream_ptr()))
+                                      ptr(t2), ptr(E), ptr(reduce_scratch()), ptr(work), stream_ptr()))
         e = to_host(E)
         if ERI_MO.dtype == torch.complex128:
             E_MP2 = np.complex128(complex(e[0], e[1]))

@@ -100,10 +100,11 @@ int apyib_gather2(int dtype, const void *d_src, const int64_t src_dims[2], int s
  * spin_orbital: same on the spin-blocked, antisymmetrised integrals,
  *           t2 = <ab||ij>/D , E = 1/4 sum <ij||ab> t2   (O = 2o, V = 2v)
  * d_eps: n orbital energies (double).  d_E: 2 doubles (re, im), written.
+ * d_work: spin_orbital only, scratch of o*o*v*v elements (the spatial amplitudes).
  * d_partials: zero-initialised scratch of apyib_reduce_scratch_len() doubles.         */
 int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, int64_t o,
                         const double *d_eps, int spin_orbital,
-                        void *d_t2, double *d_E, double *d_partials, void *stream);
+                        void *d_t2, double *d_E, double *d_partials, void *d_work, void *stream);
 int64_t apyib_reduce_scratch_len(void);
 
 /* ---- CI amplitude update (ci_wfn.py:93-94, 220-221, 316+334+336-337, 464+483+485-486)
