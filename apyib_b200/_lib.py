@@ -34,7 +34,7 @@ SIGNATURES = {
     "apyib_gather2": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _vp]),
     "apyib_mp2_t2_energy": (_int, [_int, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "apyib_reduce_scratch_len": (_i64, []),
-    "apyib_ci_update": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
+    "apyib_ci_update": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "apyib_symmetrize_ijab": (_int, [_int, _vp, _vp, _i64, _i64, _vp]),
     "apyib_dots": (_int, [_int, _vp, _i64, _int, _vp, _i64, _int, _vp, _vp, _vp]),
     "apyib_diis_push": (_int, [_int, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _int, _vp, _vp]),

@@ -94,9 +94,16 @@ class _Engine:
         return x[:, self.n1:].view(self.nb, self.O, self.O, self.V, self.V)
 
     def _update(self):
-        check(lib.apyib_ci_update(self.code, ptr(self.r), ptr(self.t), ptr(self.out6), ptr(self.eps_o),
-                                  ptr(self.eps_v), self.O, self.V, int(self.has_singles), self.so, self.nb,
-                                  ptr(self.active), stream_ptr()))
+        lr = getattr(self, "lr", None)      # linear-response mode: (E_fixed, E2_offset, t_fixed)
+        if lr is None:
+            check(lib.apyib_ci_update(self.code, ptr(self.r), ptr(self.t), ptr(self.out6), ptr(self.eps_o),
+                                      ptr(self.eps_v), self.O, self.V, int(self.has_singles), self.so, self.nb,
+                                      ptr(self.active), _NULL, _NULL, _NULL, stream_ptr()))
+        else:
+            E_fixed, E2_off, t_fixed = lr
+            check(lib.apyib_ci_update(self.code, ptr(self.r), ptr(self.t), ptr(E_fixed), ptr(self.eps_o),
+                                      ptr(self.eps_v), self.O, self.V, int(self.has_singles), self.so, self.nb,
+                                      ptr(self.active), ptr(self.out6), ptr(E2_off), ptr(t_fixed), stream_ptr()))
 
     def _energy_rms(self, use_diis):
         if use_diis:
@@ -119,6 +126,9 @@ class _Engine:
 
     def initial_guess(self):
         """t = r0 / D, E = w.t   (ci_wfn.py:66-70, 193-197, 286-293, 435-442)."""
+        if getattr(self, "custom_guess", None) is not None:
+            self.custom_guess()
+            return
         self.out6.zero_()
         self.t.zero_()
         self._copy(self.r, self.r0)
@@ -222,10 +232,10 @@ def _sizes(points, so):
     return O, V, {"o": (0, O), "v": (O, O + V)}
 
 
-def _stack(points, fn, shape, dtype):
-    out = empty((len(points),) + tuple(shape), dtype)
-    for s, pt in enumerate(points):
-        fn(pt, out[s])
+def _stack(items, fn, shape, dtype):
+    out = empty((len(items),) + tuple(shape), dtype)
+    for s, it in enumerate(items):
+        fn(it, out[s])
     return out
 
 
@@ -351,56 +361,147 @@ def _solve_CISD_SO(parameters, points, print_level):
     return eng, E
 
 
+class _CISDOperator:
+    """Spatial-orbital CISD residual of ci_wfn.py:457-483 for a stack of points, split into its
+    constant part (F_ai | <ab|ij>), its energy weights (2 F_ov | 2<ij|ab>-<ij|ba>) and the part that is
+    linear in the amplitudes -- the same contraction set serves the CISD solver and the
+    perturbed-amplitude (linear-response) iterations of analytic_aats.py:780-885 / 1032-1137."""
+
+    def __init__(self, Fs, ERIs, O, V, bd, dt):
+        nb = len(ERIs)
+        self.nb, self.O, self.V, self.n1 = nb, O, V, O * V
+        sp = dict(i="o", j="o", k="o", l="o", a="v", b="v", c="v", d="v")
+        blk = lambda lab, outl=None, c1=1.0, c2=0.0: _stack(
+            ERIs, lambda E, out: w_block(E, lab, outl or lab, sp, bd, 0, c1, c2, out=out),
+            [bd[sp[ch]][1] - bd[sp[ch]][0] for ch in (outl or lab)], dt)
+        F = torch.stack(list(Fs))
+        self.Foo, self.Fvv, self.Fov = F[:, :O, :O], F[:, O:, O:], F[:, :O, O:].contiguous()
+        self.Fai = F[:, O:, :O].transpose(1, 2).reshape(nb, -1)                 # F_ai as [i,a]  ci_wfn.py:457
+        self.K = blk("abij", "ijab").reshape(nb, -1)                             # <ab|ij>        :466
+        w1 = empty((nb, self.n1), dt)
+        check(lib.apyib_axpby(1 if dt == torch.complex128 else 0, nb * self.n1, 2.0, 0.0, ptr(self.Fov), 0, 0.0, 0.0,
+                              ptr(w1), stream_ptr()))                            # 2 F_ov         :504
+        self.w1 = w1
+        self.w2 = blk("ijab", None, 2.0, -1.0).reshape(nb, -1)                   # 2<ij|ab>-<ij|ba>
+        self.Wovvo, self.Wovov = blk("kbcj"), blk("kbic")
+        self.Lovvo = blk("jabi", None, 2.0, -1.0)                                # 2<ja|bi>-<ja|ib>  :460,478,481
+        self.Lvovv = blk("ajbc", None, 2.0, -1.0)                                # :462
+        self.Looov = blk("kjib", None, 2.0, -1.0)                                # :463
+        self.Wvvvo, self.Wvvov, self.Wovoo, self.Wvooo = blk("abcj"), blk("abic"), blk("kbij"), blk("akij")
+        self.Woooo, self.Wvvvv = blk("klij"), blk("abcd")
+
+    def apply(self, t1, t2, r1, r2):
+        """r += (linear part of the CISD residual)(t1, t2)"""
+        o = self
+        contract("sji,sja->sia", o.Foo, t1, r1, -1.0, 1.0)                  # :458
+        contract("sab,sib->sia", o.Fvv, t1, r1, 1.0, 1.0)                   # :459
+        contract("sjabi,sjb->sia", o.Lovvo, t1, r1, 1.0, 1.0)               # :460
+        contract("sjb,sijab->sia", o.Fov, t2, r1, 2.0, 1.0)                 # :461  F.(2 t2 - t2^T)
+        contract("sjb,sijba->sia", o.Fov, t2, r1, -1.0, 1.0)
+        contract("sajbc,sijbc->sia", o.Lvovv, t2, r1, 1.0, 1.0)             # :462
+        contract("skjib,skjab->sia", o.Looov, t2, r1, -1.0, 1.0)            # :463
+        contract("sabcj,sic->sijab", o.Wvvvo, t1, r2, 1.0, 1.0)             # :467
+        contract("sabic,sjc->sijab", o.Wvvov, t1, r2, 1.0, 1.0)             # :468
+        contract("skbij,ska->sijab", o.Wovoo, t1, r2, -1.0, 1.0)            # :469
+        contract("sakij,skb->sijab", o.Wvooo, t1, r2, -1.0, 1.0)            # :470
+        contract("sac,sijcb->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :471
+        contract("sbc,sijac->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :472
+        contract("ski,skjab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :473
+        contract("skj,sikab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :474
+        contract("sklij,sklab->sijab", o.Woooo, t2, r2, 1.0, 1.0)           # :475
+        contract("sabcd,sijcd->sijab", o.Wvvvv, t2, r2, 1.0, 1.0)           # :476
+        contract("skbcj,sikca->sijab", o.Wovvo, t2, r2, -1.0, 1.0)          # :477
+        contract("skaci,skjcb->sijab", o.Lovvo, t2, r2, 1.0, 1.0)           # :478
+        contract("skbic,skjac->sijab", o.Wovov, t2, r2, -1.0, 1.0)          # :479
+        contract("skaci,skjbc->sijab", o.Wovvo, t2, r2, -1.0, 1.0)          # :480
+        contract("skbcj,sikac->sijab", o.Lovvo, t2, r2, 1.0, 1.0)           # :481
+        contract("skajc,sikcb->sijab", o.Wovov, t2, r2, -1.0, 1.0)          # :482
+
+
 def _solve_CISD(parameters, points, print_level):
     """Spatial-orbital CISD (ci_wfn.py:420-574)."""
     eng, O, V, bd = _make_engine(parameters, points, True, False)
-    dt, nb, n1 = eng.dtype, eng.nb, eng.n1
-    sp = dict(i="o", j="o", k="o", l="o", a="v", b="v", c="v", d="v")
-    blk = _blocks(points, sp, bd, dt, 0)
-    F = torch.stack([pt.F for pt in points])
-    Foo, Fvv, Fov = F[:, :O, :O], F[:, O:, O:], F[:, :O, O:].contiguous()
-    eng.r0[:, :n1].copy_(F[:, O:, :O].transpose(1, 2).reshape(nb, -1))     # ci_wfn.py:457
-    eng.r0[:, n1:].copy_(blk("abij", "ijab").reshape(nb, -1))             # :466
-    w1 = empty((nb, n1), dt)
-    check(lib.apyib_axpby(eng.code, nb * n1, 2.0, 0.0, ptr(Fov), 0, 0.0, 0.0, ptr(w1), stream_ptr()))   # 2 F_ov  :504
-    eng.w[:, :n1].copy_(w1)
-    eng.w[:, n1:].copy_(blk("ijab", None, 2.0, -1.0).reshape(nb, -1))
-    Wovvo, Wovov = blk("kbcj"), blk("kbic")
-    Lovvo = blk("jabi", None, 2.0, -1.0)                                  # 2<ja|bi>-<ja|ib>  :460,478,481
-    Lvovv = blk("ajbc", None, 2.0, -1.0)                                  # :462
-    Looov = blk("kjib", None, 2.0, -1.0)                                  # :463
-    Wvvvo, Wvvov, Wovoo, Wvooo = blk("abcj"), blk("abic"), blk("kbij"), blk("akij")
-    Woooo, Wvvvv = blk("klij"), blk("abcd")
-
-    def residual(_):
-        t1, t2 = eng.t1(), eng.t2()
-        r1, r2 = eng.t1(eng.r), eng.t2(eng.r)
-        contract("sji,sja->sia", Foo, t1, r1, -1.0, 1.0)                  # :458
-        contract("sab,sib->sia", Fvv, t1, r1, 1.0, 1.0)                   # :459
-        contract("sjabi,sjb->sia", Lovvo, t1, r1, 1.0, 1.0)               # :460
-        contract("sjb,sijab->sia", Fov, t2, r1, 2.0, 1.0)                 # :461  F.(2 t2 - t2^T)
-        contract("sjb,sijba->sia", Fov, t2, r1, -1.0, 1.0)
-        contract("sajbc,sijbc->sia", Lvovv, t2, r1, 1.0, 1.0)             # :462
-        contract("skjib,skjab->sia", Looov, t2, r1, -1.0, 1.0)            # :463
-        contract("sabcj,sic->sijab", Wvvvo, t1, r2, 1.0, 1.0)             # :467
-        contract("sabic,sjc->sijab", Wvvov, t1, r2, 1.0, 1.0)             # :468
-        contract("skbij,ska->sijab", Wovoo, t1, r2, -1.0, 1.0)            # :469
-        contract("sakij,skb->sijab", Wvooo, t1, r2, -1.0, 1.0)            # :470
-        contract("sac,sijcb->sijab", Fvv, t2, r2, 1.0, 1.0)               # :471
-        contract("sbc,sijac->sijab", Fvv, t2, r2, 1.0, 1.0)               # :472
-        contract("ski,skjab->sijab", Foo, t2, r2, -1.0, 1.0)              # :473
-        contract("skj,sikab->sijab", Foo, t2, r2, -1.0, 1.0)              # :474
-        contract("sklij,sklab->sijab", Woooo, t2, r2, 1.0, 1.0)           # :475
-        contract("sabcd,sijcd->sijab", Wvvvv, t2, r2, 1.0, 1.0)           # :476
-        contract("skbcj,sikca->sijab", Wovvo, t2, r2, -1.0, 1.0)          # :477
-        contract("skaci,skjcb->sijab", Lovvo, t2, r2, 1.0, 1.0)           # :478
-        contract("skbic,skjac->sijab", Wovov, t2, r2, -1.0, 1.0)          # :479
-        contract("skaci,skjbc->sijab", Wovvo, t2, r2, -1.0, 1.0)          # :480
-        contract("skbcj,sikac->sijab", Lovvo, t2, r2, 1.0, 1.0)           # :481
-        contract("skajc,sikcb->sijab", Wovov, t2, r2, -1.0, 1.0)          # :482
-
+    n1 = eng.n1
+    op = _CISDOperator([pt.F for pt in points], [pt.ERI for pt in points], O, V, bd, eng.dtype)
+    eng.r0[:, :n1].copy_(op.Fai)
+    eng.r0[:, n1:].copy_(op.K)
+    eng.w[:, :n1].copy_(op.w1)
+    eng.w[:, n1:].copy_(op.w2)
+    residual = lambda _: op.apply(eng.t1(), eng.t2(), eng.t1(eng.r), eng.t2(eng.r))
     E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
     return eng, E
+
+
+def solve_perturbed_CISD(parameters, ci, t1, t2, E_CISD, dF_MO, dERI_MO, dE_guess=0.0, print_level=0):
+    """Perturbed-amplitude (linear-response) iterations of the analytic CISD AAT route,
+    analytic_aats.py:742-885 (magnetic field) and :994-1137 (nuclear displacement): given the
+    converged spatial CISD wavefunction (t1, t2, E_CISD) of `ci` and the perturbed MO Fock matrix /
+    chemists' MO integrals (dF_MO, dERI_MO: host inputs from CPHF + Psi4 derivative integrals),
+    solve  dR(t; dF, dERI) - dE t + R_lin(dt; F, ERI) - E_CISD dt = 0  for (dt1, dt2) with the
+    reference's Jacobi/DIIS iteration.  `dE_guess` is the relaxed energy derivative the reference
+    uses for its starting guess (:743, :759).  Returns (dE_proj, dt1, dt2).
+
+    The part of the residual that only involves the unperturbed amplitudes is built once (the
+    reference rebuilds it every iteration); each iteration then costs one CISD contraction set."""
+    pt = ci.point()
+    dt_ = pt.ERI.dtype
+    cast = lambda x: to_device(np.asarray(x), dt_)
+    dF, dERI = cast(dF_MO), cast(dERI_MO)
+    eng, O, V, bd = _make_engine(parameters, [pt], True, False)
+    n1, L = eng.n1, eng.len
+    op0 = _CISDOperator([pt.F], [pt.ERI], O, V, bd, dt_)
+    op1 = _CISDOperator([dF], [dERI], O, V, bd, dt_)
+    tfix = zeros((1, L), dt_)
+    tfix[:, :n1].copy_(cast(t1).reshape(1, -1))
+    tfix[:, n1:].copy_(cast(t2).reshape(1, -1))
+    # constant part: dF_ai | d<ab|ij>  +  (perturbed integrals) x (unperturbed amplitudes)
+    eng.r0[:, :n1].copy_(op1.Fai)
+    eng.r0[:, n1:].copy_(op1.K)
+    op1.apply(eng.t1(tfix), eng.t2(tfix), eng.t1(eng.r0), eng.t2(eng.r0))
+    eng.w[:, :n1].copy_(op0.w1)
+    eng.w[:, n1:].copy_(op0.w2)
+    # constant part of the projected energy derivative: 2 t1.dF_ov + t2.(2 d<ij|ab> - d<ij|ba>)  (:774, :868)
+    wd = zeros((1, L), dt_)
+    wd[:, :n1].copy_(op1.w1)
+    wd[:, n1:].copy_(op1.w2)
+    c0 = zeros((2,), torch.float64)
+    check(lib.apyib_dots(eng.code, ptr(wd), 0, 1, ptr(tfix), L, 0, ptr(c0), ptr(eng.scratch), stream_ptr()))
+    E2_off = zeros((1, 6), torch.float64)
+    E2_off[0, :2].copy_(c0)
+    E_fixed = zeros((1, 6), torch.float64)
+    Ec = complex(E_CISD)
+    E_fixed[0, 0], E_fixed[0, 1] = Ec.real, Ec.imag
+    c0h = to_host(c0)
+    c0v = complex(c0h[0], c0h[1]) if eng.code else float(c0h[0])
+
+    def guess():
+        # dt = [ -dE_guess t + (perturbed integrals) x t ] / D      (:743-772; no dF_ai / d<ab|ij> term)
+        eng.out6.zero_()
+        eng.t.zero_()
+        eng._copy(eng.r, eng.r0)
+        g = complex(dE_guess)
+        a = lambda alpha, x, y: check(lib.apyib_axpby(eng.code, x.numel(), alpha.real, alpha.imag, ptr(x), 0, 1.0, 0.0,
+                                                     ptr(y), stream_ptr()))
+        cons = zeros((1, L), dt_)
+        cons[:, :n1].copy_(op1.Fai)
+        cons[:, n1:].copy_(op1.K)
+        a(complex(-1.0), cons, eng.r)
+        a(-g, tfix, eng.r)
+        eng.lr = None
+        eng._update()                                  # E = 0: dt = r / D
+        eng.lr = (E_fixed, E2_off, tfix)
+        eng._copy(eng.t_old, eng.t)
+        eng._energy_rms(False)
+
+    eng.custom_guess = guess
+    eng.lr = (E_fixed, E2_off, tfix)
+    residual = lambda _: op0.apply(eng.t1(), eng.t2(), eng.t1(eng.r), eng.t2(eng.r))
+    E = eng.run(residual, print_level)
+    dE = E[0] + c0v
+    ci.iterations = eng.iterations[0]
+    if config.RETURN_DEVICE:
+        return dE, eng.t1()[0].clone(), eng.t2()[0].clone()
+    return dE, to_host(eng.t1())[0].copy(), to_host(eng.t2())[0].copy()
 
 
 _SOLVERS = {"CID": (_solve_CID, False), "CID_SO": (_solve_CID_SO, False),

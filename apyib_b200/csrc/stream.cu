@@ -231,12 +231,19 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 ci_update_kernel(T *__restrict__ r, T *__restrict__ t, const double *__restrict__ E, const double *__restrict__ eps_o,
                  const double *__restrict__ eps_v, int64_t o, int64_t v, int64_t n1, int64_t n2, int sh,
-                 const int32_t *__restrict__ active) {
+                 const int32_t *__restrict__ active, const double *__restrict__ E2, const double *__restrict__ E2off,
+                 const T *__restrict__ tfix) {
     const int z = blockIdx.y;                      // finite-difference point of a batched solve
     if (active != nullptr && active[z] == 0) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, len = n1 + n2;
     r += z * len; t += z * len; E += z * 6; eps_o += z * (o >> sh); eps_v += z * (v >> sh);
     const T Ec = scalar<T>::make(E[0], E[1]);
+    // linear-response form (analytic_aats.py:788-836): r <- r - E t - (E2 + E2off) t_fixed
+    T E2c = scalar<T>::zero();
+    if (tfix != nullptr) {
+        tfix += z * len;
+        E2c = scalar<T>::make(E2[z * 6] + E2off[z * 6], E2[z * 6 + 1] + E2off[z * 6 + 1]);
+    }
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += kUnroll * stride) {
         T tv[kUnroll], rv[kUnroll];
 #pragma unroll
@@ -260,7 +267,8 @@ ci_update_kernel(T *__restrict__ r, T *__restrict__ t, const double *__restrict_
                 const int64_t i = q / o;
                 D = eps_o[i >> sh] + eps_o[j >> sh] - eps_v[a >> sh] - eps_v[b >> sh];
             }
-            const T rn = rv[u] - Ec * tv[u];
+            T rn = rv[u] - Ec * tv[u];
+            if (tfix != nullptr) rn = rn - E2c * tfix[idx];
             r[idx] = rn;
             t[idx] = tv[u] + scalar<T>::div_real(rn, D);
         }
@@ -668,7 +676,9 @@ extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, i
 
 extern "C" int apyib_ci_update(int dtype, void *d_r, void *d_t, const double *d_E, const double *d_eps_o,
                                const double *d_eps_v, int64_t o, int64_t v, int has_singles, int spin_orbital,
-                               int nb, const int32_t *d_active, void *stream) {
+                               int nb, const int32_t *d_active, const double *d_E2, const double *d_E2_offset,
+                               const void *d_t_fixed, void *stream) {
+    APYIB_REQUIRE(d_t_fixed == nullptr || (d_E2 && d_E2_offset), "linear-response form needs E2 and its offset");
     APYIB_REQUIRE(nb >= 1 && nb <= 65535, "batch");
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(d_r && d_t && d_E && d_eps_o && d_eps_v, "null pointer");
@@ -678,9 +688,9 @@ extern "C" int apyib_ci_update(int dtype, void *d_r, void *d_t, const double *d_
     const dim3 grid(stream_grid(n1 + n2), nb);
     const int sh = spin_orbital ? 1 : 0;
     if (dtype == APYIB_C128)
-        ci_update_kernel<cplx><<<grid, kThreads, 0, st>>>((cplx *)d_r, (cplx *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh, d_active);
+        ci_update_kernel<cplx><<<grid, kThreads, 0, st>>>((cplx *)d_r, (cplx *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh, d_active, d_E2, d_E2_offset, (const cplx *)d_t_fixed);
     else
-        ci_update_kernel<double><<<grid, kThreads, 0, st>>>((double *)d_r, (double *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh, d_active);
+        ci_update_kernel<double><<<grid, kThreads, 0, st>>>((double *)d_r, (double *)d_t, d_E, d_eps_o, d_eps_v, o, v, n1, n2, sh, d_active, d_E2, d_E2_offset, (const double *)d_t_fixed);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }

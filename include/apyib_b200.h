@@ -118,11 +118,16 @@ int64_t apyib_reduce_scratch_len(void);
  * array is the single-point array with a leading [nb] dimension (vectors [nb][len], energies
  * [nb][6], eps_o [nb][o_spatial], eps_v [nb][v_spatial], DIIS history [nb][8][len], Gram matrices
  * [nb][8][8], coefficients [nb][8], reduction scratch [nb][apyib_reduce_scratch_len()]); d_active
- * (nullable, int32[nb]) freezes converged points exactly where the reference `break`s.        */
+ * (nullable, int32[nb]) freezes converged points exactly where the reference `break`s.
+ * Linear-response form (perturbed-amplitude iterations, analytic_aats.py:788-836, 1040-1088):
+ * with d_t_fixed != NULL the update is r <- r - E*t - (E2 + E2_offset)*t_fixed, where t is the
+ * perturbed amplitude vector, E = E_CISD (fixed), t_fixed the unperturbed amplitudes and
+ * E2 + E2_offset the running projected energy derivative ([nb][6] layout like d_E).             */
 int apyib_ci_update(int dtype, void *d_r, void *d_t, const double *d_E,
                     const double *d_eps_o, const double *d_eps_v,
                     int64_t o, int64_t v, int has_singles, int spin_orbital,
-                    int nb, const int32_t *d_active, void *stream);
+                    int nb, const int32_t *d_active,
+                    const double *d_E2, const double *d_E2_offset, const void *d_t_fixed, void *stream);
 int apyib_symmetrize_ijab(int dtype, const void *d_half, void *d_out, int64_t o, int64_t v,
                           void *stream);
 

@@ -803,3 +803,65 @@ def compute_SO_aats(A, alpha, beta, normalization="full"):
     I = so_aat_terms(A, alpha, beta, normalization)
     k = 1 / (4 * A.nuc_pert_strength * A.mag_pert_strength)
     return sum(k * np.imag(x) for x in I.values())
+
+
+# ----------------------------------------------------------------------------
+# a21  perturbed-amplitude (linear-response) CISD iterations   analytic_aats.py:742-885, 994-1137
+# ----------------------------------------------------------------------------
+def _cisd_linear(F, W, o, v, t1, t2):
+    """linear part of the spatial CISD residual (ci_wfn.py:458-482) for Fock F and <pq|rs> W"""
+    Lovvo = 2.0 * W[o, v, v, o] - W.swapaxes(2, 3)[o, v, v, o]
+    r1 = -np.einsum("ji,ja->ia", F[o, o], t1) + np.einsum("ab,ib->ia", F[v, v], t1)
+    r1 = r1 + np.einsum("jabi,jb->ia", Lovvo, t1)
+    r1 += np.einsum("jb,ijab->ia", F[o, v], 2.0 * t2 - t2.swapaxes(2, 3))
+    r1 += np.einsum("ajbc,ijbc->ia", 2.0 * W[v, o, v, v] - W.swapaxes(2, 3)[v, o, v, v], t2, optimize=True)
+    r1 -= np.einsum("kjib,kjab->ia", 2.0 * W[o, o, o, v] - W.swapaxes(2, 3)[o, o, o, v], t2, optimize=True)
+    r2 = np.einsum("abcj,ic->ijab", W[v, v, v, o], t1, optimize=True)
+    r2 = r2 + np.einsum("abic,jc->ijab", W[v, v, o, v], t1, optimize=True)
+    r2 -= np.einsum("kbij,ka->ijab", W[o, v, o, o], t1, optimize=True)
+    r2 -= np.einsum("akij,kb->ijab", W[v, o, o, o], t1, optimize=True)
+    r2 += np.einsum("ac,ijcb->ijab", F[v, v], t2) + np.einsum("bc,ijac->ijab", F[v, v], t2)
+    r2 -= np.einsum("ki,kjab->ijab", F[o, o], t2) + np.einsum("kj,ikab->ijab", F[o, o], t2)
+    r2 += np.einsum("klij,klab->ijab", W[o, o, o, o], t2, optimize=True)
+    r2 += np.einsum("abcd,ijcd->ijab", W[v, v, v, v], t2, optimize=True)
+    r2 -= np.einsum("kbcj,ikca->ijab", W[o, v, v, o], t2, optimize=True)
+    r2 += np.einsum("kaci,kjcb->ijab", Lovvo, t2, optimize=True)
+    r2 -= np.einsum("kbic,kjac->ijab", W[o, v, o, v], t2, optimize=True)
+    r2 -= np.einsum("kaci,kjbc->ijab", W[o, v, v, o], t2, optimize=True)
+    r2 += np.einsum("kbcj,ikac->ijab", Lovvo, t2, optimize=True)
+    r2 -= np.einsum("kajc,ikcb->ijab", W[o, v, o, v], t2, optimize=True)
+    return r1, r2
+
+
+def solve_perturbed_CISD(parameters, wfn, t1, t2, E_CISD, dF_MO, dERI_MO, dE_guess=0.0, return_iters=False):
+    """dt/dlambda of the CISD amplitudes for perturbed MO integrals (dF_MO, chemists' dERI_MO)."""
+    ci = _CI(parameters, wfn)
+    o, v = ci.I_list[1], ci.I_list[2]
+    F, W, D1, D2 = ci.F_MO, ci.ERI_MO.swapaxes(1, 2), ci.D_ia, ci.D_ijab
+    dF, dW = dF_MO, dERI_MO.swapaxes(1, 2)
+    L = 2.0 * W[o, o, v, v] - W.swapaxes(2, 3)[o, o, v, v]
+    dL = 2.0 * dW[o, o, v, v] - dW.swapaxes(2, 3)[o, o, v, v]
+    dK = dW.swapaxes(0, 2).swapaxes(1, 3)[o, o, v, v]
+    p1, p2 = _cisd_linear(dF, dW, o, v, t1, t2)
+    dt1 = (-dE_guess * t1 + p1) / D1                                        # :743-772
+    dt2 = (-dE_guess * t2 + p2) / D2
+    proj = lambda dt1, dt2: (2.0 * np.einsum("ia,ia->", t1, dF[o, v]) + np.einsum("ijab,ijab->", t2, dL)
+                             + 2.0 * np.einsum("ia,ia->", dt1, F[o, v]) + np.einsum("ijab,ijab->", dt2, L))
+    dE = proj(dt1, dt2)
+    diis = _Diis(parameters["DIIS"])
+    it = 1
+    while it <= parameters["max_iterations"]:
+        dE_old, o1, o2 = dE, dt1.copy(), dt2.copy()
+        q1, q2 = _cisd_linear(F, W, o, v, dt1, dt2)
+        r1 = dF.swapaxes(0, 1)[o, v] - dE * t1 + p1 - E_CISD * dt1 + q1       # :788-806
+        r2 = dK - dE * t2 + p2 - E_CISD * dt2 + q2                           # :808-846
+        dt1 = dt1 + r1 / D1
+        dt2 = dt2 + r2 / D2
+        dt1, dt2 = diis(it, [r1, r2], [dt1, dt2])
+        dE = proj(dt1, dt2)
+        rms1 = np.sqrt(np.einsum("ia,ia->", o1 - dt1, o1 - dt1))
+        rms2 = np.sqrt(np.einsum("ijab,ijab->", o2 - dt2, o2 - dt2))
+        if _converged(parameters, it, dE_old - dE, [rms1, rms2]):
+            break
+        it += 1
+    return (dE, dt1, dt2, min(it, parameters["max_iterations"])) if return_iters else (dE, dt1, dt2)

@@ -156,10 +156,50 @@ def synthetic(ns):
     np.savez_compressed(os.path.join(HERE, "synthetic_aat.npz"), **out)
 
 
+PERT_CASES = [("r7", 7, 3, 0, False, 901), ("c6", 6, 2, 0, True, 902), ("r8fc", 8, 3, 1, False, 903)]
+
+
+def perturbation(n, cplx, seed):
+    """Seeded perturbed MO integrals (dF Hermitian, dERI with the MO-integral symmetries)."""
+    rng = np.random.default_rng(seed)
+    dF = rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cplx else 0)
+    dF = 0.1 * (dF + dF.conj().T)
+    dG = 0.01 * (rng.standard_normal((n,) * 4) + (0.1j * rng.standard_normal((n,) * 4) if cplx else 0))
+    dG = dG + dG.transpose(2, 3, 0, 1)
+    dG = dG + dG.transpose(1, 0, 3, 2).conj()
+    return dF, dG
+
+
+def linear_response(ns):
+    """a21: the reference's analytic perturbed-amplitude loop (analytic_aats.py:780-885) needs Psi4
+    derivative integrals and cannot run here.  The fixture instead holds CENTRAL FINITE DIFFERENCES of
+    the UNMODIFIED reference solve_CISD under F_MO + lam dF, ERI_MO + lam dERI: the quantity the
+    linear-response iteration converges to."""
+    out = {}
+    lam = 1e-4
+    for name, nbf, no, nf, cplx, seed in PERT_CASES:
+        w = orc.rotated_wfn(nbf, no, seed, cplx, nf)
+        p = par("CISD", nf > 0, maxit=300, conv=1e-14)
+        dF, dG = perturbation(nbf - nf, cplx, seed + 50)
+
+        def solve(l):
+            r = ns.ci_wfn.ci_wfn(p, w)
+            r.F_MO = r.F_MO + l * dF
+            r.ERI_MO = r.ERI_MO + l * dG
+            return quiet(r.solve_CISD)
+        (Ep, t1p, t2p), (Em, t1m, t2m), (E0, t1, t2) = solve(lam), solve(-lam), solve(0.0)
+        out[name + "/dE"] = np.asarray((Ep - Em) / (2 * lam))
+        out[name + "/dt1"] = (t1p - t1m) / (2 * lam)
+        out[name + "/dt2"] = (t2p - t2m) / (2 * lam)
+        out[name + "/E0"], out[name + "/t1"], out[name + "/t2"] = np.asarray(E0), t1, t2
+    np.savez_compressed(os.path.join(HERE, "synthetic_linear_response.npz"), **out)
+
+
 if __name__ == "__main__":
     lit = extract_literals()
     json.dump(lit, open(os.path.join(HERE, "reference_literals.json"), "w"), indent=1)
     print("literals:", [(c["test"], sorted(c["arrays"])) for c in lit["cases"]])
     ns = ref_harness.load()
     synthetic(ns)
+    linear_response(ns)
     print("wrote", sorted(os.listdir(HERE)))

@@ -131,3 +131,21 @@ def _check_aat_case(c):
         for k in ("00", "DD"):
             if "I_%s_ref" % k in c["arrays"]:
                 assert np.abs(T[k] - np.array(c["arrays"]["I_%s_ref" % k])).max() < 1e-8
+
+
+# ---- a21: perturbed-amplitude (linear-response) CISD iterations ---------------------------------
+from golden.make_golden import PERT_CASES, perturbation   # noqa: E402
+LRG = np.load(os.path.join(HERE, "golden", "synthetic_linear_response.npz"))
+
+
+@pytest.mark.parametrize("name,nbf,no,nf,cplx,seed", PERT_CASES)
+def test_linear_response_matches_finite_differences_of_reference_solver(name, nbf, no, nf, cplx, seed):
+    """analytic_aats.py:780-885 restated; pinned by central differences of the unmodified reference
+    solve_CISD under perturbed MO integrals (the reference's own loop needs Psi4 derivative integrals)."""
+    w = orc.rotated_wfn(nbf, no, seed, cplx, nf)
+    p = par("CISD", nf > 0, maxit=300, conv=1e-14)
+    dF, dG = perturbation(nbf - nf, cplx, seed + 50)
+    dE, dt1, dt2 = orc.solve_perturbed_CISD(p, w, LRG[name + "/t1"], LRG[name + "/t2"], LRG[name + "/E0"], dF, dG)
+    assert abs(dE - LRG[name + "/dE"]) < 1e-8
+    assert np.abs(dt1 - LRG[name + "/dt1"]).max() < 1e-8
+    assert np.abs(dt2 - LRG[name + "/dt2"]).max() < 1e-8

@@ -38,7 +38,7 @@ E = zeros((6,), torch.float64)
 eps_o = torch.linspace(-2, -1, O // 2, dtype=torch.float64, device="cuda")
 eps_v = torch.linspace(1, 3, V // 2, dtype=torch.float64, device="cuda")
 timeit("copy (t_old = t)", lambda: check(lib.apyib_copy(1, ptr(told), ptr(t), n, stream_ptr())), 2 * n * 16)
-timeit("ci_update (r -= E t; t += r/D)", lambda: check(lib.apyib_ci_update(1, ptr(r), ptr(t), ptr(E), ptr(eps_o), ptr(eps_v), O, V, 1, 1, 1, None, stream_ptr())), 4 * n * 16)
+timeit("ci_update (r -= E t; t += r/D)", lambda: check(lib.apyib_ci_update(1, ptr(r), ptr(t), ptr(E), ptr(eps_o), ptr(eps_v), O, V, 1, 1, 1, None, None, None, None, stream_ptr())), 4 * n * 16)
 hist_e, hist_t = rnd(8, n), rnd(8, n)
 B = zeros((128,), torch.float64); c = zeros((16,), torch.float64)
 it = torch.full((1,), 8, dtype=torch.int32, device="cuda")
