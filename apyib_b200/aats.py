@@ -307,7 +307,8 @@ class AAT(object):
         no, nf, nv = self.ndocc, self.nfzc, self.nbf - self.ndocc
         o = no - nf
         cisd = X1 is not None
-        lemma = config.AAT_ALGORITHM == "lemma"
+        lemma = config.AAT_ALGORITHM in ("lemma", "factorized")
+        factorized = config.AAT_ALGORITHM == "factorized"
         T = _Tables.get(no, nf, nv)
         R0, R1, R2 = T.L
         nS, ns = len(S_hosts), self.nbf
@@ -373,11 +374,15 @@ class AAT(object):
             n2 = o * o * nv * nv
             check(lib.apyib_pack_doubles(ptr(X2), n2, nx, o, nv, nf, ptr(T.doubles_dev), P, ptr(Xh), stream_ptr()))
             check(lib.apyib_pack_doubles(ptr(Y2), n2, ny, o, nv, nf, ptr(T.doubles_dev), P, ptr(Yh), stream_ptr()))
-            z22 = matvec(2, 2, Yh, False)                                # the P x P table, fused      [s,q,r]
+            if not factorized:
+                z22 = matvec(2, 2, Yh, False)                            # the P x P table, fused      [s,q,r]
             ys = [wy.reshape(nS, ny, -1)] + ([Y1.reshape(1, ny, -1).expand(nS, ny, n1)] if cisd else [])
             z21 = matvec(2, 1, torch.cat(ys, 1).contiguous(), True)      # [s, ny(+ny), P]
             z12 = matvec(1, 2, Yh, False)                                # [s, q, ov]
-            dd["c1"] = cn("xr,sqr->sxq", Xh, z22)
+            if factorized:
+                dd["c1f"] = self._dd_factorized(prep, nS, ns, no, nf, X2, Y2)
+            else:
+                dd["c1"] = cn("xr,sqr->sxq", Xh, z22)
             dd["v1"] = cn("xr,sr->sx", Xh, D20)
             dd["v2"] = cn("sr,qr->sq", D02, Yh)
             dd["c3"] = cn("xr,sqr->sxq", Xh, z21[:, :ny])
@@ -413,7 +418,10 @@ class AAT(object):
             g = lambda k: h[k][s] if k in h else zero
             v1 = g("v1").reshape(nx, 1) if "v1" in h else np.zeros((nx, 1), dtype=np.complex128)
             v2 = g("v2").reshape(1, ny) if "v2" in h else np.zeros((1, ny), dtype=np.complex128)
-            out = {"DD": 0.125 * (dSh * g("c1") + v1 * v2 + 4 * g("c3") + 2 * g("c4") + 8 * g("c6"))}
+            c1 = g("c1")
+            if "c1f" in h:                    # factorised: 16 x (restricted double sum) / det(S_oo)
+                c1 = dSh * h["c1f"][s] / 16.0
+            out = {"DD": 0.125 * (dSh * c1 + v1 * v2 + 4 * g("c3") + 2 * g("c4") + 8 * g("c6"))}
             if cisd:
                 xA, yB = g("s_xA").reshape(nx, 1), g("s_yB").reshape(1, ny)
                 out["SS"] = 2 * (dSh * g("s_xGy") + xA * yB)
@@ -425,6 +433,53 @@ class AAT(object):
                 out["0D"] = 0.5 * v2 * dSh + g("0db").reshape(1, ny) + zero
             res.append(out)
         return res
+
+    def _dd_factorized(self, prep, nS, ns, no, nf, X2, Y2):
+        """sum_{i,j,a,b,k,l,c,d} Xf[ijab] Yf[klcd] det T / det-free form of the doubles-doubles table
+        contraction (SURVEY.md 8(f).1 "factorise the DD sums").  With the 4 x 4 lemma matrix
+            T = [[P_ai P_aj R_ac R_ad], [P_bi P_bj R_bc R_bd], [A_ki A_kj -Q_kc -Q_kd], [A_li A_lj -Q_lc -Q_ld]]
+        (A = S_oo^-1) expanded by 2 x 2 minors, and Xf / Yf the fully antisymmetrised amplitudes
+        (antisymmetric under i<->j, a<->b resp. k<->l, c<->d), the 24 terms of det T collapse to
+            sum Xf Yf det T = 4 [ (Xf.PP)(Yf.QQ) + 4 sum_kc (A U R)_kc W_kc + sum_klcd Z_klcd Yf_klcd ]
+            U_jb = sum_ia Xf_ijab P_ai,  W_kc = sum_ld Yf_klcd Q_ld,  Z_klcd = sum A_ki A_lj R_ac R_bd Xf_ijab
+        i.e. O(o^2 v^2 (o+v)) DMMA contractions instead of (C(o,2) C(v,2))^2 determinants.
+        Returns [nS, nx, ny]: the unrestricted sum (= 16 x the restricted i<j,a<b,k<l,c<d sum) over det T."""
+        from .utils import gather4
+        nv = ns - no
+        o = no - nf
+        cn = contract_new
+        body = prep[:, 1:]
+        off = 0
+        Ai = body[:, off:off + no * no].reshape(nS, no, no); off += no * no
+        P = body[:, off:off + nv * no].reshape(nS, nv, no); off += nv * no
+        Q = body[:, off:off + no * nv].reshape(nS, no, nv); off += no * nv
+        R = body[:, off:off + nv * nv].reshape(nS, nv, nv)
+        Ai, P, Q = Ai[:, nf:, nf:], P[:, :, nf:], Q[:, nf:, :]            # frozen-core rows/cols are never substituted
+
+        def antisym(X):      # Xf[x,i,j,a,b] = 2 (x_ijab - x_ijba - x_jiab + x_jiba)
+            out = torch.empty_like(X)
+            for q in range(X.shape[0]):
+                t = gather4(X[q], 0, X[q].shape, [0, 1, 2, 3], [0, 0, 0, 0], 1.0, [0, 1, 3, 2], [0, 0, 0, 0], -1.0)
+                gather4(t, 0, t.shape, [0, 1, 2, 3], [0, 0, 0, 0], 2.0, [1, 0, 2, 3], [0, 0, 0, 0], -2.0, out=out[q])
+            return out
+
+        Xf, Yf = antisym(X2), antisym(Y2)
+        U = cn("xijab,sai->sxjb", Xf, P)
+        alpha = cn("sxjb,sbj->sx", U, P)
+        W = cn("qklcd,sld->sqkc", Yf, Q)
+        beta = cn("sqkc,skc->sq", W, Q)
+        M = cn("sxkb,sbc->sxkc", cn("skj,sxjb->sxkb", Ai, U), R)
+        mixed = cn("sxkc,sqkc->sxq", M, W)
+        Z = cn("ski,xijab->sxkjab", Ai, Xf)
+        Z = cn("slj,sxkjab->sxklab", Ai, Z)
+        Z = cn("sac,sxklab->sxklcb", R, Z)
+        Z = cn("sbd,sxklcb->sxklcd", R, Z)
+        gamma = cn("sxklcd,qklcd->sxq", Z, Yf)
+        ab = cn("sx,sq->sxq", alpha, beta)
+        _axpby(4.0, mixed, 1.0, ab)
+        _axpby(1.0, gamma, 1.0, ab)
+        _axpby(4.0, ab, 0.0, mixed)          # mixed <- 4 (alpha beta + 4 mixed + gamma)
+        return mixed
 
     def _spatial_terms(self, alpha, beta, normalization):
         m = self.parameters["method"]

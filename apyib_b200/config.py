@@ -34,4 +34,6 @@ def timed(name):
 #   "lu"    : sub-warp LU with partial pivoting of every n x n matrix (csrc/dets.cu; the north star's
 #             "batched small-LU/determinant kernel")
 #   "lemma" : <= 4 x 4 determinants from S_oo^-1 (csrc/lemma.cu), same results
+#   "factorized" : lemma for the small families, and the doubles x doubles table contracted in closed
+#             form, O(o^2 v^2 (o+v)) DMMA contractions instead of (C(o,2) C(v,2))^2 determinants
 AAT_ALGORITHM = "lu"

@@ -222,7 +222,9 @@ class SyntheticProvider:
     SURVEY 8(d) generator, angular-momentum-like antisymmetric matrices for the magnetic field
     and symmetric dipole-like matrices for the electric field."""
 
-    def __init__(self, nbf, ndocc, natom, seed=0, nfzc=0, scale=0.01):
+    def __init__(self, nbf, ndocc, natom, seed=0, nfzc=0, scale=None):
+        if scale is None:                 # keep the two-electron part a perturbation of the 4 Eh gap
+            scale = 0.01 if nbf <= 30 else 0.25 / nbf
         rng = np.random.default_rng(seed)
         self.nbf, self.ndocc, self.natom_, self.nfzc = nbf, ndocc, natom, nfzc
         g = scale * rng.standard_normal((nbf,) * 4)
@@ -394,7 +396,16 @@ class hf_wfn(object):
         H_core = H.T + H.V
         X = np.linalg.inv(la.sqrtm(H.S))
         nd = self.ndocc
-        GK = 2 * H.ERI - H.ERI.swapaxes(1, 2)
+        n = self.nbf
+        GK = getattr(H.provider, "_gk_cache", None) if hasattr(H, "provider") else None
+        if GK is None or GK[0] is not H.ERI:
+            GK = (H.ERI, np.ascontiguousarray((2 * H.ERI - H.ERI.swapaxes(1, 2)).reshape(n * n, n * n)))
+            if hasattr(H, "provider"):
+                try:
+                    H.provider._gk_cache = GK           # synthetic / fixed-geometry providers reuse it
+                except Exception:
+                    pass
+        GK = GK[1]
         e, C_p = np.linalg.eigh(X @ H_core @ X)
         C = X @ C_p
         D = 2 * C[:, :nd] @ C[:, :nd].conj().T
@@ -402,7 +413,12 @@ class hf_wfn(object):
         i = 1
         while i <= parameters["max_iterations"]:
             E_old, D_old = E_SCF, D
-            F = H_core + 0.5 * np.einsum("ls,mnls->mn", D, GK)
+            d = D.reshape(-1)
+            if np.iscomplexobj(d) and not np.iscomplexobj(GK):      # avoid upcasting the nbf^4 tensor
+                jk = (GK @ d.real) + 1j * (GK @ d.imag)
+            else:
+                jk = GK @ d
+            F = H_core + 0.5 * jk.reshape(n, n)
             if parameters["DIIS"]:
                 SDF = H.S @ D @ F
                 res_vec = (X @ (SDF - SDF.conj().T) @ X).reshape(-1)

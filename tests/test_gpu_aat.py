@@ -22,7 +22,7 @@ PARTS = ("overlap_uu", "overlap_up", "overlap_un", "overlap_pu", "overlap_nu", "
          "overlap_np", "overlap_nn", "unperturbed_T", "nuc_pos_T", "nuc_neg_T", "mag_pos_T", "mag_neg_T")
 
 
-@pytest.fixture(params=["lu", "lemma"])
+@pytest.fixture(params=["lu", "lemma", "factorized"])
 def algo(request):
     import apyib_b200
     old = apyib_b200.config.AAT_ALGORITHM
