@@ -29,7 +29,7 @@ SIGNATURES = {
     "apyib_graph_launch": (_int, [_vp, _vp]),
     "apyib_graph_destroy": (_int, [_vp]),
     "apyib_contract": (_int, [_int, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                              _int, _int, _int, _int, _dbl, _dbl, _dbl, _dbl, _int, _i64, _i64, _i64, _vp, _vp]),
+                              _int, _int, _int, _int, _dbl, _dbl, _dbl, _dbl, _int, _i64, _i64, _i64, _vp, _int, _vp, _vp]),
     "apyib_gather4": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _dbl, _i32p, _i64p, _dbl, _vp]),
     "apyib_gather2": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _vp]),
     "apyib_mp2_t2_energy": (_int, [_int, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp]),

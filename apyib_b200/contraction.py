@@ -73,7 +73,13 @@ def _plan(spec, A, B, out):
     for s in sizes:
         ptrs.append(dev.data_ptr() + 8 * off)
         off += s
-    p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch)
+    # split-K for dot-product-like shapes: few output tiles, long K (one CTA would walk K alone)
+    tiles = ((M + 31) // 32) * ((N + 31) // 32) * batch[0]
+    ksplit = 1
+    if tiles < 148 and K >= 4096:
+        ksplit = int(min(max(1, (2 * 148) // tiles), (K + 1023) // 1024, 65535 // batch[0]))
+    work = torch.empty(batch[0] * ksplit * M * N, dtype=A.dtype, device=A.device) if ksplit > 1 else None
+    p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch, ksplit, work)
     _table_cache[key] = p
     return p
 
@@ -81,22 +87,22 @@ def _plan(spec, A, B, out):
 def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
     """out = alpha * einsum(spec, op(A), op(B)) + beta * out, on the current stream."""
     assert A.dtype == B.dtype == out.dtype, "mixed dtypes: %s %s %s" % (A.dtype, B.dtype, out.dtype)
-    M, N, K, ptrs, a_kfast, b_kfast, _keep, batch = _plan(spec, A, B, out)
+    M, N, K, ptrs, a_kfast, b_kfast, _keep, batch, ksplit, work = _plan(spec, A, B, out)
     alpha, beta = complex(alpha), complex(beta)
     if config.TIMING is not None:
         with config.timed("contract[%s %dx%dx%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K)):
-            check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch))
+            check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch, ksplit, work))
         return out
-    check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch))
+    check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch, ksplit, work))
     return out
 
 
-def _launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch):
+def _launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch, ksplit, work):
     return (lib.apyib_contract(dtype_code(A), ptr(A), ptr(B), ptr(out), M, N, K,
                              *[C.c_void_p(p) for p in ptrs],
                              a_kfast, b_kfast, int(conj_a), int(conj_b),
                              alpha.real, alpha.imag, beta.real, beta.imag,
-                             batch[0], batch[1], batch[2], batch[3], C.c_void_p(0), stream_ptr()))
+                             batch[0], batch[1], batch[2], batch[3], C.c_void_p(0), ksplit, ptr(work), stream_ptr()))
 
 
 def contract_new(spec, A, B, alpha=1.0, conj_a=False, conj_b=False):

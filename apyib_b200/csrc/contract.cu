@@ -45,6 +45,8 @@ struct ContractArgs {
     const int32_t *active;
     double alpha_re, alpha_im, beta_re, beta_im;
     int a_kfast, b_kfast, conj_a, conj_b;
+    int ksplit;          // > 1: K is split over `ksplit` CTAs; raw partial tiles go to `work`
+    void *work;          // [batch][ksplit][M][N] elements
 };
 
 template <bool CPLX> struct elem_t { using type = double; };
@@ -82,7 +84,7 @@ contract_kernel(const ContractArgs p) {
     T *As = reinterpret_cast<T *>(smem_raw);                       // [STAGES][LA::size]
     T *Bs = As + (size_t)STAGES * LA::size;                        // [STAGES][LB::size]
 
-    const int z = blockIdx.z;
+    const int z = blockIdx.z / p.ksplit, ks = blockIdx.z % p.ksplit;
     if (p.active != nullptr && p.active[z] == 0) return;
     const T *A = reinterpret_cast<const T *>(p.A) + (size_t)z * p.a_bs;
     const T *B = reinterpret_cast<const T *>(p.B) + (size_t)z * p.b_bs;
@@ -143,17 +145,23 @@ contract_kernel(const ContractArgs p) {
             if (CPLX) ci[i][j][0] = ci[i][j][1] = 0.0;
         }
 
-    const int64_t nslab = (p.K + BK - 1) / BK;
+    // slab range of this CTA (split-K: contiguous chunk of the K slabs)
+    const int64_t nslab_all = (p.K + BK - 1) / BK;
+    const int64_t per = (nslab_all + p.ksplit - 1) / p.ksplit;
+    const int64_t slab0 = (int64_t)ks * per;
+    int64_t nslab = nslab_all - slab0;
+    if (nslab > per) nslab = per;
+    if (nslab < 0) nslab = 0;
     int64_t ak_next, bk_next;                  // k offsets of the next slab to be issued (prefetched)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
         if (s < nslab) {
-            k_offsets((int64_t)s * BK, ak_next, bk_next);
+            k_offsets((slab0 + s) * BK, ak_next, bk_next);
             load_slab(s, ak_next, bk_next);
         }
         cp_async_commit();
     }
-    k_offsets((int64_t)(STAGES - 1) * BK, ak_next, bk_next);
+    k_offsets((slab0 + STAGES - 1) * BK, ak_next, bk_next);
 
     const int fr = lane >> 2, fk = lane & 3;   // fragment row (or col) / k within the 8x4 atom
     const double sa = p.conj_a ? -1.0 : 1.0, sb = p.conj_b ? -1.0 : 1.0;
@@ -165,7 +173,7 @@ contract_kernel(const ContractArgs p) {
             const int64_t nk = kt + STAGES - 1;
             if (nk < nslab) load_slab((int)(nk % STAGES), ak_next, bk_next);
             cp_async_commit();
-            k_offsets((nk + 1) * BK, ak_next, bk_next);
+            k_offsets((slab0 + nk + 1) * BK, ak_next, bk_next);
         }
         const T *as = As + (size_t)(kt % STAGES) * LA::size;
         const T *bs = Bs + (size_t)(kt % STAGES) * LB::size;
@@ -209,6 +217,24 @@ contract_kernel(const ContractArgs p) {
     }
     cp_async_wait<0>();
 
+    if (p.ksplit > 1) {   // split-K: raw partial tile -> work[z][ks][m][n]; alpha/beta applied by the reduce kernel
+        T *W = reinterpret_cast<T *>(p.work) + ((size_t)z * p.ksplit + ks) * (size_t)p.M * p.N;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int64_t m = m0 + wm0 + i * 8 + fr;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int64_t n = n0 + wn0 + j * 8 + fk * 2 + q;
+                    if (n >= p.N) continue;
+                    if constexpr (CPLX) W[m * p.N + n] = make_cplx(cr[i][j][q], ci[i][j][q]);
+                    else W[m * p.N + n] = cr[i][j][q];
+                }
+        }
+        return;
+    }
     // epilogue: thread owns rows fr (+8i), column pairs 2*fk (+8j) of its warp tile
     const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
 #pragma unroll
@@ -242,6 +268,33 @@ contract_kernel(const ContractArgs p) {
     }
 }
 
+// C[c_m[m] + c_n[n]] = alpha * sum_ks work[z][ks][m][n] + beta * C   (fixed summation order)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const ContractArgs p, int batch) {
+    using T = typename elem_t<CPLX>::type;
+    const int64_t MN = p.M * p.N, total = MN * batch;
+    const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t z = e / MN, mn = e % MN, m = mn / p.N, n = mn % p.N;
+        if (p.active != nullptr && p.active[z] == 0) continue;
+        const T *W = reinterpret_cast<const T *>(p.work) + (size_t)z * p.ksplit * MN + mn;
+        T *dst = reinterpret_cast<T *>(p.C) + (size_t)z * p.c_bs + p.c_m[m] + p.c_n[n];
+        if constexpr (CPLX) {
+            double xr = 0.0, xi = 0.0;
+            for (int ks = 0; ks < p.ksplit; ++ks) { const cplx w = W[(size_t)ks * MN]; xr += w.x; xi += w.y; }
+            double vr = p.alpha_re * xr - p.alpha_im * xi, vi = p.alpha_re * xi + p.alpha_im * xr;
+            if (has_beta) { const cplx o = *dst; vr += p.beta_re * o.x - p.beta_im * o.y; vi += p.beta_re * o.y + p.beta_im * o.x; }
+            *dst = make_cplx(vr, vi);
+        } else {
+            double x = 0.0;
+            for (int ks = 0; ks < p.ksplit; ++ks) x += W[(size_t)ks * MN];
+            double v = p.alpha_re * x;
+            if (has_beta) v += p.beta_re * (*dst);
+            *dst = v;
+        }
+    }
+}
+
 template <bool CPLX, int BM, int BN, int BK, int WM, int WN, int STAGES, bool AKF, bool BKF>
 static int launch_contract2(const ContractArgs &a, int batch, cudaStream_t st) {
     using T = typename elem_t<CPLX>::type;
@@ -253,9 +306,15 @@ static int launch_contract2(const ContractArgs &a, int batch, cudaStream_t st) {
         APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    dim3 grid((unsigned)((a.N + BN - 1) / BN), (unsigned)((a.M + BM - 1) / BM), (unsigned)batch);
+    dim3 grid((unsigned)((a.N + BN - 1) / BN), (unsigned)((a.M + BM - 1) / BM), (unsigned)(batch * a.ksplit));
     kern<<<grid, NT, smem, st>>>(a);
     APYIB_LAUNCH_CHECK();
+    if (a.ksplit > 1) {
+        int64_t b = (a.M * a.N * batch + 255) / 256;
+        if (b > 148 * 8) b = 148 * 8;
+        splitk_reduce_kernel<CPLX><<<(unsigned)b, 256, 0, st>>>(a, batch);
+        APYIB_LAUNCH_CHECK();
+    }
     return APYIB_OK;
 }
 
@@ -278,7 +337,9 @@ extern "C" int apyib_contract(int dtype, const void *d_A, const void *d_B, void 
                               const int64_t *d_b_n, const int64_t *d_c_m, const int64_t *d_c_n, int a_kfast,
                               int b_kfast, int conj_a, int conj_b, double alpha_re, double alpha_im,
                               double beta_re, double beta_im, int batch, int64_t a_bstride,
-                              int64_t b_bstride, int64_t c_bstride, const int32_t *d_active, void *stream) {
+                              int64_t b_bstride, int64_t c_bstride, const int32_t *d_active, int ksplit,
+                              void *d_work, void *stream) {
+    APYIB_REQUIRE(ksplit >= 1 && (ksplit == 1 || d_work != nullptr) && (int64_t)batch * ksplit <= 65535, "split-K");
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 1 && batch <= 65535, "sizes");
     APYIB_REQUIRE(d_A && d_B && d_C && d_a_m && d_a_k && d_b_k && d_b_n && d_c_m && d_c_n, "null pointer");
@@ -292,10 +353,11 @@ extern "C" int apyib_contract(int dtype, const void *d_A, const void *d_B, void 
     a.active = d_active;
     a.alpha_re = alpha_re; a.alpha_im = alpha_im; a.beta_re = beta_re; a.beta_im = beta_im;
     a.a_kfast = a_kfast; a.b_kfast = b_kfast; a.conj_a = conj_a; a.conj_b = conj_b;
+    a.ksplit = ksplit; a.work = d_work;
     cudaStream_t st = (cudaStream_t)stream;
     // tile choice: 64x64 when that already yields >= 1 wave of CTAs on 148 SMs, else 32x32
     const int64_t big_tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
-    const bool big = big_tiles >= 148;
+    const bool big = big_tiles >= 148 && ksplit == 1;
     if (dtype == APYIB_C128) {
         return big ? launch_contract<true, 64, 64, 8, 32, 32, 3>(a, batch, st)
                    : launch_contract<true, 32, 32, 16, 16, 16, 4>(a, batch, st);

@@ -62,6 +62,9 @@ int apyib_graph_destroy(void *graph_exec);
  * points solved together); d_active (nullable, int32[batch]) skips entries
  * whose flag is 0.  alpha/beta are given as (re, im); im ignored for F64.
  * conj_a / conj_b conjugate the operand (np.conjugate(C) in utils.py:252,275,277).
+ * ksplit > 1 splits the K range over ksplit CTAs per output tile (dot-product-like contractions
+ * with tiny M x N, e.g. the scalar energy/AAT sums); partial tiles go to d_work (batch * ksplit *
+ * M * N elements) and are summed in fixed order by a second kernel -- deterministic.
  */
 int apyib_contract(int dtype, const void *d_A, const void *d_B, void *d_C,
                    int64_t M, int64_t N, int64_t K,
@@ -71,7 +74,7 @@ int apyib_contract(int dtype, const void *d_A, const void *d_B, void *d_C,
                    int a_kfast, int b_kfast, int conj_a, int conj_b,
                    double alpha_re, double alpha_im, double beta_re, double beta_im,
                    int batch, int64_t a_bstride, int64_t b_bstride, int64_t c_bstride,
-                   const int32_t *d_active, void *stream);
+                   const int32_t *d_active, int ksplit, void *d_work, void *stream);
 
 /* ---- 4-index block gather with optional on-the-fly spin blocking ----------------
  * out[x0,x1,x2,x3] = c1 * G(start1 + x[perm1]) + c2 * G(start2 + x[perm2])   (dense out)

@@ -174,3 +174,25 @@ def test_dots_and_axpby(cplx):
     check(lib.apyib_axpby(dtype_code(dX), n, 0.5, 0.25 if cplx else 0.0, ptr(dX[1]), 1, 2.0, 0.0, ptr(dy), stream_ptr()))
     a = (0.5 + 0.25j) if cplx else 0.5
     assert np.abs(to_host(dy) - (a * X[1].conj() + 2.0 * y)).max() < 1e-13
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_contract_split_k_dot_like_shapes(cplx):
+    """tiny M x N with long K takes the split-K path (partials + fixed-order reduce)"""
+    from apyib_b200.contraction import contract, _plan
+    from apyib_b200.device import to_device, to_host
+    rng = np.random.default_rng(9)
+    X = _rand(rng, (3, 6, 6, 20, 20), cplx)
+    Z = _rand(rng, (2, 6, 20, 6, 20), cplx)
+    out0 = _rand(rng, (3, 2), cplx)
+    dX, dZ, dO = to_device(X), to_device(Z), to_device(out0)
+    assert _plan("xijab,qiajb->xq", dX, dZ, dO)[8] > 1, "expected split-K"
+    contract("xijab,qiajb->xq", dX, dZ, dO, 0.5, 2.0)
+    want = 0.5 * np.einsum("xijab,qiajb->xq", X, Z) + 2.0 * out0
+    assert np.abs(to_host(dO) - want).max() < 1e-11 * max(1.0, np.abs(want).max())
+    v = _rand(rng, (70001,), cplx)
+    w = _rand(rng, (70001,), cplx)
+    dv = to_device(v)
+    s = torch.zeros((), dtype=dv.dtype, device=dv.device)
+    contract("r,r->", dv, to_device(w), s, 1.0, 0.0, conj_a=True)
+    assert abs(to_host(s) - np.vdot(v, w)) < 1e-10

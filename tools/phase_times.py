@@ -5,13 +5,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, apyib_b200
 from apyib_b200 import _lib
 apyib_b200.config.VERBOSE = False
+apyib_b200.config.AAT_ALGORITHM = os.environ.get("ALGO", "lu")
 wl = bench.WORKLOADS[os.environ.get("WL", "h2o2")]
 work = bench.prepare(wl)
 apyib_b200.config.RETURN_DEVICE = True
 bench.gpu_step(work)            # warm-up
 torch.cuda.synchronize()
 par = work["par"]
-for graph in (True, False):
+from apyib_b200.ci_wfn import solve_many
+t0 = time.perf_counter()
+sols = solve_many("CISD", par, [work["w0"]] + list(work["pts"].values()))
+torch.cuda.synchronize()
+print("solve_many (all %d points): %.3f s" % (len(sols), time.perf_counter() - t0))
+del sols
+for graph in ((True, False) if os.environ.get("WL", "h2o2") != "methyloxirane" else ()):
     apyib_b200.config.USE_CUDA_GRAPH = graph
     t0 = time.perf_counter(); n0 = _lib.LAUNCHES[0]
     its = []
