@@ -262,6 +262,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="h2o2", choices=sorted(WORKLOADS))
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run the warm-up and ONE device-resident step only (target for ncu launch lists)")
     ap.add_argument("--aat-algorithm", default="lu", choices=["lu", "lemma", "factorized"],
                     help="substituted determinants by sub-warp LU (north star) or by the determinant lemma")
     args = ap.parse_args()
@@ -329,6 +331,12 @@ def main():
             tot += max(e0.elapsed_time(e1) * 1e-3, wall)       # host-orchestrated step: never below wall clock
         return tot, res
 
+    if args.profile_step:
+        timed_steps(max(1, args.warmup), True)
+        t, _ = timed_steps(1, True)
+        if rank == 0:
+            print(json.dumps({"profile_step_s": t, "launches": _lib.LAUNCHES[0]}))
+        return
     sampler = ClockSampler(local_rank)
     # warm-up (also fills the device-resident AO-integral caches and the offset-table cache)
     timed_steps(args.warmup, True)
