@@ -37,3 +37,7 @@ def timed(name):
 #   "factorized" : lemma for the small families, and the doubles x doubles table contracted in closed
 #             form, O(o^2 v^2 (o+v)) DMMA contractions instead of (C(o,2) C(v,2))^2 determinants
 AAT_ALGORITHM = "lu"
+
+# Route k-contiguous 2-D operand contractions (ladder term, first AO->MO quarter transform) through the
+# TMA-fed kernel (csrc/contract_tma.cu); the gather kernel handles everything else.
+USE_TMA = True

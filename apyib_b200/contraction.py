@@ -73,13 +73,24 @@ def _plan(spec, A, B, out):
     for s in sizes:
         ptrs.append(dev.data_ptr() + 8 * off)
         off += s
+    # plain k-contiguous strided matrices on both sides -> eligible for the TMA-fed kernel
+    def linear(tab):
+        if len(tab) < 2:
+            return int(tab[0]) == 0 and 1
+        ld = int(tab[1] - tab[0])
+        return ld if ld > 0 and np.array_equal(tab, np.arange(len(tab), dtype=np.int64) * ld) else 0
+    tma = None
+    if K >= 16 and linear(tabs[1]) == 1 and linear(tabs[2]) == 1 and tabs[0][0] == 0 and tabs[3][0] == 0:
+        lda, ldb = (linear(tabs[0]) if M > 1 else K), (linear(tabs[3]) if N > 1 else K)
+        if lda and ldb and lda >= K and ldb >= K and ((M + 63) // 64) * ((N + 63) // 64) * batch[0] >= 148:
+            tma = (lda, ldb)
     # split-K for dot-product-like shapes: few output tiles, long K (one CTA would walk K alone)
     tiles = ((M + 31) // 32) * ((N + 31) // 32) * batch[0]
     ksplit = 1
     if tiles < 148 and K >= 4096:
         ksplit = int(min(max(1, (2 * 148) // tiles), (K + 1023) // 1024, 65535 // batch[0]))
     work = torch.empty(batch[0] * ksplit * M * N, dtype=A.dtype, device=A.device) if ksplit > 1 else None
-    p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch, ksplit, work)
+    p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch, ksplit, work, tma)
     _table_cache[key] = p
     return p
 
@@ -87,8 +98,18 @@ def _plan(spec, A, B, out):
 def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
     """out = alpha * einsum(spec, op(A), op(B)) + beta * out, on the current stream."""
     assert A.dtype == B.dtype == out.dtype, "mixed dtypes: %s %s %s" % (A.dtype, B.dtype, out.dtype)
-    M, N, K, ptrs, a_kfast, b_kfast, _keep, batch, ksplit, work = _plan(spec, A, B, out)
+    M, N, K, ptrs, a_kfast, b_kfast, _keep, batch, ksplit, work, tma = _plan(spec, A, B, out)
     alpha, beta = complex(alpha), complex(beta)
+    if tma is not None and ksplit == 1 and config.USE_TMA:
+        with config.timed("contract_tma[%s %dx%dx%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K)):
+            rc = lib.apyib_contract_tma(dtype_code(A), ptr(A), ptr(B), ptr(out), M, N, K, tma[0], tma[1],
+                                        C.c_void_p(ptrs[4]), C.c_void_p(ptrs[5]), int(conj_a), int(conj_b),
+                                        alpha.real, alpha.imag, beta.real, beta.imag,
+                                        batch[0], batch[1], batch[2], batch[3], C.c_void_p(0), stream_ptr())
+        if rc == 0:
+            return out
+        if rc != -3:          # APYIB_ERR_UNSUPPORTED -> fall through to the gather kernel
+            check(rc)
     if config.TIMING is not None:
         with config.timed("contract[%s %dx%dx%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K)):
             check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch, ksplit, work))

@@ -76,6 +76,18 @@ int apyib_contract(int dtype, const void *d_A, const void *d_B, void *d_C,
                    int batch, int64_t a_bstride, int64_t b_bstride, int64_t c_bstride,
                    const int32_t *d_active, int ksplit, void *d_work, void *stream);
 
+/* TMA-fed variant (cp.async.bulk.tensor + mbarrier ring, 128B-swizzled tiles) for operands that
+ * are k-contiguous strided matrices: opA(A[z*a_bstride + m*lda + k]), opB(B[z*b_bstride + n*ldb + k]);
+ * C through offset tables as in apyib_contract.  Used for the ladder term <ab|cd> t_ijcd and the
+ * first AO->MO quarter transform.  Returns APYIB_ERR_UNSUPPORTED (nothing launched) when the
+ * operands do not meet the TMA alignment rules; the caller then uses apyib_contract.        */
+int apyib_contract_tma(int dtype, const void *d_A, const void *d_B, void *d_C,
+                       int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                       const int64_t *d_c_m, const int64_t *d_c_n, int conj_a, int conj_b,
+                       double alpha_re, double alpha_im, double beta_re, double beta_im,
+                       int batch, int64_t a_bstride, int64_t b_bstride, int64_t c_bstride,
+                       const int32_t *d_active, void *stream);
+
 /* ---- 4-index block gather with optional on-the-fly spin blocking ----------------
  * out[x0,x1,x2,x3] = c1 * G(start1 + x[perm1]) + c2 * G(start2 + x[perm2])   (dense out)
  * where G is the dense chemists' tensor src[n0,n1,n2,n3] (spin==0), or its
