@@ -49,6 +49,7 @@ SIGNATURES = {
     "apyib_det_matvec": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _int, _vp, _vp, _vp]),
     "apyib_pack_doubles": (_int, [_vp, _i64, _int, _int, _int, _int, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec_work_len": (_i64, [_i64, _i64, _int, _int]),
+    "apyib_det_set_kernel": (_int, [_int]),
     "apyib_lemma_prep_len": (_i64, [_int, _int]),
     "apyib_lemma_prepare": (_int, [_vp, _int, _int, _int, _vp, _vp]),
     "apyib_lemma_outer": (_int, [_vp, _int, _int, _int, _int, _vp, _i64, _int, _vp, _i64, _vp, _vp]),

@@ -185,15 +185,48 @@ static int launch_det(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, 
     return APYIB_OK;
 }
 
+// thread-per-matrix LU (dets_tpm.cu), n <= 12
+int launch_det_tpm(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
+                   const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny, cplx *out, int outer);
+int tpm_blocks_per_sm(int n, int ns);
+constexpr int kTpmThreadsHost = 128;
+constexpr int kTpmMaxN = 12;
+static int g_det_kernel = 0;   // 0 = thread-per-matrix for 2 <= n <= 12, sub-warp above; 1 = sub-warp always
+static bool use_tpm(int n) { return g_det_kernel == 0 && n >= 2 && n <= kTpmMaxN; }
+
+// column chunks for a (row blocks) x (chunks) grid of about `target` CTAs, never more than one wave over
+static int64_t chunks_for(int64_t rb, int64_t ncol, int64_t target, int64_t cap) {
+    int64_t nchunk = target / rb;
+    if (nchunk > ncol) nchunk = ncol;
+    if (nchunk > cap) nchunk = cap;
+    if (nchunk < 1) nchunk = 1;
+    const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
+    return (ncol + chunk_len - 1) / chunk_len;
+}
+
 }  // namespace apyib
 
 using namespace apyib;
+
+extern "C" int apyib_det_set_kernel(int which) {
+    APYIB_REQUIRE(which == 0 || which == 1, "0 = auto (thread-per-matrix for n <= 12), 1 = sub-warp LU");
+    g_det_kernel = which;
+    return APYIB_OK;
+}
 
 extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
                                const int32_t *d_cols, int64_t ncol, void *d_out, void *stream) {
     APYIB_REQUIRE(d_S && d_rows && d_cols && d_out, "null pointer");
     APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
     if (nrow == 0 || ncol == 0) return APYIB_OK;
+    if (use_tpm(n)) {
+        const int64_t rb = (nrow + kTpmThreadsHost - 1) / kTpmThreadsHost;
+        APYIB_REQUIRE(rb <= 2147483647LL, "too many rows");
+        const int64_t nchunk = chunks_for(rb, ncol, 148 * 3, 65535);
+        const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
+        return launch_det_tpm(n, dim3((unsigned)rb, (unsigned)nchunk), (cudaStream_t)stream, (const cplx *)d_S, ns,
+                              d_rows, nrow, d_cols, ncol, chunk_len, nullptr, 0, (cplx *)d_out, 1);
+    }
     const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     int64_t nchunk = (148 * 8 + rb - 1) / rb;
@@ -211,6 +244,7 @@ extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_
 // Z[iy*nrow + r] = sum_c det(S[rows[r], cols[c]]) * Y[iy*ncol + c]
 // d_work: scratch of apyib_det_matvec_work_len(nrow, ncol, ny, n) complex128 elements.
 extern "C" int64_t apyib_det_matvec_nchunk(int64_t nrow, int64_t ncol, int n) {
+    if (use_tpm(n)) return chunks_for((nrow + kTpmThreadsHost - 1) / kTpmThreadsHost, ncol, 148 * 3, 4096);
     const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     int64_t nchunk = (148 * 8 + rb - 1) / rb;
@@ -237,12 +271,14 @@ extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d
         APYIB_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(cplx) * ny * nrow, st));
         return APYIB_OK;
     }
-    const int64_t gpb = groups_per_block(n);
+    const int64_t gpb = use_tpm(n) ? kTpmThreadsHost : groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     const int64_t nchunk = apyib_det_matvec_nchunk(nrow, ncol, n);
     const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
     dim3 grid((unsigned)rb, (unsigned)nchunk);
-    int rc = launch_det<false>(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
+    int rc = use_tpm(n) ? launch_det_tpm(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
+                                         (const cplx *)d_Y, ny, (cplx *)d_work, 0)
+                        : launch_det<false>(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
                                (const cplx *)d_Y, ny, (cplx *)d_work);
     if (rc != APYIB_OK) return rc;
     const int64_t len = (int64_t)ny * nrow;

@@ -188,7 +188,8 @@ int apyib_copy(int dtype, void *d_dst, const void *d_src, int64_t len, void *str
 
 /* ---- determinants of substituted occupied-overlap matrices ----------------------
  * out[r*ncol + c] = det( S[rows[r, :], cols[c, :]] ),  n x n, LU with partial
- * pivoting, one sub-warp per matrix (np.linalg.det in aats.py:128, 578-618, 672-675).
+ * pivoting, one thread (n <= 12) or one sub-warp per matrix (np.linalg.det in aats.py:128,
+ * 578-618, 672-675).
  * d_S: (ns x ns) complex128 row-major overlap (device); rows/cols: int32 index
  * lists (nrow x n), (ncol x n) as produced by apyib_det_index_lists / apyib_so_index_lists. */
 int apyib_det_outer(const void *d_S, int ns, int n,
@@ -206,6 +207,10 @@ int apyib_det_matvec(const void *d_S, int ns, int n,
                      const int32_t *d_cols, int64_t ncol,
                      const void *d_Y, int ny, void *d_Z, void *d_work, void *stream);
 int64_t apyib_det_matvec_work_len(int64_t nrow, int64_t ncol, int ny, int n);
+/* Which LU kernel apyib_det_outer / apyib_det_matvec launch: 0 (default) = one thread per matrix,
+ * column panels in registers + L in shared memory, for 2 <= n <= 12 and the sub-warp kernel above
+ * that; 1 = the sub-warp (one lane per row) kernel for every n.  Same results either way.       */
+int apyib_det_set_kernel(int which);
 
 /* Restricted-pair packing of doubles amplitudes, complex128 only:
  *   out[q*P + r] = 2 (x_q[i,j,a,b] - x_q[i,j,b,a] - x_q[j,i,a,b] + x_q[j,i,b,a]),  r = (i,a,j,b)

@@ -102,14 +102,26 @@ def test_spin_block_bit_exact():
     assert np.array_equal(utils.compute_so_overlap(5, F), orc.spin_block_2(F))
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 12, 16, 17, 24, 32])
-def test_det_outer_vs_numpy(n):
+@pytest.fixture(params=[0, 1], ids=["thread-per-matrix", "sub-warp"])
+def det_kernel(request):
+    """Both LU kernels behind apyib_det_outer / apyib_det_matvec (0 = default dispatch)."""
+    from apyib_b200._lib import lib, check
+    check(lib.apyib_det_set_kernel(request.param))
+    yield request.param
+    check(lib.apyib_det_set_kernel(0))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 17, 24, 32])
+@pytest.mark.parametrize("extra", [5, 60])      # ns = n + extra: S inside / outside shared memory
+def test_det_outer_vs_numpy(n, extra, det_kernel):
     from apyib_b200._lib import lib, check
     from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
+    if extra == 60 and (det_kernel == 1 or n > 12):
+        pytest.skip("large-S variant only differs for the thread-per-matrix kernel")
     rng = np.random.default_rng(5 + n)
-    ns = n + 5
+    ns = n + extra
     S = np.eye(ns) + 0.3 * (rng.standard_normal((ns, ns)) + 1j * rng.standard_normal((ns, ns)))
-    nrow, ncol = 37, 29
+    nrow, ncol = 137, 29
     rows = np.array([rng.permutation(ns)[:n] for _ in range(nrow)], dtype=np.int32)
     cols = np.array([rng.permutation(ns)[:n] for _ in range(ncol)], dtype=np.int32)
     dS, dr, dc = to_device(S), torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()
@@ -120,7 +132,7 @@ def test_det_outer_vs_numpy(n):
     assert np.abs(got - want).max() < 1e-11 * max(1.0, np.abs(want).max())
 
 
-def test_det_singular_and_tiny_pivots():
+def test_det_singular_and_tiny_pivots(det_kernel):
     from apyib_b200._lib import lib, check
     from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
     n = 6
@@ -137,14 +149,14 @@ def test_det_singular_and_tiny_pivots():
     assert to_host(out)[0, 0] == 0
 
 
-@pytest.mark.parametrize("n", [4, 9, 16])
-def test_det_matvec_vs_numpy(n):
+@pytest.mark.parametrize("n", [2, 4, 7, 9, 10, 12, 16])
+def test_det_matvec_vs_numpy(n, det_kernel):
     from apyib_b200._lib import lib, check
     from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
     rng = np.random.default_rng(50 + n)
     ns = n + 6
     S = np.eye(ns) + 0.2 * (rng.standard_normal((ns, ns)) + 1j * rng.standard_normal((ns, ns)))
-    nrow, ncol, ny = 53, 211, 3
+    nrow, ncol, ny = 153, 211, 3
     rows = np.array([rng.permutation(ns)[:n] for _ in range(nrow)], dtype=np.int32)
     cols = np.array([rng.permutation(ns)[:n] for _ in range(ncol)], dtype=np.int32)
     Y = rng.standard_normal((ny, ncol)) + 1j * rng.standard_normal((ny, ncol))
@@ -155,6 +167,27 @@ def test_det_matvec_vs_numpy(n):
     D = np.linalg.det(S[rows[:, None, :, None], cols[None, :, None, :]])
     want = Y @ D.T
     assert np.abs(to_host(Z) - want).max() < 1e-11 * max(1.0, np.abs(want).max())
+
+
+def test_det_kernels_agree_on_fd_overlap():
+    """Finite-difference-like overlap (I + O(h)): the thread-per-matrix and the sub-warp LU give the
+    same doubles x doubles products to rounding (the O(h^2)..O(h^4) determinants of aats.py:581-618)."""
+    from apyib_b200._lib import lib, check
+    from apyib_b200.aats import _Tables, _det_matvec
+    from apyib_b200.device import to_device, to_host
+    no, nv = 6, 7
+    rng = np.random.default_rng(77)
+    S = np.eye(no + nv) + 1e-4 * (rng.standard_normal((no + nv,) * 2) + 0.1j * rng.standard_normal((no + nv,) * 2))
+    T = _Tables.get(no, 0, nv)
+    Y = to_device(rng.standard_normal((2, T.n2)) + 1j * rng.standard_normal((2, T.n2)), torch.complex128)
+    dS = to_device(S, torch.complex128)
+    res = []
+    for which in (0, 1):
+        check(lib.apyib_det_set_kernel(which))
+        res.append(to_host(_det_matvec(dS, no, T.L[2], T.L[2], Y)))
+    check(lib.apyib_det_set_kernel(0))
+    scale = np.abs(res[1]).max()
+    assert scale > 0 and np.abs(res[0] - res[1]).max() < 1e-9 * scale
 
 
 @pytest.mark.parametrize("cplx", [False, True])

@@ -13,14 +13,23 @@ S = to_device(np.eye(nbf) + 1e-4 * (rng.standard_normal((nbf, nbf)) + 0.1j * rng
 T = _Tables.get(no, nf, nv)
 P = T.n2
 Y = to_device(rng.standard_normal((1, P)) + 1j * rng.standard_normal((1, P)), torch.complex128)
-for _ in range(3):
-    Z = _det_matvec(S, no, T.L[2], T.L[2], Y)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-reps = 5
-for _ in range(reps):
-    Z = _det_matvec(S, no, T.L[2], T.L[2], Y)
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
-print("n=%d P=%d  %.3f ms/launch  %.3e dets/s  %.2f TFLOP/s (8/3 n^3)" % (no, P, ms, P * P / ms * 1e3, P * P * 8 / 3 * no ** 3 / ms * 1e3 / 1e12))
+from apyib_b200._lib import lib, check
+kernels = [int(k) for k in os.environ.get("KERNELS", "0,1").split(",")]     # 0 = thread-per-matrix, 1 = sub-warp
+ref = None
+for which in kernels:
+    check(lib.apyib_det_set_kernel(which))
+    for _ in range(3):
+        Z = _det_matvec(S, no, T.L[2], T.L[2], Y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        Z = _det_matvec(S, no, T.L[2], T.L[2], Y)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if ref is None:
+        ref = Z.clone()
+    print("kernel=%d n=%d P=%d  %.3f ms/launch  %.3e dets/s  %.2f TFLOP/s (8/3 n^3)  maxdiff vs first %.2e (scale %.2e)"
+          % (which, no, P, ms, P * P / ms * 1e3, P * P * 8 / 3 * no ** 3 / ms * 1e3 / 1e12,
+             float((Z - ref).abs().max()), float(ref.abs().max())))
