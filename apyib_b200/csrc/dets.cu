@@ -186,10 +186,10 @@ static int launch_det(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, 
 }
 
 // thread-per-matrix LU (dets_tpm.cu), n <= 12
-int launch_det_tpm(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
-                   const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny, cplx *out, int outer);
-int tpm_blocks_per_sm(int n, int ns);
-constexpr int kTpmThreadsHost = 128;
+int launch_det_tpm(int n, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
+                   const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const cplx *Y, int ny,
+                   cplx *out, int outer);
+int tpm_total_warps(int n);
 constexpr int kTpmMaxN = 12;
 static int g_det_kernel = 0;   // 0 = thread-per-matrix for 2 <= n <= 12, sub-warp above; 1 = sub-warp always
 static bool use_tpm(int n) { return g_det_kernel == 0 && n >= 2 && n <= kTpmMaxN; }
@@ -220,12 +220,10 @@ extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_
     APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
     if (nrow == 0 || ncol == 0) return APYIB_OK;
     if (use_tpm(n)) {
-        const int64_t rb = (nrow + kTpmThreadsHost - 1) / kTpmThreadsHost;
-        APYIB_REQUIRE(rb <= 2147483647LL, "too many rows");
-        const int64_t nchunk = chunks_for(rb, ncol, 148 * 3, 65535);
+        const int64_t nchunk = chunks_for((nrow + 31) / 32, ncol, tpm_total_warps(n), 1 << 20);
         const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
-        return launch_det_tpm(n, dim3((unsigned)rb, (unsigned)nchunk), (cudaStream_t)stream, (const cplx *)d_S, ns,
-                              d_rows, nrow, d_cols, ncol, chunk_len, nullptr, 0, (cplx *)d_out, 1);
+        return launch_det_tpm(n, (cudaStream_t)stream, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
+                              nchunk, nullptr, 0, (cplx *)d_out, 1);
     }
     const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
@@ -244,7 +242,7 @@ extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_
 // Z[iy*nrow + r] = sum_c det(S[rows[r], cols[c]]) * Y[iy*ncol + c]
 // d_work: scratch of apyib_det_matvec_work_len(nrow, ncol, ny, n) complex128 elements.
 extern "C" int64_t apyib_det_matvec_nchunk(int64_t nrow, int64_t ncol, int n) {
-    if (use_tpm(n)) return chunks_for((nrow + kTpmThreadsHost - 1) / kTpmThreadsHost, ncol, 148 * 3, 4096);
+    if (use_tpm(n)) return chunks_for((nrow + 31) / 32, ncol, tpm_total_warps(n), 4096);
     const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     int64_t nchunk = (148 * 8 + rb - 1) / rb;
@@ -271,12 +269,12 @@ extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d
         APYIB_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(cplx) * ny * nrow, st));
         return APYIB_OK;
     }
-    const int64_t gpb = use_tpm(n) ? kTpmThreadsHost : groups_per_block(n);
+    const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     const int64_t nchunk = apyib_det_matvec_nchunk(nrow, ncol, n);
     const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
     dim3 grid((unsigned)rb, (unsigned)nchunk);
-    int rc = use_tpm(n) ? launch_det_tpm(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
+    int rc = use_tpm(n) ? launch_det_tpm(n, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len, nchunk,
                                          (const cplx *)d_Y, ny, (cplx *)d_work, 0)
                         : launch_det<false>(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
                                (const cplx *)d_Y, ny, (cplx *)d_work);

@@ -21,14 +21,17 @@
 //     of S (or through L1 when S is too large for it): no substituted matrix, and in the fused
 //     mode no determinant table (the reference's 8-index tensor, aats.py:575), exists in memory.
 //
-// Mapping: thread = one row list r (kept for the whole kernel), the block walks a chunk of column
-// lists c (uniform per warp -> broadcast loads); fused mode accumulates
+// Mapping: a warp takes one task = (32 consecutive row lists r) x (one chunk of column lists c);
+// lane = row list, the column list is warp-uniform (broadcast loads).  One block per SM, sized by
+// registers and shared memory; tasks are dealt out per warp.  Fused mode accumulates
 // z[q] += det(r,c) * Y[q,c] in registers and writes ny numbers per (chunk, r).
+#include <type_traits>
 #include "common.cuh"
 
 namespace apyib {
 
-constexpr int kTpmThreads = 128;
+// panel width: the whole matrix in registers up to n = 6, three columns above
+__host__ __device__ constexpr int tpm_panel(int n) { return n <= 6 ? n : 3; }
 
 template <int N, int B> struct tpm_cfg {
     static constexpr int NP = (N + B - 1) / B;                  // panels
@@ -38,16 +41,22 @@ template <int N, int B> struct tpm_cfg {
     static constexpr int per_thread_bytes = LCOUNT * 16 + N * 4;
 };
 
-// panel width by size: B*N complex = 4*B*N registers for the panel
-__host__ __device__ constexpr int tpm_panel(int n) { return n <= 6 ? n : (n <= 8 ? 4 : (n <= 12 ? 3 : 2)); }
+// ONE block per SM; its size is what registers (launch bounds -> <= 65536/T per thread) and the
+// per-thread shared-memory footprint allow.  Work is handed out per warp, so the block size does
+// not quantise the problem.
+__host__ __device__ constexpr int tpm_threads(int n) {
+    return n <= 4 ? 512 : n <= 6 ? 256 : n <= 9 ? 384 : n == 10 ? 288 : n == 11 ? 224 : 192;
+}
+constexpr int kTpmSmemMax = 227 * 1024;
 
 template <int N, int B, bool SSM>
-__global__ void __launch_bounds__(kTpmThreads, (N <= 10) ? 3 : 2)
+__global__ void __launch_bounds__(tpm_threads(N), 1)
 det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ rows, int64_t nrow,
-               const int32_t *__restrict__ cols, int64_t ncol, int64_t chunk_len, const cplx *__restrict__ Y, int ny,
-               cplx *__restrict__ out, int outer) {
+               const int32_t *__restrict__ cols, int64_t ncol, int64_t chunk_len, int64_t nchunk,
+               const cplx *__restrict__ Y, int ny, cplx *__restrict__ out, int outer) {
     using cfg = tpm_cfg<N, B>;
-    constexpr int T = kTpmThreads;
+    constexpr int T = tpm_threads(N);
+    static_assert((size_t)cfg::per_thread_bytes * T <= kTpmSmemMax - 1024, "shared-memory footprint");
     extern __shared__ __align__(16) unsigned char tpm_smem[];
     cplx *Ssm = reinterpret_cast<cplx *>(tpm_smem);
     const int ssz = SSM ? ns * ns : 0;
@@ -57,214 +66,223 @@ det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ r
         for (int e = threadIdx.x; e < ssz; e += T) Ssm[e] = ldg(&S[e]);
         __syncthreads();
     }
-    const int64_t r = (int64_t)blockIdx.x * T + threadIdx.x;
-    const bool rvalid = r < nrow;
-    const int64_t rr = rvalid ? r : nrow - 1;
-    int rowoff[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) rowoff[i] = __ldg(&rows[rr * N + i]) * ns;
-
-    const int64_t c0 = (int64_t)blockIdx.y * chunk_len;
-    int64_t c1 = c0 + chunk_len;
-    if (c1 > ncol) c1 = ncol;
-
+    const int lane = threadIdx.x & 31;
+    const int64_t nrg = (nrow + 31) >> 5;                        // groups of 32 row lists
+    const int64_t ntask = nrg * nchunk;
     constexpr int NYMAX = 4;
-    cplx z[NYMAX];
-#pragma unroll
-    for (int q = 0; q < NYMAX; ++q) z[q] = make_cplx(0.0, 0.0);
 
-    for (int64_t c = c0; c < c1; ++c) {
-        const int32_t *cl = cols + c * N;
+    for (int64_t task = (int64_t)blockIdx.x * (T / 32) + (threadIdx.x >> 5); task < ntask;
+         task += (int64_t)gridDim.x * (T / 32)) {
+        const int64_t ch = task / nrg, rg = task - ch * nrg;
+        const int64_t r = rg * 32 + lane;
+        const bool rvalid = r < nrow;
+        const int64_t rr = rvalid ? r : nrow - 1;
+        int rowoff[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) rpsm[i * T] = rowoff[i];
-        double detx = 1.0, dety = 0.0;
-        bool neg = false;
+        for (int i = 0; i < N; ++i) rowoff[i] = __ldg(&rows[rr * N + i]) * ns;
+        const int64_t c0 = ch * chunk_len;
+        int64_t c1 = c0 + chunk_len;
+        if (c1 > ncol) c1 = ncol;
+        cplx z[NYMAX];
 #pragma unroll
-        for (int jb = 0; jb < N; jb += B) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int bw = (N - jb < B) ? (N - jb) : B;
-            cplx a[B][N];
-            // ---- form the panel columns from S (row order = current permutation) ----
-            {
-                int ro[N];
+        for (int q = 0; q < NYMAX; ++q) z[q] = make_cplx(0.0, 0.0);
+
+        for (int64_t c = c0; c < c1; ++c) {
+            const int32_t *cl = cols + c * N;
+            if (cfg::NP > 1) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) ro[i] = (jb == 0) ? rowoff[i] : rpsm[i * T];
-#pragma unroll
-                for (int jj = 0; jj < B; ++jj) {
-                    if (jj < bw) {
-                        const int col = __ldg(&cl[jb + jj]);
-#pragma unroll
-                        for (int i = 0; i < N; ++i) a[jj][i] = SSM ? Ssm[ro[i] + col] : ldg(&S[ro[i] + col]);
-                    }
-                }
+                for (int i = 0; i < N; ++i) rpsm[i * T] = rowoff[i];
             }
-            // ---- left-looking update with the L columns of earlier panels ----
+            double detx = 1.0, dety = 0.0;
+            bool neg = false;
 #pragma unroll
-            for (int k = 0; k < jb; ++k) {
+            for (int jb = 0; jb < N; jb += B) {
+                const int bw = (N - jb < B) ? (N - jb) : B;
+                cplx a[B][N];
+                // ---- form the panel columns from S (row order = current permutation) ----
+                {
+                    int ro[N];
 #pragma unroll
-                for (int i = k + 1; i < N; ++i) {
-                    const cplx l = Lsm[(cfg::loff(k) + i - k - 1) * T];
+                    for (int i = 0; i < N; ++i) ro[i] = (jb == 0) ? rowoff[i] : rpsm[i * T];
 #pragma unroll
                     for (int jj = 0; jj < B; ++jj) {
                         if (jj < bw) {
-                            a[jj][i].x = fma(l.y, a[jj][k].y, fma(-l.x, a[jj][k].x, a[jj][i].x));
-                            a[jj][i].y = fma(-l.y, a[jj][k].x, fma(-l.x, a[jj][k].y, a[jj][i].y));
+                            const int col = __ldg(&cl[jb + jj]);
+#pragma unroll
+                            for (int i = 0; i < N; ++i) a[jj][i] = SSM ? Ssm[ro[i] + col] : ldg(&S[ro[i] + col]);
+                        }
+                    }
+                }
+                // ---- left-looking update with the L columns of earlier panels ----
+#pragma unroll
+                for (int k = 0; k < jb; ++k) {
+#pragma unroll
+                    for (int i = k + 1; i < N; ++i) {
+                        const cplx l = Lsm[(cfg::loff(k) + i - k - 1) * T];
+#pragma unroll
+                        for (int jj = 0; jj < B; ++jj) {
+                            if (jj < bw) {
+                                a[jj][i].x = fma(l.y, a[jj][k].y, fma(-l.x, a[jj][k].x, a[jj][i].x));
+                                a[jj][i].y = fma(-l.y, a[jj][k].x, fma(-l.x, a[jj][k].y, a[jj][i].y));
+                            }
+                        }
+                    }
+                }
+                // ---- factorise the panel (right-looking inside it) ----
+#pragma unroll
+                for (int jj = 0; jj < B; ++jj) {
+                    if (jj < bw) {
+                        const int j = jb + jj;
+                        // pivot: first maximum of |re|+|im| over rows j..N-1
+                        unsigned best = 0u;
+#pragma unroll
+                        for (int i = j; i < N; ++i) {
+                            const double mag = fabs(a[jj][i].x) + fabs(a[jj][i].y);
+                            const unsigned key = (((unsigned)__double2hiint(mag)) & 0xffffffe0u) | (unsigned)(31 - i);
+                            best = (key > best) ? key : best;
+                        }
+                        const int p = 31 - (int)(best & 31u);
+                        const bool sw = (p != j);
+                        // One elimination step.  SWAP = true first gathers the pivot row (dynamic p) and
+                        // drops the old row j into slot p with selects; the selected values are only
+                        // temporaries of the FMAs that follow, so the two code versions merge without
+                        // register shuffling (an in-place swap under a branch costs ~2 MOVs per select).
+                        auto step = [&](auto swap_tag) {
+                            constexpr bool SWAP = decltype(swap_tag)::value;
+                            cplx u[B];                       // pivot row in the panel columns
+#pragma unroll
+                            for (int j2 = jj; j2 < B; ++j2) {
+                                if (j2 < bw) {
+                                    u[j2] = a[j2][j];
+                                    if (SWAP) {
+#pragma unroll
+                                        for (int i = j + 1; i < N; ++i) {
+                                            const bool m = (i == p);
+                                            u[j2].x = m ? a[j2][i].x : u[j2].x;
+                                            u[j2].y = m ? a[j2][i].y : u[j2].y;
+                                        }
+                                    }
+                                }
+                            }
+                            const double pvx = u[jj].x, pvy = u[jj].y;
+                            const double ndx = detx * pvx - dety * pvy;
+                            dety = detx * pvy + dety * pvx;
+                            detx = ndx;
+                            const double d2 = fma(pvx, pvx, pvy * pvy);
+                            const double rinv = (d2 > 0.0) ? __drcp_rn(d2) : 0.0;   // singular column -> det = 0
+                            const double ix = pvx * rinv, iy = -pvy * rinv;
+#pragma unroll
+                            for (int i = j + 1; i < N; ++i) {
+                                const bool m = SWAP && (i == p);
+                                const double xr = m ? a[jj][j].x : a[jj][i].x, xi = m ? a[jj][j].y : a[jj][i].y;
+                                const double lx = fma(xr, ix, -xi * iy);
+                                const double ly = fma(xr, iy, xi * ix);
+                                if (j < cfg::NL) Lsm[(cfg::loff(j) + i - j - 1) * T] = make_cplx(lx, ly);
+#pragma unroll
+                                for (int j2 = jj + 1; j2 < B; ++j2) {
+                                    if (j2 < bw) {
+                                        const double yr = m ? a[j2][j].x : a[j2][i].x, yi = m ? a[j2][j].y : a[j2][i].y;
+                                        a[j2][i].x = fma(ly, u[j2].y, fma(-lx, u[j2].x, yr));
+                                        a[j2][i].y = fma(-ly, u[j2].x, fma(-lx, u[j2].y, yi));
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j2 = jj + 1; j2 < B; ++j2)
+                                if (j2 < bw) a[j2][j] = u[j2];
+                        };
+                        if (j + 1 < N) {
+                            if (__any_sync(0xffffffffu, sw)) {
+                                if (sw) {
+                                    if (cfg::NP > 1) {
+                                        const int t0 = rpsm[j * T], t1 = rpsm[p * T];
+                                        rpsm[j * T] = t1;
+                                        rpsm[p * T] = t0;
+                                    }
+                                    // L rows j <-> p: all loads first, then all stores (latency overlapped)
+                                    constexpr int KS = (cfg::NL < N ? cfg::NL : N);
+                                    cplx lj[KS > 0 ? KS : 1], lp[KS > 0 ? KS : 1];
+#pragma unroll
+                                    for (int k = 0; k < j; ++k) {
+                                        if (k < cfg::NL) {
+                                            lj[k] = Lsm[(cfg::loff(k) + j - k - 1) * T];
+                                            lp[k] = Lsm[(cfg::loff(k) + p - k - 1) * T];
+                                        }
+                                    }
+#pragma unroll
+                                    for (int k = 0; k < j; ++k) {
+                                        if (k < cfg::NL) {
+                                            Lsm[(cfg::loff(k) + j - k - 1) * T] = lp[k];
+                                            Lsm[(cfg::loff(k) + p - k - 1) * T] = lj[k];
+                                        }
+                                    }
+                                    neg = !neg;
+                                }
+                                step(std::true_type{});
+                            } else {
+                                step(std::false_type{});
+                            }
+                        } else {
+                            const double pvx = a[jj][j].x, pvy = a[jj][j].y;
+                            const double ndx = detx * pvx - dety * pvy;
+                            dety = detx * pvy + dety * pvx;
+                            detx = ndx;
                         }
                     }
                 }
             }
-            // ---- factorise the panel (right-looking inside it) ----
+            const cplx d = make_cplx(neg ? -detx : detx, neg ? -dety : dety);
+            if (outer) {
+                if (rvalid) out[r * ncol + c] = d;
+            } else {
 #pragma unroll
-            for (int jj = 0; jj < B; ++jj) {
-                if (jj < bw) {
-                    const int j = jb + jj;
-                    // pivot: first maximum of |re|+|im| over rows j..N-1
-                    unsigned best = 0u;
-#pragma unroll
-                    for (int i = j; i < N; ++i) {
-                        const double mag = fabs(a[jj][i].x) + fabs(a[jj][i].y);
-                        const unsigned key = (((unsigned)__double2hiint(mag)) & 0xffffffe0u) | (unsigned)(31 - i);
-                        best = (key > best) ? key : best;
-                    }
-                    const int p = 31 - (int)(best & 31u);
-                    const bool sw = (p != j);
-                    if (j + 1 < N && __any_sync(0xffffffffu, sw)) {
-#pragma unroll
-                        for (int j2 = jj; j2 < B; ++j2) {
-                            if (j2 < bw) {
-                                const cplx t = a[j2][j];
-#pragma unroll
-                                for (int i = j + 1; i < N; ++i) {
-                                    const bool m = (i == p);
-                                    const cplx ci = a[j2][i];
-                                    a[j2][j].x = m ? ci.x : a[j2][j].x;
-                                    a[j2][j].y = m ? ci.y : a[j2][j].y;
-                                    a[j2][i].x = m ? t.x : ci.x;
-                                    a[j2][i].y = m ? t.y : ci.y;
-                                }
-                            }
-                        }
-                        if (sw) {
-                            if (cfg::NL > 0 && j < N - 1) {
-                                const int t0 = rpsm[j * T], t1 = rpsm[p * T];
-                                rpsm[j * T] = t1;
-                                rpsm[p * T] = t0;
-                            }
-#pragma unroll
-                            for (int k = 0; k < j; ++k) {
-                                if (k < cfg::NL) {
-                                    cplx *pj = &Lsm[(cfg::loff(k) + j - k - 1) * T];
-                                    cplx *pp = &Lsm[(cfg::loff(k) + p - k - 1) * T];
-                                    const cplx u = *pj, w = *pp;
-                                    *pj = w;
-                                    *pp = u;
-                                }
-                            }
-                            neg = !neg;
-                        }
-                    }
-                    const double pvx = a[jj][j].x, pvy = a[jj][j].y;
-                    const double ndx = detx * pvx - dety * pvy;
-                    dety = detx * pvy + dety * pvx;
-                    detx = ndx;
-                    if (j + 1 < N) {
-                        const double d2 = fma(pvx, pvx, pvy * pvy);
-                        const double rinv = (d2 > 0.0) ? __drcp_rn(d2) : 0.0;   // singular column -> det = 0
-                        const double ix = pvx * rinv, iy = -pvy * rinv;
-#pragma unroll
-                        for (int i = j + 1; i < N; ++i) {
-                            const double lx = fma(a[jj][i].x, ix, -a[jj][i].y * iy);
-                            const double ly = fma(a[jj][i].x, iy, a[jj][i].y * ix);
-                            a[jj][i].x = lx;
-                            a[jj][i].y = ly;
-                            if (j < cfg::NL) Lsm[(cfg::loff(j) + i - j - 1) * T] = make_cplx(lx, ly);
-#pragma unroll
-                            for (int j2 = jj + 1; j2 < B; ++j2) {
-                                if (j2 < bw) {
-                                    a[j2][i].x = fma(ly, a[j2][j].y, fma(-lx, a[j2][j].x, a[j2][i].x));
-                                    a[j2][i].y = fma(-ly, a[j2][j].x, fma(-lx, a[j2][j].y, a[j2][i].y));
-                                }
-                            }
-                        }
-                    }
-                }
+                for (int q = 0; q < NYMAX; ++q)
+                    if (q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
             }
         }
-        const cplx d = make_cplx(neg ? -detx : detx, neg ? -dety : dety);
-        if (outer) {
-            if (rvalid) out[r * ncol + c] = d;
-        } else {
+        if (!outer && rvalid) {
 #pragma unroll
             for (int q = 0; q < NYMAX; ++q)
-                if (q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
+                if (q < ny) out[(ch * ny + q) * nrow + r] = z[q];
         }
-    }
-    if (!outer && rvalid) {
-#pragma unroll
-        for (int q = 0; q < NYMAX; ++q)
-            if (q < ny) out[((int64_t)blockIdx.y * ny + q) * nrow + r] = z[q];
     }
 }
 
 template <int N>
-static int launch_tpm_n(dim3 grid, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
-                        const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny, cplx *out,
-                        int outer) {
+static int launch_tpm_n(cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
+                        const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const cplx *Y, int ny,
+                        cplx *out, int outer) {
     constexpr int B = tpm_panel(N);
+    constexpr int T = tpm_threads(N);
     using cfg = tpm_cfg<N, B>;
-    const size_t base = (size_t)cfg::per_thread_bytes * kTpmThreads;
+    const size_t base = (size_t)cfg::per_thread_bytes * T;
     const size_t s_bytes = (size_t)ns * ns * sizeof(cplx);
-    // S in shared memory only while three blocks per SM still fit (227 KB per SM)
-    const bool ssm = (base + s_bytes) * 3 <= 220 * 1024;
+    const bool ssm = base + s_bytes <= (size_t)kTpmSmemMax - 1024;   // S in shared memory when it fits
     const size_t smem = base + (ssm ? s_bytes : 0);
-    if (ssm) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            APYIB_CUDA_CHECK(cudaFuncSetAttribute(det_tpm_kernel<N, B, true>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done = true;
-        }
-        det_tpm_kernel<N, B, true><<<grid, kTpmThreads, smem, st>>>(S, ns, rows, nrow, cols, ncol, chunk_len, Y, ny,
-                                                                    out, outer);
-    } else {
-        static bool attr_done = false;
-        if (!attr_done) {
-            APYIB_CUDA_CHECK(cudaFuncSetAttribute(det_tpm_kernel<N, B, false>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_done = true;
-        }
-        det_tpm_kernel<N, B, false><<<grid, kTpmThreads, smem, st>>>(S, ns, rows, nrow, cols, ncol, chunk_len, Y, ny,
-                                                                     out, outer);
+    const int64_t ntask = ((nrow + 31) / 32) * nchunk;
+    int64_t blocks = (ntask + T / 32 - 1) / (T / 32);
+    if (blocks > 148) blocks = 148;
+    auto kern = ssm ? det_tpm_kernel<N, B, true> : det_tpm_kernel<N, B, false>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[ssm]) {
+        APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTpmSmemMax));
+        attr_done[ssm] = true;
     }
+    kern<<<(unsigned)blocks, T, smem, st>>>(S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, Y, ny, out, outer);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
 
-// resident blocks per SM (shared-memory bound), used by the host to size the grid in whole waves
-int tpm_blocks_per_sm(int n, int ns) {
-    int per_thread = 0;
-    switch (n) {
-#define APYIB_TPM_PT(NN) case NN: per_thread = tpm_cfg<NN, tpm_panel(NN)>::per_thread_bytes; break;
-        APYIB_TPM_PT(2) APYIB_TPM_PT(3) APYIB_TPM_PT(4) APYIB_TPM_PT(5) APYIB_TPM_PT(6) APYIB_TPM_PT(7)
-        APYIB_TPM_PT(8) APYIB_TPM_PT(9) APYIB_TPM_PT(10) APYIB_TPM_PT(11) APYIB_TPM_PT(12)
-#undef APYIB_TPM_PT
-        default: return 0;
-    }
-    const size_t base = (size_t)per_thread * kTpmThreads;
-    const size_t s_bytes = (size_t)ns * ns * sizeof(cplx);
-    const size_t smem = ((base + s_bytes) * 3 <= 220 * 1024) ? base + s_bytes : base;
-    int b = (int)((227 * 1024) / (smem + 1024));
-    if (b > (n <= 10 ? 3 : 2)) b = (n <= 10 ? 3 : 2);     // register bound (launch bounds of the kernel)
-    if (b < 1) b = 1;
-    return b;
-}
+// warps resident on the device for size n (one block per SM): the host sizes the column chunks so
+// that (row groups) x (chunks) fills them in whole waves
+int tpm_total_warps(int n) { return 148 * (tpm_threads(n) / 32); }
 
-int launch_det_tpm(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
-                   const int32_t *cols, int64_t ncol, int64_t chunk_len, const cplx *Y, int ny, cplx *out, int outer) {
+int launch_det_tpm(int n, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
+                   const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const cplx *Y, int ny,
+                   cplx *out, int outer) {
     switch (n) {
 #define APYIB_TPM_CASE(NN) \
-    case NN: return launch_tpm_n<NN>(grid, st, S, ns, rows, nrow, cols, ncol, chunk_len, Y, ny, out, outer);
+    case NN: return launch_tpm_n<NN>(st, S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, Y, ny, out, outer);
         APYIB_TPM_CASE(2) APYIB_TPM_CASE(3) APYIB_TPM_CASE(4) APYIB_TPM_CASE(5) APYIB_TPM_CASE(6) APYIB_TPM_CASE(7)
         APYIB_TPM_CASE(8) APYIB_TPM_CASE(9) APYIB_TPM_CASE(10) APYIB_TPM_CASE(11) APYIB_TPM_CASE(12)
 #undef APYIB_TPM_CASE
