@@ -374,20 +374,33 @@ class AAT(object):
             n2 = o * o * nv * nv
             check(lib.apyib_pack_doubles(ptr(X2), n2, nx, o, nv, nf, ptr(T.doubles_dev), P, ptr(Xh), stream_ptr()))
             check(lib.apyib_pack_doubles(ptr(Y2), n2, ny, o, nv, nf, ptr(T.doubles_dev), P, ptr(Yh), stream_ptr()))
-            if not factorized:
-                z22 = matvec(2, 2, Yh, False)                            # the P x P table, fused      [s,q,r]
-            ys = [wy.reshape(nS, ny, -1)] + ([Y1.reshape(1, ny, -1).expand(nS, ny, n1)] if cisd else [])
-            z21 = matvec(2, 1, torch.cat(ys, 1).contiguous(), True)      # [s, ny(+ny), P]
-            z12 = matvec(1, 2, Yh, False)                                # [s, q, ov]
-            if factorized:
-                dd["c1f"] = self._dd_factorized(prep, nS, ns, no, nf, X2, Y2)
-            else:
-                dd["c1"] = cn("xr,sqr->sxq", Xh, z22)
+            uxs = _axpby(1.0, uxp, 1.0, ux.clone())                      # ux + ux'
             dd["v1"] = cn("xr,sr->sx", Xh, D20)
             dd["v2"] = cn("sr,qr->sq", D02, Yh)
-            dd["c3"] = cn("xr,sqr->sxq", Xh, z21[:, :ny])
-            uxs = _axpby(1.0, uxp, 1.0, ux.clone())                      # ux + ux'
-            dd["c4"] = cn("sxr,sqr->sxq", uxs.reshape(nS, nx, -1), z12)
+            if factorized:
+                # doubles x doubles, doubles x singles and singles x doubles tables in closed form
+                f = self._dd_factorized(prep, nS, ns, no, nf, X2, Y2)
+                dd["c1f"] = f["dd"]
+                half = lambda a, b, rest: _axpby(0.5, cn("sx,sq->sxq", a, b), 1.0, rest)
+                # sum_r Xh[r] D21[r,c] y[c] / det(S_oo) = alpha (Q.y)/2 + M.y
+                dd["c3f"] = half(f["alpha"], cn("skc,sqkc->sq", f["Q"], wy), cn("sxkc,sqkc->sxq", f["M"], wy))
+                # sum_c D12[(i,a),c] Yh[c] / det(S_oo) = beta P_ai/2 + N_ia,  N = A^-T W R^T
+                Nq = cn("ski,sqka->sqia", f["Ai"], cn("sac,sqkc->sqka", f["R"], f["W"]))
+                dd["c4f"] = half(cn("sxia,sai->sx", uxs, f["P"]), f["beta"], cn("sxia,sqia->sxq", uxs, Nq))
+                if cisd:
+                    dd["ds1f"] = half(f["alpha"], cn("skc,qkc->sq", f["Q"], Y1), cn("sxkc,qkc->sxq", f["M"], Y1))
+                    dd["sd1f"] = half(cn("xia,sai->sx", X1, f["P"]), f["beta"], cn("xia,sqia->sxq", X1, Nq))
+            else:
+                z22 = matvec(2, 2, Yh, False)                            # the P x P table, fused      [s,q,r]
+                ys = [wy.reshape(nS, ny, -1)] + ([Y1.reshape(1, ny, -1).expand(nS, ny, n1)] if cisd else [])
+                z21 = matvec(2, 1, torch.cat(ys, 1).contiguous(), True)  # [s, ny(+ny), P]
+                z12 = matvec(1, 2, Yh, False)                            # [s, q, ov]
+                dd["c1"] = cn("xr,sqr->sxq", Xh, z22)
+                dd["c3"] = cn("xr,sqr->sxq", Xh, z21[:, :ny])
+                dd["c4"] = cn("sxr,sqr->sxq", uxs.reshape(nS, nx, -1), z12)
+                if cisd:
+                    dd["ds1"] = cn("xr,sqr->sxq", Xh, z21[:, ny:])
+                    dd["sd1"] = cn("xr,sqr->sxq", X1.reshape(nx, -1), z12)
         if cisd:
             Gy1 = cn("siakc,qkc->sqia", G, Y1)
             Gwy = cn("siakc,sqkc->sqia", G, wy)
@@ -398,9 +411,6 @@ class AAT(object):
             dd["sd3"] = cn("xia,sqia->sxq", X1, Gwy)
             dd["d0b"] = cn("sxjb,sjb->sx", uxp, A)
             dd["0db"] = cn("skc,sqkc->sq", B, wy)
-            if P:
-                dd["ds1"] = cn("xr,sqr->sxq", Xh, z21[:, ny:])
-                dd["sd1"] = cn("xr,sqr->sxq", X1.reshape(nx, -1), z12)
         # one device->host copy for all the small result tensors of the stack
         keys = list(dd)
         flat = torch.cat([dS.reshape(-1)] + [dd[k].reshape(-1) for k in keys])
@@ -411,6 +421,9 @@ class AAT(object):
             n_el = dd[k].numel()
             h[k] = fh[off:off + n_el].reshape(tuple(dd[k].shape))
             off += n_el
+        for k in ("c3", "c4", "ds1", "sd1"):          # closed forms are per det(S_oo), like c1f
+            if k + "f" in h:
+                h[k] = dSh_all.reshape(nS, 1, 1) * h[k + "f"]
         res = []
         for s in range(nS):
             dSh = complex(dSh_all[s])
@@ -443,7 +456,8 @@ class AAT(object):
             sum Xf Yf det T = 4 [ (Xf.PP)(Yf.QQ) + 4 sum_kc (A U R)_kc W_kc + sum_klcd Z_klcd Yf_klcd ]
             U_jb = sum_ia Xf_ijab P_ai,  W_kc = sum_ld Yf_klcd Q_ld,  Z_klcd = sum A_ki A_lj R_ac R_bd Xf_ijab
         i.e. O(o^2 v^2 (o+v)) DMMA contractions instead of (C(o,2) C(v,2))^2 determinants.
-        Returns [nS, nx, ny]: the unrestricted sum (= 16 x the restricted i<j,a<b,k<l,c<d sum) over det T."""
+        Returns the intermediates and "dd" [nS, nx, ny]: the unrestricted sum (= 16 x the restricted
+        i<j,a<b,k<l,c<d sum) over det T."""
         from .utils import gather4
         nv = ns - no
         o = no - nf
@@ -479,7 +493,9 @@ class AAT(object):
         _axpby(4.0, mixed, 1.0, ab)
         _axpby(1.0, gamma, 1.0, ab)
         _axpby(4.0, ab, 0.0, mixed)          # mixed <- 4 (alpha beta + 4 mixed + gamma)
-        return mixed
+        # alpha, beta, M, W also give the doubles x singles / singles x doubles tables (see _blocks):
+        #   sum_ijab Xf det3(ijab; kc) = -2 alpha Q_kc - 4 M_kc,   sum_klcd Yf det3(ia; klcd) = 2 beta P_ai + 4 N_ia
+        return dict(dd=mixed, alpha=alpha, beta=beta, M=M, W=W, Ai=Ai, P=P, Q=Q, R=R)
 
     def _spatial_terms(self, alpha, beta, normalization):
         m = self.parameters["method"]

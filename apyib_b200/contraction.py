@@ -101,7 +101,7 @@ def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
     M, N, K, ptrs, a_kfast, b_kfast, _keep, batch, ksplit, work, tma = _plan(spec, A, B, out)
     alpha, beta = complex(alpha), complex(beta)
     if tma is not None and ksplit == 1 and config.USE_TMA:
-        with config.timed("contract_tma[%s %dx%dx%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K)):
+        with config.timed("contract_tma[%s %dx%dx%d b%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K, batch[0])):
             rc = lib.apyib_contract_tma(dtype_code(A), ptr(A), ptr(B), ptr(out), M, N, K, tma[0], tma[1],
                                         C.c_void_p(ptrs[4]), C.c_void_p(ptrs[5]), int(conj_a), int(conj_b),
                                         alpha.real, alpha.imag, beta.real, beta.imag,
@@ -111,7 +111,7 @@ def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
         if rc != -3:          # APYIB_ERR_UNSUPPORTED -> fall through to the gather kernel
             check(rc)
     if config.TIMING is not None:
-        with config.timed("contract[%s %dx%dx%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K)):
+        with config.timed("contract[%s %dx%dx%d b%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K, batch[0])):
             check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch, ksplit, work))
         return out
     check(_launch(A, B, out, M, N, K, ptrs, a_kfast, b_kfast, conj_a, conj_b, alpha, beta, batch, ksplit, work))

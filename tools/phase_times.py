@@ -52,4 +52,19 @@ print("step with timing hooks: %.3f s, launches %d" % (dt, _lib.LAUNCHES[0] - n0
 for k, v in agg.most_common(12):
     print("  %-40s n=%6d %9.1f ms" % (k, cnt[k], v))
 
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+import re
+print("top contraction signatures (eager step):")
+rows = []
+for k, ev in tm.items():
+    m = re.match(r"contract(_tma)?\[(f64|c128) (\d+)x(\d+)x(\d+) b(\d+)\]", k)
+    if not m:
+        continue
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    M, N, K, nb = (int(m.group(i)) for i in (3, 4, 5, 6))
+    fl = (8.0 if m.group(2) == "c128" else 2.0) * M * N * K * nb * len(ev)
+    rows.append((ms, k, len(ev), fl / (ms * 1e-3) / 1e12))
+for ms, k, n, tf in sorted(rows, reverse=True)[:24]:
+    print("  %-46s n=%5d %8.1f ms  %6.2f TFLOP/s" % (k, n, ms, tf))
+print("  total contraction time %.1f ms" % sum(r[0] for r in rows))
+
+pstats.Stats(pr).sort_stats("cumulative").print_stats(12)
