@@ -30,7 +30,7 @@ def _offsets(dims, strides):
 
 def _plan(spec, A, B, out):
     key = (spec, tuple(A.shape), tuple(A.stride()), tuple(B.shape), tuple(B.stride()),
-           tuple(out.shape), tuple(out.stride()), A.device.index)
+           tuple(out.shape), tuple(out.stride()), A.device.index, A.dtype)
     p = _table_cache.get(key)
     if p is not None:
         return p
@@ -80,15 +80,24 @@ def _plan(spec, A, B, out):
         ld = int(tab[1] - tab[0])
         return ld if ld > 0 and np.array_equal(tab, np.arange(len(tab), dtype=np.int64) * ld) else 0
     tma = None
-    if K >= 16 and linear(tabs[1]) == 1 and linear(tabs[2]) == 1 and tabs[0][0] == 0 and tabs[3][0] == 0:
+    # (skinny sides go to the 16-wide tiles of the gather kernel: a 64 x 64 TMA tile would be mostly padding)
+    if K >= 16 and M > 16 and N > 16 and linear(tabs[1]) == 1 and linear(tabs[2]) == 1 and tabs[0][0] == 0 and tabs[3][0] == 0:
         lda, ldb = (linear(tabs[0]) if M > 1 else K), (linear(tabs[3]) if N > 1 else K)
         if lda and ldb and lda >= K and ldb >= K and ((M + 63) // 64) * ((N + 63) // 64) * batch[0] >= 148:
             tma = (lda, ldb)
-    # split-K for dot-product-like shapes: few output tiles, long K (one CTA would walk K alone)
-    tiles = ((M + 31) // 32) * ((N + 31) // 32) * batch[0]
+    # split-K for dot-product-like shapes: few output tiles, long K (one CTA would walk K alone).
+    # Tile shapes mirror apyib_contract's choice (csrc/contract.cu): 16-wide tiles for skinny sides.
+    cplx = A.dtype == torch.complex128
+    if N <= 16 and M > 16:
+        bm, bn = (64 if cplx else 128), 16
+    elif M <= 16 and N > 16:
+        bm, bn = 16, (64 if cplx else 128)
+    else:
+        bm = bn = 32
+    tiles = ((M + bm - 1) // bm) * ((N + bn - 1) // bn) * batch[0]
     ksplit = 1
-    if tiles < 148 and K >= 4096:
-        ksplit = int(min(max(1, (2 * 148) // tiles), (K + 1023) // 1024, 65535 // batch[0]))
+    if tiles < 2 * 148 and K >= 2048:
+        ksplit = int(min(max(1, (3 * 148) // tiles), (K + 511) // 512, 65535 // batch[0]))
     work = torch.empty(batch[0] * ksplit * M * N, dtype=A.dtype, device=A.device) if ksplit > 1 else None
     p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch, ksplit, work, tma)
     _table_cache[key] = p

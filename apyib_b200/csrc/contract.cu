@@ -355,6 +355,17 @@ extern "C" int apyib_contract(int dtype, const void *d_A, const void *d_B, void 
     a.a_kfast = a_kfast; a.b_kfast = b_kfast; a.conj_a = conj_a; a.conj_b = conj_b;
     a.ksplit = ksplit; a.work = d_work;
     cudaStream_t st = (cudaStream_t)stream;
+    // Skinny shapes (T1 <-> T2 couplings of ci_wfn.py:457-470, Fock-like terms :471-474, J/K builds): one
+    // side is <= 16 wide, the other operand is streamed once -> HBM-bound.  A 64-wide tile would spend
+    // >= 75 % of its DMMAs and of its B-tile loads on padding, so these get N (or M) = 16 tiles.
+    if (N <= 16 && M > 16) {
+        return dtype == APYIB_C128 ? launch_contract<true, 64, 16, 16, 16, 16, 3>(a, batch, st)
+                                   : launch_contract<false, 128, 16, 16, 32, 16, 3>(a, batch, st);
+    }
+    if (M <= 16 && N > 16) {
+        return dtype == APYIB_C128 ? launch_contract<true, 16, 64, 16, 16, 16, 3>(a, batch, st)
+                                   : launch_contract<false, 16, 128, 16, 16, 32, 3>(a, batch, st);
+    }
     // tile choice: 64x64 when that already yields >= 1 wave of CTAs on 148 SMs, else 32x32
     const int64_t big_tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
     const bool big = big_tiles >= 148 && ksplit == 1;

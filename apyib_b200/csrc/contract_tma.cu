@@ -56,18 +56,21 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
         : "memory");
 }
 
-// 64 x 64 CTA tile, 4 warps of 32 x 32, slab = 128 bytes of k (8 complex / 16 real), STAGES-deep ring.
-template <bool CPLX, int STAGES>
+// 64 x BN CTA tile (BN = 64 or 48), 4 warps of 32 x BN/2, slab = 128 bytes of k (8 complex / 16 real),
+// STAGES-deep ring.  BN = 48 exists for the ladder term: N = o^2 = 144 is 3 x 48 but 2.25 x 64, i.e. a
+// quarter of the DMMAs of a 64-wide tiling would multiply padding.
+template <bool CPLX, int STAGES, int BN>
 __global__ void __launch_bounds__(128)
 contract_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TmaArgs p) {
-    constexpr int BM = 64, BN = 64, WM = 32, WN = 32, TM = 4, TN = 4;
+    constexpr int BM = 64, WM = 32, WN = BN / 2, TM = 4, TN = WN / 8;
     constexpr int BK = CPLX ? 8 : 16;                     // elements per 128-byte row
-    constexpr unsigned TILE_BYTES = 64 * 128;             // one operand tile
+    constexpr unsigned TILE_BYTES = 64 * 128;             // A tile
+    constexpr unsigned TILE_BYTES_B = BN * 128;           // B tile (multiple of 1024: swizzle atom)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // 1024-byte aligned tiles (required by the 128B swizzle), barriers after them
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *As = base, *Bs = base + STAGES * TILE_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + 2 * STAGES * TILE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + STAGES * (TILE_BYTES + TILE_BYTES_B));
 
     const int z = blockIdx.z;
     if (p.active != nullptr && p.active[z] == 0) return;
@@ -85,10 +88,10 @@ contract_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     auto issue = [&](int64_t slab) {
         const int s = (int)(slab % STAGES);
         const unsigned bar = smem_u32(&bars[s]);
-        mbar_expect_tx(bar, 2 * TILE_BYTES);
+        mbar_expect_tx(bar, TILE_BYTES + TILE_BYTES_B);
         const int kcoord = (int)(slab * BK) * (CPLX ? 2 : 1);       // inner coordinate in doubles
         tma_load_3d(smem_u32(As + s * TILE_BYTES), &mapA, bar, kcoord, (int)m0, z);
-        tma_load_3d(smem_u32(Bs + s * TILE_BYTES), &mapB, bar, kcoord, (int)n0, z);
+        tma_load_3d(smem_u32(Bs + s * TILE_BYTES_B), &mapB, bar, kcoord, (int)n0, z);
     };
     if (tid == 0)
         for (int s = 0; s < STAGES && s < nslab; ++s) issue(s);
@@ -108,7 +111,7 @@ contract_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     for (int64_t kt = 0; kt < nslab; ++kt) {
         const int s = (int)(kt % STAGES);
         mbar_wait(smem_u32(&bars[s]), (unsigned)((kt / STAGES) & 1));
-        const unsigned char *as = As + s * TILE_BYTES, *bs = Bs + s * TILE_BYTES;
+        const unsigned char *as = As + s * TILE_BYTES, *bs = Bs + s * TILE_BYTES_B;
 #pragma unroll
         for (int kk = 0; kk < BK; kk += 4) {
             if constexpr (CPLX) {
@@ -221,12 +224,12 @@ static EncodeTiledFn get_encode() {
 
 // rows x kdoubles matrix of doubles (complex = 2 doubles), `batch` of them
 static bool make_map(CUtensorMap *map, const void *base, int64_t kdoubles, int64_t rows, int64_t ld_bytes, int batch,
-                     int64_t bs_bytes) {
+                     int64_t bs_bytes, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)kdoubles, (cuuint64_t)rows, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld_bytes, (cuuint64_t)(batch > 1 ? bs_bytes : ld_bytes * rows)};
-    cuuint32_t box[3] = {16, 64, 1};
+    cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -259,8 +262,9 @@ extern "C" int apyib_contract_tma(int dtype, const void *d_A, const void *d_B, v
     }
     CUtensorMap mapA, mapB;
     const int64_t kd = K * (dtype == APYIB_C128 ? 2 : 1);
-    if (!make_map(&mapA, d_A, kd, M, lda * es, batch, a_bstride * es) ||
-        !make_map(&mapB, d_B, kd, N, ldb * es, batch, b_bstride * es)) {
+    const int bn = (((N + 47) / 48) * 48 < ((N + 63) / 64) * 64) ? 48 : 64;      // less padding wins
+    if (!make_map(&mapA, d_A, kd, M, lda * es, batch, a_bstride * es, 64) ||
+        !make_map(&mapB, d_B, kd, N, ldb * es, batch, b_bstride * es, bn)) {
         set_error("apyib_contract_tma: cuTensorMapEncodeTiled failed or is unavailable");
         return APYIB_ERR_UNSUPPORTED;
     }
@@ -269,16 +273,26 @@ extern "C" int apyib_contract_tma(int dtype, const void *d_A, const void *d_B, v
     a.alpha_re = alpha_re; a.alpha_im = alpha_im; a.beta_re = beta_re; a.beta_im = beta_im;
     a.conj_a = conj_a; a.conj_b = conj_b;
     constexpr int STAGES = 4;
-    const size_t smem = 2 * STAGES * 64 * 128 + STAGES * 8 + 1024;
-    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)batch);
+    const size_t smem = (size_t)STAGES * (64 + bn) * 128 + STAGES * 8 + 1024;
+    dim3 grid((unsigned)((N + bn - 1) / bn), (unsigned)((M + 63) / 64), (unsigned)batch);
     cudaStream_t st = (cudaStream_t)stream;
+#define APYIB_TMA_LAUNCH(CP, BNN)                                                                                  \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            APYIB_CUDA_CHECK(cudaFuncSetAttribute(contract_tma_kernel<CP, STAGES, BNN>,                            \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,                      \
+                                                  (int)(STAGES * (64 + BNN) * 128 + STAGES * 8 + 1024)));           \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        contract_tma_kernel<CP, STAGES, BNN><<<grid, 128, smem, st>>>(mapA, mapB, a);                               \
+    } while (0)
     if (dtype == APYIB_C128) {
-        APYIB_CUDA_CHECK(cudaFuncSetAttribute(contract_tma_kernel<true, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        contract_tma_kernel<true, STAGES><<<grid, 128, smem, st>>>(mapA, mapB, a);
+        if (bn == 48) APYIB_TMA_LAUNCH(true, 48); else APYIB_TMA_LAUNCH(true, 64);
     } else {
-        APYIB_CUDA_CHECK(cudaFuncSetAttribute(contract_tma_kernel<false, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        contract_tma_kernel<false, STAGES><<<grid, 128, smem, st>>>(mapA, mapB, a);
+        if (bn == 48) APYIB_TMA_LAUNCH(false, 48); else APYIB_TMA_LAUNCH(false, 64);
     }
+#undef APYIB_TMA_LAUNCH
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }

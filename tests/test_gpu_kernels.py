@@ -26,6 +26,14 @@ def _rand(rng, shape, cplx):
     ("mnlg,gs->mnls", [(6, 6, 6, 6), (6, 5)]),
     ("mk,kn->mn", [(1, 1), (1, 1)]),
     ("ia,jb->iajb", [(3, 4), (2, 5)]),
+    # skinny sides (16-wide tiles): T1 <-> T2 couplings, Fock-like terms, J/K builds, long-K split
+    ("sabcj,sic->sijab", [(3, 9, 9, 11, 5), (3, 5, 11)]),
+    ("sajbc,sijbc->sia", [(2, 30, 6, 30, 30), (2, 6, 6, 30, 30)]),
+    ("ski,skjab->sijab", [(3, 5, 5), (3, 5, 5, 9, 9)]),
+    ("sac,sijcb->sijab", [(2, 20, 20), (2, 4, 4, 20, 20)]),
+    ("ls,mnls->mn", [(40, 40), (12, 30, 40, 40)]),
+    ("mk,kn->mn", [(300, 5000), (5000, 7)]),
+    ("mk,kn->mn", [(1, 9000), (9000, 200)]),
 ])
 def test_contract_matches_einsum(spec, shapes, cplx):
     from apyib_b200.contraction import contract
