@@ -396,9 +396,17 @@ class _CISDOperator:
         self.Wovoo, self.Wvooo = blk("kbij", "kijb"), blk("akij", "kija")
         self.Woooo, self.Wvvvv = blk("klij"), blk("abcd")
 
-    def apply(self, t1, t2, r1, r2):
-        """r += (linear part of the CISD residual)(t1, t2)"""
+    def apply(self, t1, t2, r1, r2, half=False):
+        """r += (linear part of the CISD residual)(t1, t2).
+
+        half=True: r2 receives only h with (linear part) = h + P h, P = (i<->j, a<->b): the reference's 16
+        r_T2 terms (ci_wfn.py:467-482) are the ladder and the oooo term, which are P-symmetric, and seven
+        pairs (X, P X) -- :467/:468, :469/:470, :471/:472, :473/:474, :477/:480, :478/:481, :479/:482 -- by
+        <pq|rs> = <qp|sr> and t_ijab = t_jiba.  This is the half-sum-then-symmetrise form the reference
+        itself uses for CID (ci_wfn.py:83-92); the caller applies r2 = h + P h (apyib_symmetrize_ijab).
+        It halves the ring and coupling work of every iteration."""
         o = self
+        c = 0.5 if half else 1.0
         contract("sji,sja->sia", o.Foo, t1, r1, -1.0, 1.0)                  # :458
         contract("sab,sib->sia", o.Fvv, t1, r1, 1.0, 1.0)                   # :459
         contract("sjaib,sjb->sia", o.Lovvo, t1, r1, 1.0, 1.0)               # :460
@@ -407,33 +415,36 @@ class _CISDOperator:
         contract("sajbc,sijbc->sia", o.Lvovv, t2, r1, 1.0, 1.0)             # :462
         contract("skjib,skjab->sia", o.Looov, t2, r1, -1.0, 1.0)            # :463
         contract("sjabc,sic->sijab", o.Wvvvo, t1, r2, 1.0, 1.0)             # :467
-        contract("siabc,sjc->sijab", o.Wvvov, t1, r2, 1.0, 1.0)             # :468
         contract("skijb,ska->sijab", o.Wovoo, t1, r2, -1.0, 1.0)            # :469
-        contract("skija,skb->sijab", o.Wvooo, t1, r2, -1.0, 1.0)            # :470
         contract("sac,sijcb->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :471
-        contract("sbc,sijac->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :472
         contract("ski,skjab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :473
-        contract("skj,sikab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :474
-        contract("sklij,sklab->sijab", o.Woooo, t2, r2, 1.0, 1.0)           # :475
-        contract("sabcd,sijcd->sijab", o.Wvvvv, t2, r2, 1.0, 1.0)           # :476
+        contract("sklij,sklab->sijab", o.Woooo, t2, r2, c, 1.0)             # :475
+        contract("sabcd,sijcd->sijab", o.Wvvvv, t2, r2, c, 1.0)             # :476
         contract("skbjc,sikca->sijab", o.Wovvo, t2, r2, -1.0, 1.0)          # :477
         contract("skaic,skjcb->sijab", o.Lovvo, t2, r2, 1.0, 1.0)           # :478
         contract("skbic,skjac->sijab", o.Wovov, t2, r2, -1.0, 1.0)          # :479
+        if half:
+            return
+        contract("siabc,sjc->sijab", o.Wvvov, t1, r2, 1.0, 1.0)             # :468
+        contract("skija,skb->sijab", o.Wvooo, t1, r2, -1.0, 1.0)            # :470
+        contract("sbc,sijac->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :472
+        contract("skj,sikab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :474
         contract("skaic,skjbc->sijab", o.Wovvo, t2, r2, -1.0, 1.0)          # :480
         contract("skbjc,sikac->sijab", o.Lovvo, t2, r2, 1.0, 1.0)           # :481
         contract("skajc,sikcb->sijab", o.Wovov, t2, r2, -1.0, 1.0)          # :482
 
 
 def _solve_CISD(parameters, points, print_level):
-    """Spatial-orbital CISD (ci_wfn.py:420-574)."""
-    eng, O, V, bd = _make_engine(parameters, points, True, False)
-    n1 = eng.n1
+    """Spatial-orbital CISD (ci_wfn.py:420-574).  r_T2 is built as h + P h (see _CISDOperator.apply)."""
+    eng, O, V, bd = _make_engine(parameters, points, True, False, symmetrize=True)
+    n1, nb = eng.n1, eng.nb
     op = _CISDOperator([pt.F for pt in points], [pt.ERI for pt in points], O, V, bd, eng.dtype)
     eng.r0[:, :n1].copy_(op.Fai)
-    eng.r0[:, n1:].copy_(op.K)
+    for s in range(nb):                      # the engine keeps K/2 and symmetrises (ci_wfn.py:83 form)
+        check(lib.apyib_axpby(eng.code, eng.n2, 0.5, 0.0, ptr(op.K[s]), 0, 0.0, 0.0, ptr(eng.r0[s, n1:]), stream_ptr()))
     eng.w[:, :n1].copy_(op.w1)
     eng.w[:, n1:].copy_(op.w2)
-    residual = lambda _: op.apply(eng.t1(), eng.t2(), eng.t1(eng.r), eng.t2(eng.r))
+    residual = lambda rh: op.apply(eng.t1(), eng.t2(), eng.t1(eng.r), rh.view(nb, O, O, V, V), half=True)
     E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
     return eng, E
 
