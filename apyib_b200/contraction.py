@@ -88,16 +88,20 @@ def _plan(spec, A, B, out):
     # split-K for dot-product-like shapes: few output tiles, long K (one CTA would walk K alone).
     # Tile shapes mirror apyib_contract's choice (csrc/contract.cu): 16-wide tiles for skinny sides.
     cplx = A.dtype == torch.complex128
-    if N <= 16 and M > 16:
-        bm, bn = (64 if cplx else 128), 16
-    elif M <= 16 and N > 16:
-        bm, bn = 16, (64 if cplx else 128)
+    if M * N <= 16 and K >= 64:
+        # dot-product-like (contract_dot_kernel): one CTA of 256 threads per 16 Ki elements of k
+        ksplit = int(min(max(1, (K + 16383) // 16384), max(1, (4 * 148) // batch[0]), 65535 // batch[0]))
     else:
-        bm = bn = 32
-    tiles = ((M + bm - 1) // bm) * ((N + bn - 1) // bn) * batch[0]
-    ksplit = 1
-    if tiles < 2 * 148 and K >= 2048:
-        ksplit = int(min(max(1, (3 * 148) // tiles), (K + 511) // 512, 65535 // batch[0]))
+        if N <= 16 and M > 16:
+            bm, bn = (64 if cplx else 128), 16
+        elif M <= 16 and N > 16:
+            bm, bn = 16, (64 if cplx else 128)
+        else:
+            bm = bn = 32
+        tiles = ((M + bm - 1) // bm) * ((N + bn - 1) // bn) * batch[0]
+        ksplit = 1
+        if tiles < 2 * 148 and K >= 2048:
+            ksplit = int(min(max(1, (3 * 148) // tiles), (K + 511) // 512, 65535 // batch[0]))
     work = torch.empty(batch[0] * ksplit * M * N, dtype=A.dtype, device=A.device) if ksplit > 1 else None
     p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch, ksplit, work, tma)
     _table_cache[key] = p

@@ -268,6 +268,78 @@ contract_kernel(const ContractArgs p) {
     }
 }
 
+// Dot-product-like contractions (M*N <= 16 outputs: norms <t|t>, energy-like sums, the scalar and
+// 3-vector intermediates of the AAT assembly): a DMMA tile would be 99 % padding and one CTA would
+// walk K slab by slab at L2 latency (60 us for K = 840).  Here every thread strides over k, keeps
+// the M*N partial sums in registers and the block reduces them in fixed order.
+//   grid = (ksplit, batch); ksplit > 1: raw partials -> work[z][ks][m][n] (then splitk_reduce_kernel).
+constexpr int kDotThreads = 256;
+constexpr int kDotMaxOut = 16;
+template <bool CPLX>
+__global__ void __launch_bounds__(kDotThreads) contract_dot_kernel(const ContractArgs p) {
+    using T = typename elem_t<CPLX>::type;
+    const int z = blockIdx.y, ks = blockIdx.x;
+    if (p.active != nullptr && p.active[z] == 0) return;
+    const T *A = reinterpret_cast<const T *>(p.A) + (size_t)z * p.a_bs;
+    const T *B = reinterpret_cast<const T *>(p.B) + (size_t)z * p.b_bs;
+    const int M = (int)p.M, N = (int)p.N, MN = M * N;
+    const int64_t per = (p.K + p.ksplit - 1) / p.ksplit;
+    const int64_t k0 = (int64_t)ks * per;
+    int64_t k1 = k0 + per;
+    if (k1 > p.K) k1 = p.K;
+    double accr[kDotMaxOut], acci[CPLX ? kDotMaxOut : 1];
+#pragma unroll
+    for (int e = 0; e < kDotMaxOut; ++e) { accr[e] = 0.0; if (CPLX) acci[e] = 0.0; }
+    const double sa = p.conj_a ? -1.0 : 1.0, sb = p.conj_b ? -1.0 : 1.0;
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += kDotThreads) {
+        const int64_t ak = p.a_k[k], bk = p.b_k[k];
+#pragma unroll
+        for (int e = 0; e < kDotMaxOut; ++e) {
+            if (e >= MN) break;
+            const T av = A[p.a_m[e / N] + ak], bv = B[bk + p.b_n[e % N]];     // repeats hit L1
+            if constexpr (CPLX) {
+                const double ar = av.x, ai = sa * av.y, br = bv.x, bi = sb * bv.y;
+                accr[e] = fma(ar, br, fma(-ai, bi, accr[e]));
+                acci[e] = fma(ar, bi, fma(ai, br, acci[e]));
+            } else {
+                accr[e] = fma(av, bv, accr[e]);
+            }
+        }
+    }
+    // fixed-order block reduction, one output at a time (MN <= 16)
+    __shared__ double red[2][kDotThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
+    T *C = reinterpret_cast<T *>(p.C) + (size_t)z * p.c_bs;
+    T *W = reinterpret_cast<T *>(p.work) + ((size_t)z * p.ksplit + ks) * (size_t)MN;
+#pragma unroll
+    for (int e = 0; e < kDotMaxOut; ++e) {
+        if (e >= MN) break;
+        double xr = warp_sum(accr[e]), xi = CPLX ? warp_sum(acci[e]) : 0.0;
+        if (lane == 0) { red[0][w] = xr; red[1][w] = xi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            xr = 0.0; xi = 0.0;
+            for (int q = 0; q < kDotThreads / 32; ++q) { xr += red[0][q]; xi += red[1][q]; }
+            if (p.ksplit > 1) {
+                if constexpr (CPLX) W[e] = make_cplx(xr, xi); else W[e] = xr;
+            } else {
+                T *dst = C + p.c_m[e / N] + p.c_n[e % N];
+                if constexpr (CPLX) {
+                    double vr = p.alpha_re * xr - p.alpha_im * xi, vi = p.alpha_re * xi + p.alpha_im * xr;
+                    if (has_beta) { const cplx o = *dst; vr += p.beta_re * o.x - p.beta_im * o.y; vi += p.beta_re * o.y + p.beta_im * o.x; }
+                    *dst = make_cplx(vr, vi);
+                } else {
+                    double v = p.alpha_re * xr;
+                    if (has_beta) v += p.beta_re * (*dst);
+                    *dst = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // C[c_m[m] + c_n[n]] = alpha * sum_ks work[z][ks][m][n] + beta * C   (fixed summation order)
 template <bool CPLX>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ContractArgs p, int batch) {
@@ -355,6 +427,18 @@ extern "C" int apyib_contract(int dtype, const void *d_A, const void *d_B, void 
     a.a_kfast = a_kfast; a.b_kfast = b_kfast; a.conj_a = conj_a; a.conj_b = conj_b;
     a.ksplit = ksplit; a.work = d_work;
     cudaStream_t st = (cudaStream_t)stream;
+    if (M * N <= kDotMaxOut && K >= 64) {      // dot-product-like: strided-k reduction, no tiles
+        dim3 grid((unsigned)ksplit, (unsigned)batch);
+        if (dtype == APYIB_C128) contract_dot_kernel<true><<<grid, kDotThreads, 0, st>>>(a);
+        else contract_dot_kernel<false><<<grid, kDotThreads, 0, st>>>(a);
+        APYIB_LAUNCH_CHECK();
+        if (ksplit > 1) {
+            if (dtype == APYIB_C128) splitk_reduce_kernel<true><<<1, 256, 0, st>>>(a, batch);
+            else splitk_reduce_kernel<false><<<1, 256, 0, st>>>(a, batch);
+            APYIB_LAUNCH_CHECK();
+        }
+        return APYIB_OK;
+    }
     // Skinny shapes (T1 <-> T2 couplings of ci_wfn.py:457-470, Fock-like terms :471-474, J/K builds): one
     // side is <= 16 wide, the other operand is streamed once -> HBM-bound.  A 64-wide tile would spend
     // >= 75 % of its DMMAs and of its B-tile loads on padding, so these get N (or M) = 16 tiles.

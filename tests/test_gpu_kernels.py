@@ -34,6 +34,11 @@ def _rand(rng, shape, cplx):
     ("ls,mnls->mn", [(40, 40), (12, 30, 40, 40)]),
     ("mk,kn->mn", [(300, 5000), (5000, 7)]),
     ("mk,kn->mn", [(1, 9000), (9000, 200)]),
+    # dot-product-like (contract_dot_kernel), with and without split-K
+    ("sxia,sia->sx", [(2, 3, 5, 40), (2, 5, 40)]),
+    ("xk,qk->xq", [(1, 70000), (1, 70000)]),
+    ("xk,qk->xq", [(3, 900), (4, 900)]),
+    ("sxklcd,qklcd->sxq", [(2, 1, 4, 4, 9, 9), (3, 4, 4, 9, 9)]),
 ])
 def test_contract_matches_einsum(spec, shapes, cplx):
     from apyib_b200.contraction import contract
