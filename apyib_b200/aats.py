@@ -520,6 +520,8 @@ class AAT(object):
         def cached(name, S, bra, ket):
             key = ("blk", name, normalization)
             if key not in self._cache:
+                self._fill_family(name, normalization, A1, A2)
+            if key not in self._cache:
                 self._cache[key] = self._block(S, pick(A1, bra), A2[bra], pick(A1, ket), A2[ket])
             return self._cache[key]
 
@@ -553,6 +555,33 @@ class AAT(object):
         add(r4[2], -1, 0, 0, s0_N=N_mp[b], os_N=N_nn[a], d0=True, od=True)
         add(r4[3], +1, 0, 0, s0_N=N_mn[b], os_N=N_nn[a], d0=True, od=True)
         return I
+
+    def prefetch_rows(self, alphas):
+        """Hint: the tensor rows (nuclear coordinates alpha) this process is going to ask for.  The
+        overlap families that share their amplitude sets -- pu/nu[alpha] for all hinted alpha, up/un[beta]
+        for the three beta -- are then evaluated as ONE stack each (all launches batched over the stack)
+        instead of one overlap at a time.  Without a hint every row is assumed (single-process use)."""
+        self._rows = sorted(set(int(a) for a in alphas))
+
+    def _fill_family(self, name, normalization, A1, A2, max_stack=32):
+        if not isinstance(name, tuple) or name[0] not in ("pu", "nu", "up", "un"):
+            return
+        pick = lambda Am, k: None if Am is None else Am[k]
+        if name[0] in ("pu", "nu"):
+            rows = getattr(self, "_rows", None) or list(range(len(self.overlap_pu)))
+            if name[1] not in rows:
+                rows = [name[1]]
+            items = [(("pu", a), self.overlap_pu[a]) for a in rows] + [(("nu", a), self.overlap_nu[a]) for a in rows]
+            bra, ket = "tc", "dH"
+        else:
+            items = [(("up", b), self.overlap_up[b]) for b in range(3)] + [(("un", b), self.overlap_un[b]) for b in range(3)]
+            bra, ket = "dR", "t"
+        items = [it for it in items if ("blk", it[0], normalization) not in self._cache]
+        for i0 in range(0, len(items), max_stack):
+            chunk = items[i0:i0 + max_stack]
+            res = self._blocks([S for _, S in chunk], pick(A1, bra), A2[bra], pick(A1, ket), A2[ket])
+            for (nm, _), r in zip(chunk, res):
+                self._cache[("blk", nm, normalization)] = r
 
     def compute_spatial_aats(self, alpha, beta, normalization="full"):
         """Reference: aats.py:646-1055.  Returns Im(I)/(4 h_R h_B) for one (alpha, beta)."""

@@ -20,6 +20,8 @@ def timed(name):
     if TIMING is None or (TIMING_ONLY is not None and not name.startswith(TIMING_ONLY)):
         return contextlib.nullcontext()
     import torch
+    if torch.cuda.is_current_stream_capturing():      # launches recorded into a CUDA graph carry no events
+        return contextlib.nullcontext()
 
     @contextlib.contextmanager
     def _cm():

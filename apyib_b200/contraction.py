@@ -89,8 +89,8 @@ def _plan(spec, A, B, out):
     # Tile shapes mirror apyib_contract's choice (csrc/contract.cu): 16-wide tiles for skinny sides.
     cplx = A.dtype == torch.complex128
     if M * N <= 16 and K >= 64:
-        # dot-product-like (contract_dot_kernel): one CTA of 256 threads per 16 Ki elements of k
-        ksplit = int(min(max(1, (K + 16383) // 16384), max(1, (4 * 148) // batch[0]), 65535 // batch[0]))
+        # dot-product-like (contract_dot_kernel): one CTA of 256 threads per 4 Ki elements of k
+        ksplit = int(min(max(1, (K + 4095) // 4096), max(1, (4 * 148) // batch[0]), 65535 // batch[0]))
     else:
         if N <= 16 and M > 16:
             bm, bn = (64 if cplx else 128), 16

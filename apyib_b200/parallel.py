@@ -126,6 +126,7 @@ def compute_parallel_aats(parameters, nuc_pert_strength, mag_pert_strength, norm
     spatial = parameters['method'] in ('RHF', 'MP2', 'CID', 'CISD')
     fn = AATs.compute_spatial_aats if spatial else AATs.compute_SO_aats
     I = np.zeros((3 * natom, 3))
+    AATs.prefetch_rows([a for a, _ in owned_elements(3 * natom, rank, world)])
     for a, b in owned_elements(3 * natom, rank, world):
         I[a, b] = fn(a, b, normalization)
     I = gather_tensor(dist, I, world)

@@ -139,6 +139,7 @@ def gpu_step(work, rank=0, world=1, dist=None):
             [T("B", b, +1) for b in range(3)], [T("B", b, -1) for b in range(3)], H_R, H_B)
     from apyib_b200.parallel import owned_elements
     I = np.zeros((n3, 3))
+    A.prefetch_rows([a for a, _ in owned_elements(n3, rank, world)])
     for a, b in owned_elements(n3, rank, world):
         I[a, b] = A.compute_spatial_aats(a, b)
     if world > 1:
@@ -297,6 +298,8 @@ def main():
     import apyib_b200
     from apyib_b200 import _lib, device as dev
     apyib_b200.config.VERBOSE = False
+    if args.workload == "methyloxirane" and args.aat_algorithm == "lu":
+        args.aat_algorithm = "factorized"      # 2.5e10 16x16 LUs per overlap: only the closed forms are feasible
     apyib_b200.config.AAT_ALGORITHM = args.aat_algorithm
     config["aat_algorithm"] = args.aat_algorithm
     torch.cuda.set_device(local_rank)
@@ -342,7 +345,10 @@ def main():
     timed_steps(args.warmup, True)
     sampler.start()
     apyib_b200.config.TIMING = {}
-    apyib_b200.config.TIMING_ONLY = "det_matvec" if args.aat_algorithm == "lu" else "lemma_matvec"
+    # kernels timed live (CUDA events on the launching stream): the LU kernel, or for the closed-form
+    # algorithms the lemma kernel and the TMA-fed contractions (ladder); launches replayed from a CUDA
+    # graph cannot carry events, so for those only the eager first iteration of every solve is timed
+    apyib_b200.config.TIMING_ONLY = "det_matvec" if args.aat_algorithm == "lu" else ("lemma_matvec", "contract_tma[")
     _lib.LAUNCHES[0] = 0
     t_dev, I_dev = timed_steps(args.steps, True)
     launches = _lib.LAUNCHES[0] // max(args.steps, 1)
@@ -375,31 +381,62 @@ def main():
     except Exception:
         pass
     roof = None
+    traffic_tab = {}
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        pass
     if timing:
-        name = max(timing, key=lambda k: sum(a.elapsed_time(b) for a, b in timing[k]))
+        import re
+        tot_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in timing.items()}
+        if args.aat_algorithm == "lu":
+            name = max(tot_ms, key=tot_ms.get)
+        else:   # graph-replayed launches are not timed: rank by the duration of ONE launch instead of the sum
+            name = max(tot_ms, key=lambda k: tot_ms[k] / len(timing[k]))
         evs = timing[name]
         avg_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
         share = sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / t_dev
         n = wl["ndocc"]
+        extra = {}
         if name.startswith("det_matvec"):
             nrow, ncol = (int(x) for x in name.split(",")[1].rstrip("]").split("x"))
-            ndet, kern = nrow * ncol, "det_kernel<N=%d,fused> " % n
-        else:
+            ndet = nrow * ncol
+            kern = "det_tpm_kernel<N=%d,B=3> (fused LU + table x vector) " % n if n <= 12 else "det_kernel<N=%d,fused> " % n
+            # (8/3) n^3 real flop per substituted n x n complex LU -- all of them executed
+            flops = ndet * (8.0 / 3.0) * n ** 3
+            extra = {"determinants_per_s": ndet / (avg_ms * 1e-3)}
+            note = ("FP64 compute roofline (LU on the FP64 FMA pipe, every flop of the (8/3)n^3 count executed); "
+                    "peak = own DMMA/DFMA microbenchmark measured in this run (MEASURED_PEAKS.json holds bf16/HBM only, %s)"
+                    % peak_src)
+            tkey = "det_tpm_kernel"
+        elif name.startswith("lemma_matvec"):
             dims = name.split(",")[1]
             nrow, ncol = (int(x) for x in dims.split("x"))
             ndet = nrow * ncol * int(name.split("nS=")[1].rstrip("]"))
-            kern = "lemma_kernel<2,2,fused> "
-        # (8/3) n^3 real flop per substituted n x n complex determinant (algorithmic count)
-        flops = ndet * (8.0 / 3.0) * n ** 3
+            kern = "lemma_kernel<fused> "
+            flops = ndet * (8.0 / 3.0) * n ** 3
+            extra = {"determinants_per_s": ndet / (avg_ms * 1e-3)}
+            note = ("ALGORITHMIC flops of the reference's formulation ((8/3)n^3 per n x n LU, SURVEY 8d U3) / measured "
+                    "time; the lemma kernel executes far fewer flops than it is credited with, so frac is a speed-up "
+                    "measure, not a pipe utilisation; peak = own FP64 microbenchmark in this run (%s)" % peak_src)
+            tkey = "lemma_kernel"
+        else:
+            m = re.match(r"contract(_tma)?\[(f64|c128) (\d+)x(\d+)x(\d+) b(\d+)\]", name)
+            M_, N_, K_, nb_ = (int(m.group(i)) for i in (3, 4, 5, 6))
+            flops = (8.0 if m.group(2) == "c128" else 2.0) * M_ * N_ * K_ * nb_
+            kern = "contract_tma_kernel (DMMA, TMA-fed) " if m.group(1) else "contract_kernel (DMMA) "
+            note = ("FP64 tensor (DMMA) roofline, dense flop count of the reference's einsum (8 MNK complex / 2 MNK real "
+                    "per point); only the eager first iteration of each solve carries events (the rest replays from a "
+                    "CUDA graph), so share_of_step counts those launches only; peak = own DMMA microbenchmark in this "
+                    "run (%s)" % peak_src)
+            tkey = "contract_tma_kernel" if m.group(1) else "contract_kernel"
         ach = flops / (avg_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                "traffic": None, "kernel": kern + name, "launches_timed": len(evs), "avg_ms": avg_ms,
-                "share_of_step": share, "determinants_per_s": ndet / (avg_ms * 1e-3),
-                "note": "FP64 compute roofline; achieved = ALGORITHMIC flops of the reference's formulation "
-                        "((8/3)n^3 per substituted n x n LU, SURVEY 8d U3) / measured time; peak = own DMMA "
-                        "microbenchmark in this run (MEASURED_PEAKS.json has bf16/HBM only, %s). With "
-                        "--aat-algorithm lemma the kernel executes ~7x fewer flops than it is credited with "
-                        "here, so frac is a speed-up measure, not a pipe utilisation." % peak_src}
+                "traffic": traffic_tab.get(tkey, {}).get("dram_bytes_per_launch"), "kernel": kern + name,
+                "launches_timed": len(evs), "avg_ms": avg_ms, "share_of_step": share, "note": note}
+        roof.update(extra)
+        if tkey in traffic_tab:
+            roof["traffic_source"] = traffic_tab[tkey].get("source")
     # the algorithmic fast path (determinant lemma) on the same workload, as an extra leg
     alt = None
     if args.aat_algorithm == "lu" and world == 1:
