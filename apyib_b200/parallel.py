@@ -5,8 +5,9 @@ solves all finite-difference points serially first.  Here the unit of parallelis
 
   phase 1  the 6N+6 displaced / field points are partitioned over the ranks (one process per
            GPU, torch.distributed); every rank runs full, independent solves (no collective);
-  exchange one all_gather_object of the per-point (C, T_list) blobs -- every AAT element
-           needs the amplitudes of the unperturbed, R+-alpha and B+-beta points;
+  exchange one all_gather of the per-point (C, T_list) payloads as raw device bytes (NCCL over
+           NVLink; metadata only is pickled) -- every AAT element needs the amplitudes of the
+           unperturbed, R+-alpha and B+-beta points;
   phase 2  tensor rows alpha are partitioned over the ranks; each rank evaluates its rows with
            the fused determinant kernels;
   gather   final all-gather of the (3N, 3) float64 tensor (NCCL on GPUs, gloo in CPU tests).
@@ -48,15 +49,62 @@ def partition(items, costs, world):
 
 
 def exchange_points(dist, blob, world):
-    """The one exchange step of the path: every rank contributes {point: payload} for the points
-    it solved and receives the union (every AAT element needs all amplitudes, aats.py:690-711)."""
+    """The one exchange step of the path: every rank contributes {point: payload} for the points it
+    solved and receives the union (every AAT element needs all amplitudes, aats.py:690-711).
+
+    payload = (nested) list / tuple of numpy arrays, torch tensors and python scalars.  The array bytes
+    of a rank travel as ONE padded uint8 buffer through a single all_gather -- NCCL over NVLink between
+    device buffers on GPUs (amplitudes that are already device-resident never touch the host), gloo in
+    the CPU tests; only the few hundred bytes of metadata (point, dtypes, shapes, scalars) are pickled.
+    Arrays come back as device tensors under NCCL and as numpy arrays under gloo."""
     if dist is None or world == 1:
         return dict(blob)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, blob)
+    import torch
+    nccl = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    meta, chunks, nbytes = [], [], 0
+
+    def pack(x):
+        nonlocal nbytes
+        if isinstance(x, (list, tuple)):
+            return ("seq", type(x).__name__, [pack(y) for y in x])
+        if isinstance(x, np.ndarray) or torch.is_tensor(x):
+            t = (torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x.detach().contiguous()).to(dev)
+            raw = t.reshape(-1).view(torch.uint8)
+            pad = (-raw.numel()) % 16                      # keep every slice 16-byte aligned (complex128 views)
+            chunks.append(raw)
+            if pad:
+                chunks.append(torch.zeros(pad, dtype=torch.uint8, device=dev))
+            m = ("arr", str(t.dtype).replace("torch.", ""), tuple(t.shape), nbytes, raw.numel())
+            nbytes += raw.numel() + pad
+            return m
+        return ("obj", x)
+
+    for pt in sorted(blob):
+        meta.append((pt, pack(blob[pt])))
+    metas = [None] * world
+    dist.all_gather_object(metas, (meta, nbytes))
+    width = max(16, max(m[1] for m in metas))
+    buf = torch.zeros(width, dtype=torch.uint8, device=dev)
+    if chunks:
+        buf[:nbytes] = torch.cat(chunks)
+    parts = [torch.empty(width, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, buf)
+
+    def unpack(m, raw):
+        if m[0] == "seq":
+            seq = [unpack(y, raw) for y in m[2]]
+            return tuple(seq) if m[1] == "tuple" else seq
+        if m[0] == "arr":
+            _, dt, shape, off, n = m
+            t = raw[off:off + n].view(getattr(torch, dt)).reshape(shape)
+            return t if nccl else t.numpy()
+        return m[1]
+
     out = {}
-    for part in gathered:
-        out.update(part)
+    for r in range(world):
+        for pt, m in metas[r][0]:
+            out[pt] = blob[pt] if pt in blob else unpack(m, parts[r])
     return out
 
 

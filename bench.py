@@ -122,12 +122,8 @@ def gpu_step(work, rank=0, world=1, dist=None):
     mine = {p: [1, r[1], r[2]] for p, r in zip(my_pts, sols[1:])}
     if world > 1:
         # exchange step: every AAT element needs T(R+-alpha), T(B+-beta)  (aats.py:690-711)
-        blob = {p: [1] + [x.cpu().numpy() if hasattr(x, "cpu") else x for x in T[1:]] for p, T in mine.items()}
-        gathered = [None] * world
-        dist.all_gather_object(gathered, blob)
-        for part in gathered:
-            for p, T in part.items():
-                mine.setdefault(p, T)
+        from apyib_b200.parallel import exchange_points
+        mine = exchange_points(dist, mine, world)
     T = lambda k, i, s: mine[(k, i, s)]
     W = lambda k, i, s: work["pts"][(k, i, s)]
     A = AAT(par, w0, w0.C, w0.H.basis_set, T0,

@@ -32,11 +32,24 @@ def _worker(rank, world, port, natom, q):
         assert (r, w) == (rank, world)
         pts = aat_points(natom)
         own = partition(pts, [point_cost(p[0]) for p in pts], world)
-        mine = {p: (rank, np.full((2, 2), _code(p), dtype=np.float64)) for p, o in zip(pts, own) if o == rank}
+        # payload shaped like the real one: (C, [1, t1, t2]); real for R points, complex for B points,
+        # odd byte counts (alignment padding), a scalar 0 standing for "no singles"
+        def payload(p):
+            dt = np.complex128 if p[0] == "B" else np.float64
+            c = _code(p)
+            return (rank, np.full((3, 3), c, dtype=dt), [1, 0 if p[1] % 2 else np.arange(5, dtype=dt) * c,
+                                                        np.full((2, 2, 3, 3), c + 1, dtype=dt)])
+        mine = {p: payload(p) for p, o in zip(pts, own) if o == rank}
         allp = exchange_points(d, mine, world)
         assert sorted(allp) == sorted(pts)
-        for p, (src, arr) in allp.items():
-            assert src == own[pts.index(p)] and arr[0, 0] == _code(p)
+        for p, (src, C, T) in allp.items():
+            dt = np.complex128 if p[0] == "B" else np.float64
+            assert src == own[pts.index(p)] and C.dtype == dt and C.shape == (3, 3) and C[0, 0] == _code(p)
+            assert T[0] == 1 and T[2].shape == (2, 2, 3, 3) and T[2].dtype == dt and T[2][1, 1, 2, 2] == _code(p) + 1
+            if p[1] % 2:
+                assert isinstance(T[1], int) and T[1] == 0
+            else:
+                assert np.array_equal(np.asarray(T[1]), np.arange(5, dtype=dt) * _code(p))
         n3 = 3 * natom
         I = np.zeros((n3, 3))
         for a, b in owned_elements(n3, rank, world):
