@@ -58,6 +58,20 @@ class _Tables:
                 check(lib.apyib_det_index_lists(no, _i32_host(sub)[1] if sub is not None else None, cnt, nsub,
                                                 _i32_host(out)[1]))
             self.L.append(torch.from_numpy(out[:cnt].copy()).to(device()))
+        # column-side lists re-ordered for factorisation reuse in the thread-per-matrix LU kernel
+        # (substituted columns last, lists sorted; include/apyib_b200.h: apyib_det_sort_lists)
+        self.LS = [None, None, None]
+        if 2 <= no <= 12:
+            for k, cnt in ((1, self.n1), (2, self.n2)):
+                if not cnt:
+                    continue
+                src = self.L[k].cpu().numpy()
+                srt = np.zeros_like(src)
+                sign = np.zeros(cnt, dtype=np.float64)
+                idx = np.zeros(cnt, dtype=np.int32)
+                check(lib.apyib_det_sort_lists(no, _i32_host(src)[1], cnt, _i32_host(srt)[1],
+                                               sign.ctypes.data_as(C.POINTER(C.c_double)), _i32_host(idx)[1]))
+                self.LS[k] = tuple(torch.from_numpy(x.copy()).to(device()) for x in (srt, sign, idx))
         self.doubles_dev = torch.from_numpy(self.doubles.copy()).to(device())
         self.singles_dev = torch.from_numpy(self.singles.copy()).to(device())
 
@@ -69,15 +83,21 @@ class _Tables:
         return _tables[key]
 
 
-def _det_outer(S, n, rows, cols):
+def _det_outer(S, n, rows, cols, sorted_cols=None):
     out = empty((rows.shape[0], cols.shape[0]), _C128)
+    if sorted_cols is not None and config.LU_REUSE:
+        cs, sg, ix = sorted_cols
+        check(lib.apyib_det_outer_sorted(ptr(S), S.shape[0], n, ptr(rows), rows.shape[0], ptr(cs), ptr(sg), ptr(ix),
+                                         cs.shape[0], ptr(out), stream_ptr()))
+        return out
     check(lib.apyib_det_outer(ptr(S), S.shape[0], n, ptr(rows), rows.shape[0], ptr(cols), cols.shape[0], ptr(out),
                               stream_ptr()))
     return out
 
 
-def _det_matvec(S, n, rows, cols, Y):
+def _det_matvec(S, n, rows, cols, Y, sorted_cols=None):
     """Z[q, r] = sum_c det(S[rows[r], cols[c]]) Y[q, c]; any number of vectors (<= 4 per launch)."""
+    use_sorted = sorted_cols is not None and config.LU_REUSE
     Y = Y.contiguous()
     nq, nrow, ncol = Y.shape[0], rows.shape[0], cols.shape[0]
     Z = empty((nq, nrow), _C128)
@@ -85,8 +105,13 @@ def _det_matvec(S, n, rows, cols, Y):
         q1 = min(nq, q0 + 4)
         work = empty((int(lib.apyib_det_matvec_work_len(nrow, ncol, q1 - q0, n)),), _C128)
         with config.timed("det_matvec[n=%d,%dx%d]" % (n, nrow, ncol)):
-            check(lib.apyib_det_matvec(ptr(S), S.shape[0], n, ptr(rows), nrow, ptr(cols), ncol, ptr(Y[q0:q1]),
-                                       q1 - q0, ptr(Z[q0:q1]), ptr(work), stream_ptr()))
+            if use_sorted:
+                cs, sg, ix = sorted_cols
+                check(lib.apyib_det_matvec_sorted(ptr(S), S.shape[0], n, ptr(rows), nrow, ptr(cs), ptr(sg), ptr(ix), ncol,
+                                                  ptr(Y[q0:q1]), q1 - q0, ptr(Z[q0:q1]), ptr(work), stream_ptr()))
+            else:
+                check(lib.apyib_det_matvec(ptr(S), S.shape[0], n, ptr(rows), nrow, ptr(cols), ncol, ptr(Y[q0:q1]),
+                                           q1 - q0, ptr(Z[q0:q1]), ptr(work), stream_ptr()))
     return Z
 
 
@@ -351,10 +376,11 @@ class AAT(object):
             L = {0: R0, 1: R1, 2: R2}
 
             def outer(rk, ck):
-                return torch.stack([_det_outer(S[s], no, L[rk], L[ck]) for s in range(nS)])
+                return torch.stack([_det_outer(S[s], no, L[rk], L[ck], T.LS[ck]) for s in range(nS)])
 
             def matvec(rk, ck, Y, per_overlap):
-                return torch.stack([_det_matvec(S[s], no, L[rk], L[ck], Y[s] if per_overlap else Y) for s in range(nS)])
+                return torch.stack([_det_matvec(S[s], no, L[rk], L[ck], Y[s] if per_overlap else Y, T.LS[ck])
+                                    for s in range(nS)])
 
         dS = outer(0, 0).reshape(nS)                                     # det_S
         A = outer(1, 0).reshape(nS, o, nv)                               # ia_S

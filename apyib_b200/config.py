@@ -43,3 +43,8 @@ AAT_ALGORITHM = "lu"
 # Route k-contiguous 2-D operand contractions (ladder term, first AO->MO quarter transform) through the
 # TMA-fed kernel (csrc/contract_tma.cu); the gather kernel handles everything else.
 USE_TMA = True
+
+# LU path: feed the thread-per-matrix kernel column lists re-ordered for factorisation reuse (substituted
+# columns last, lists sorted -> consecutive determinants share their leading panels).  Same results; False
+# factorises every matrix from scratch (what bench.py's roofline line for the LU kernel is quoted on).
+LU_REUSE = True

@@ -8,6 +8,8 @@
 // (L1/L2-resident) MO overlap S and two index lists, so neither the substituted matrices nor,
 // in the fused variant, the determinant table (the reference's 8-index tensor, aats.py:575)
 // ever exist in memory.
+#include <algorithm>
+#include <vector>
 #include "common.cuh"
 
 namespace apyib {
@@ -187,8 +189,8 @@ static int launch_det(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, 
 
 // thread-per-matrix LU (dets_tpm.cu), n <= 12
 int launch_det_tpm(int n, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
-                   const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const cplx *Y, int ny,
-                   cplx *out, int outer);
+                   const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const double *csign,
+                   const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer);
 int tpm_total_warps(int n);
 constexpr int kTpmMaxN = 12;
 static int g_det_kernel = 0;   // 0 = thread-per-matrix for 2 <= n <= 12, sub-warp above; 1 = sub-warp always
@@ -214,8 +216,8 @@ extern "C" int apyib_det_set_kernel(int which) {
     return APYIB_OK;
 }
 
-extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
-                               const int32_t *d_cols, int64_t ncol, void *d_out, void *stream) {
+static int det_outer_impl(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow, const int32_t *d_cols,
+                          int64_t ncol, const double *d_csign, const int32_t *d_cindex, void *d_out, void *stream) {
     APYIB_REQUIRE(d_S && d_rows && d_cols && d_out, "null pointer");
     APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
     if (nrow == 0 || ncol == 0) return APYIB_OK;
@@ -223,7 +225,11 @@ extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_
         const int64_t nchunk = chunks_for((nrow + 31) / 32, ncol, tpm_total_warps(n), 1 << 20);
         const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
         return launch_det_tpm(n, (cudaStream_t)stream, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
-                              nchunk, nullptr, 0, (cplx *)d_out, 1);
+                              nchunk, d_csign, d_cindex, nullptr, 0, (cplx *)d_out, 1);
+    }
+    if (d_csign || d_cindex) {
+        set_error("sorted column lists need the thread-per-matrix LU kernel (2 <= n <= 12)");
+        return APYIB_ERR_UNSUPPORTED;
     }
     const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
@@ -257,10 +263,14 @@ extern "C" int64_t apyib_det_matvec_work_len(int64_t nrow, int64_t ncol, int ny,
     return apyib_det_matvec_nchunk(nrow, ncol, n) * ny * nrow;
 }
 
-extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
-                                const int32_t *d_cols, int64_t ncol, const void *d_Y, int ny, void *d_Z,
-                                void *d_work, void *stream) {
+static int det_matvec_impl(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow, const int32_t *d_cols,
+                           int64_t ncol, const double *d_csign, const int32_t *d_cindex, const void *d_Y, int ny,
+                           void *d_Z, void *d_work, void *stream) {
     APYIB_REQUIRE(d_S && d_rows && d_cols && d_Y && d_Z && d_work, "null pointer");
+    if ((d_csign || d_cindex) && !use_tpm(n)) {
+        set_error("sorted column lists need the thread-per-matrix LU kernel (2 <= n <= 12)");
+        return APYIB_ERR_UNSUPPORTED;
+    }
     APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
     APYIB_REQUIRE(ny >= 1 && ny <= 4, "1 <= ny <= 4");
     if (nrow == 0) return APYIB_OK;
@@ -275,7 +285,7 @@ extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d
     const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
     dim3 grid((unsigned)rb, (unsigned)nchunk);
     int rc = use_tpm(n) ? launch_det_tpm(n, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len, nchunk,
-                                         (const cplx *)d_Y, ny, (cplx *)d_work, 0)
+                                         d_csign, d_cindex, (const cplx *)d_Y, ny, (cplx *)d_work, 0)
                         : launch_det<false>(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
                                (const cplx *)d_Y, ny, (cplx *)d_work);
     if (rc != APYIB_OK) return rc;
@@ -284,6 +294,67 @@ extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d
     if (b > 148 * 8) b = 148 * 8;
     chunk_reduce_kernel<<<(unsigned)b, 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
     APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_det_outer(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                               const int32_t *d_cols, int64_t ncol, void *d_out, void *stream) {
+    return det_outer_impl(d_S, ns, n, d_rows, nrow, d_cols, ncol, nullptr, nullptr, d_out, stream);
+}
+
+extern "C" int apyib_det_matvec(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                                const int32_t *d_cols, int64_t ncol, const void *d_Y, int ny, void *d_Z,
+                                void *d_work, void *stream) {
+    return det_matvec_impl(d_S, ns, n, d_rows, nrow, d_cols, ncol, nullptr, nullptr, d_Y, ny, d_Z, d_work, stream);
+}
+
+extern "C" int apyib_det_outer_sorted(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                                      const int32_t *d_cols, const double *d_col_sign, const int32_t *d_col_index,
+                                      int64_t ncol, void *d_out, void *stream) {
+    APYIB_REQUIRE(d_col_sign && d_col_index, "null pointer");
+    return det_outer_impl(d_S, ns, n, d_rows, nrow, d_cols, ncol, d_col_sign, d_col_index, d_out, stream);
+}
+
+extern "C" int apyib_det_matvec_sorted(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                                       const int32_t *d_cols, const double *d_col_sign, const int32_t *d_col_index,
+                                       int64_t ncol, const void *d_Y, int ny, void *d_Z, void *d_work, void *stream) {
+    APYIB_REQUIRE(d_col_sign && d_col_index, "null pointer");
+    return det_matvec_impl(d_S, ns, n, d_rows, nrow, d_cols, ncol, d_col_sign, d_col_index, d_Y, ny, d_Z, d_work, stream);
+}
+
+// Re-orders column index lists for factorisation reuse (host): inside every list the substituted entries
+// (value >= n) move to the end, order preserved, and the lists are sorted lexicographically, so consecutive
+// lists share the longest possible leading part.  sign[c] = parity of the in-list move (det of the original
+// list = sign * det of the re-ordered one); index[c] = position of sorted list c in the input enumeration.
+extern "C" int apyib_det_sort_lists(int n, const int32_t *h_lists, int64_t count, int32_t *h_sorted, double *h_sign,
+                                    int32_t *h_index) {
+    APYIB_REQUIRE(n >= 1 && count >= 0 && count < 2147483647LL && (count == 0 || (h_lists && h_sorted && h_sign && h_index)),
+                  "arguments");
+    std::vector<int32_t> tmp((size_t)count * n);
+    std::vector<double> sg((size_t)count);
+    for (int64_t q = 0; q < count; ++q) {
+        const int32_t *in = h_lists + q * n;
+        int32_t *o = tmp.data() + q * n;
+        int w = 0, inversions = 0, nsub = 0;
+        for (int j = 0; j < n; ++j) {
+            if (in[j] < n) { o[w++] = in[j]; inversions += nsub; } else { ++nsub; }
+        }
+        for (int j = 0; j < n; ++j)
+            if (in[j] >= n) o[w++] = in[j];
+        sg[q] = (inversions & 1) ? -1.0 : 1.0;
+    }
+    std::vector<int32_t> order((size_t)count);
+    for (int64_t q = 0; q < count; ++q) order[q] = (int32_t)q;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return std::lexicographical_compare(tmp.begin() + (size_t)a * n, tmp.begin() + (size_t)(a + 1) * n,
+                                            tmp.begin() + (size_t)b * n, tmp.begin() + (size_t)(b + 1) * n);
+    });
+    for (int64_t c = 0; c < count; ++c) {
+        const int32_t q = order[c];
+        for (int j = 0; j < n; ++j) h_sorted[c * n + j] = tmp[(size_t)q * n + j];
+        h_sign[c] = sg[q];
+        h_index[c] = q;
+    }
     return APYIB_OK;
 }
 

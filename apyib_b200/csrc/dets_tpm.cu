@@ -53,6 +53,7 @@ template <int N, int B, bool SSM>
 __global__ void __launch_bounds__(tpm_threads(N), 1)
 det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ rows, int64_t nrow,
                const int32_t *__restrict__ cols, int64_t ncol, int64_t chunk_len, int64_t nchunk,
+               const double *__restrict__ csign, const int32_t *__restrict__ cindex,
                const cplx *__restrict__ Y, int ny, cplx *__restrict__ out, int outer) {
     using cfg = tpm_cfg<N, B>;
     constexpr int T = tpm_threads(N);
@@ -87,16 +88,31 @@ det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ r
 #pragma unroll
         for (int q = 0; q < NYMAX; ++q) z[q] = make_cplx(0.0, 0.0);
 
+        double pdx = 1.0, pdy = 0.0;          // determinant prefix after the leading panels (factorisation reuse)
+        bool pneg = false;
         for (int64_t c = c0; c < c1; ++c) {
             const int32_t *cl = cols + c * N;
-            if (cfg::NP > 1) {
+            // Left-looking LU touches column j only after columns < j: if this column list starts with the
+            // same NL columns as the previous one (same thread -> same rows), the leading panels, their L
+            // columns in shared memory, the row permutation and the partial determinant are all still valid
+            // and only the last panel is factorised.  Callers order the column lists accordingly
+            // (substituted columns last, lists sorted; apyib_det_sort_lists).
+            bool reuse = false;
+            if (cfg::NL > 0 && c > c0) {
+                reuse = true;
+#pragma unroll
+                for (int j = 0; j < cfg::NL; ++j) reuse = reuse && (__ldg(&cl[j]) == __ldg(&cl[j - N]));
+            }
+            if (cfg::NP > 1 && !reuse) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) rpsm[i * T] = rowoff[i];
             }
-            double detx = 1.0, dety = 0.0;
-            bool neg = false;
+            double detx = reuse ? pdx : 1.0, dety = reuse ? pdy : 0.0;
+            bool neg = reuse ? pneg : false;
 #pragma unroll
             for (int jb = 0; jb < N; jb += B) {
+                const bool last_panel = (jb + B >= N);
+                if (!last_panel && reuse) continue;
                 const int bw = (N - jb < B) ? (N - jb) : B;
                 cplx a[B][N];
                 // ---- form the panel columns from S (row order = current permutation) ----
@@ -193,8 +209,8 @@ det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ r
                         };
                         if (j + 1 < N) {
                             if (__any_sync(0xffffffffu, sw)) {
-                                if (sw) {
-                                    if (cfg::NP > 1) {
+                                if (sw && !last_panel) {       // (nobody reads L or the row list after the last panel)
+                                    {
                                         const int t0 = rpsm[j * T], t1 = rpsm[p * T];
                                         rpsm[j * T] = t1;
                                         rpsm[p * T] = t0;
@@ -216,8 +232,8 @@ det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ r
                                             Lsm[(cfg::loff(k) + p - k - 1) * T] = lj[k];
                                         }
                                     }
-                                    neg = !neg;
                                 }
+                                neg = neg != sw;
                                 step(std::true_type{});
                             } else {
                                 step(std::false_type{});
@@ -230,14 +246,17 @@ det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ r
                         }
                     }
                 }
+                if (cfg::NL > 0 && jb + B == cfg::NL) { pdx = detx; pdy = dety; pneg = neg; }
             }
-            const cplx d = make_cplx(neg ? -detx : detx, neg ? -dety : dety);
+            const double sg = (csign ? __ldg(&csign[c]) : 1.0) * (neg ? -1.0 : 1.0);
+            const cplx d = make_cplx(sg * detx, sg * dety);
+            const int64_t cc = cindex ? (int64_t)__ldg(&cindex[c]) : c;
             if (outer) {
-                if (rvalid) out[r * ncol + c] = d;
+                if (rvalid) out[r * ncol + cc] = d;
             } else {
 #pragma unroll
                 for (int q = 0; q < NYMAX; ++q)
-                    if (q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
+                    if (q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + cc]);
             }
         }
         if (!outer && rvalid) {
@@ -250,8 +269,8 @@ det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ r
 
 template <int N>
 static int launch_tpm_n(cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
-                        const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const cplx *Y, int ny,
-                        cplx *out, int outer) {
+                        const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const double *csign,
+                        const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer) {
     constexpr int B = tpm_panel(N);
     constexpr int T = tpm_threads(N);
     using cfg = tpm_cfg<N, B>;
@@ -268,7 +287,8 @@ static int launch_tpm_n(cudaStream_t st, const cplx *S, int ns, const int32_t *r
         APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTpmSmemMax));
         attr_done[ssm] = true;
     }
-    kern<<<(unsigned)blocks, T, smem, st>>>(S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, Y, ny, out, outer);
+    kern<<<(unsigned)blocks, T, smem, st>>>(S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, csign, cindex, Y, ny, out,
+                                            outer);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
@@ -278,11 +298,11 @@ static int launch_tpm_n(cudaStream_t st, const cplx *S, int ns, const int32_t *r
 int tpm_total_warps(int n) { return 148 * (tpm_threads(n) / 32); }
 
 int launch_det_tpm(int n, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
-                   const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const cplx *Y, int ny,
-                   cplx *out, int outer) {
+                   const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const double *csign,
+                   const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer) {
     switch (n) {
 #define APYIB_TPM_CASE(NN) \
-    case NN: return launch_tpm_n<NN>(st, S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, Y, ny, out, outer);
+    case NN: return launch_tpm_n<NN>(st, S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, csign, cindex, Y, ny, out, outer);
         APYIB_TPM_CASE(2) APYIB_TPM_CASE(3) APYIB_TPM_CASE(4) APYIB_TPM_CASE(5) APYIB_TPM_CASE(6) APYIB_TPM_CASE(7)
         APYIB_TPM_CASE(8) APYIB_TPM_CASE(9) APYIB_TPM_CASE(10) APYIB_TPM_CASE(11) APYIB_TPM_CASE(12)
 #undef APYIB_TPM_CASE

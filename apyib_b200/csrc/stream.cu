@@ -29,24 +29,46 @@ __device__ __forceinline__ T fetch4(const T *src, const int64_t (&sd)[4], int sp
     return src[((p0 * sd[1] + p1) * sd[2] + p2) * sd[3] + p3];
 }
 
-template <typename T> __global__ void __launch_bounds__(kThreads) gather4_kernel(const T *src, T *out, Gather4Args g) {
-    const int64_t total = g.od[0] * g.od[1] * g.od[2] * g.od[3];
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        int64_t x[4], r = idx;
-        x[3] = r % g.od[3]; r /= g.od[3];
-        x[2] = r % g.od[2]; r /= g.od[2];
-        x[1] = r % g.od[1]; r /= g.od[1];
-        x[0] = r;
-        T v = fetch4<T>(src, g.sd, g.spin, g.st1[0] + x[g.perm1[0]], g.st1[1] + x[g.perm1[1]],
-                        g.st1[2] + x[g.perm1[2]], g.st1[3] + x[g.perm1[3]]);
-        v = g.c1 * v;
-        if (g.c2 != 0.0) {
-            T w = fetch4<T>(src, g.sd, g.spin, g.st2[0] + x[g.perm2[0]], g.st2[1] + x[g.perm2[1]],
-                            g.st2[2] + x[g.perm2[2]], g.st2[3] + x[g.perm2[3]]);
-            v = v + g.c2 * w;
+// One CTA per leading-index group (x0, x1[, x2]); the trailing `inner` output elements are walked with
+// 32-bit index arithmetic and four independent elements in flight per thread.  (The first version
+// decomposed a flat int64 index per element: three 64-bit div/mod pairs per output made the one-off block
+// extraction run at 31 % of HBM peak.)
+template <typename T> __global__ void __launch_bounds__(kThreads) gather4_kernel(const T *__restrict__ src, T *__restrict__ out, Gather4Args g, int lead) {
+    const int64_t nouter = (lead == 3) ? g.od[0] * g.od[1] * g.od[2] : g.od[0] * g.od[1];
+    const unsigned od3 = (unsigned)g.od[3];
+    const unsigned inner = (lead == 3) ? od3 : (unsigned)(g.od[2] * g.od[3]);
+    const bool two = g.c2 != 0.0;
+    for (int64_t outer = blockIdx.x; outer < nouter; outer += gridDim.x) {
+        int64_t x[4];
+        int64_t r = outer;
+        if (lead == 3) { x[2] = r % g.od[2]; r /= g.od[2]; } else { x[2] = 0; }
+        x[1] = r % g.od[1];
+        x[0] = r / g.od[1];
+        T *dst = out + outer * inner;
+        for (unsigned e0 = threadIdx.x; e0 < inner; e0 += 4 * kThreads) {
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned e = e0 + u * kThreads;
+                if (e >= inner) break;
+                int64_t y[4] = {x[0], x[1], x[2], 0};
+                if (lead == 3) { y[3] = e; } else { const unsigned q = e / od3; y[2] = q; y[3] = e - q * od3; }
+                T a = fetch4<T>(src, g.sd, g.spin, g.st1[0] + y[g.perm1[0]], g.st1[1] + y[g.perm1[1]],
+                                g.st1[2] + y[g.perm1[2]], g.st1[3] + y[g.perm1[3]]);
+                a = g.c1 * a;
+                if (two) {
+                    const T w = fetch4<T>(src, g.sd, g.spin, g.st2[0] + y[g.perm2[0]], g.st2[1] + y[g.perm2[1]],
+                                          g.st2[2] + y[g.perm2[2]], g.st2[3] + y[g.perm2[3]]);
+                    a = a + g.c2 * w;
+                }
+                v[u] = a;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned e = e0 + u * kThreads;
+                if (e < inner) dst[e] = v[u];
+            }
         }
-        out[idx] = v;
     }
 }
 
@@ -87,7 +109,11 @@ constexpr int kMp2Threads = 256;
 // SO_ENERGY: accumulate the spin-orbital energy 1/4 sum <IJ||AB> t_IJAB instead, spin-summed analytically
 // and relabelled so that all reads stay contiguous:
 //     E_SO = sum_ijab [ t_ijab ((ia|jb) - 1/2 (ja|ib)) + t_ijba ((ja|ib) - 1/2 (ia|jb)) ]
-template <typename T, bool SO_ENERGY>
+// HERM: the caller guarantees (pq|rs) = conj((qp|sr)) -- true for every MO tensor transformed from real
+// AO integrals (utils.py:274-277) -- so (ia|jb) = conj((ai|bj)) and (ja|ib) = conj((bi|aj)) are already in
+// the shared-memory tiles and the energy needs no second pass over the integrals: 2 reads + 1 write per
+// amplitude, the algorithmic minimum of SURVEY 8(d) U2.
+template <typename T, bool SO_ENERGY, bool HERM>
 __global__ void __launch_bounds__(kMp2Threads)
 mp2_spatial_kernel(const T *__restrict__ eri, int64_t n, int64_t o, const double *__restrict__ eps, T *__restrict__ t2,
                    double *E_out, double *partials, int bt) {
@@ -143,7 +169,7 @@ mp2_spatial_kernel(const T *__restrict__ eri, int64_t n, int64_t o, const double
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {                                  // integral loads first (MLP)
                         bb[u] = b; jj[u] = j;
-                        if (e0 + u * kMp2Threads < total) {
+                        if (!HERM && e0 + u * kMp2Threads < total) {
                             g[u] = rowg[(int64_t)j * n + b0 + b];                  // (ia|jb), contiguous in b
                             if (SO_ENERGY) g2[u] = rowh[(int64_t)j * n * n * n + b0 + b];   // (ja|ib)
                         }
@@ -155,8 +181,10 @@ mp2_spatial_kernel(const T *__restrict__ eri, int64_t n, int64_t o, const double
                         if (e0 + u * kMp2Threads >= total) continue;
                         const int64_t B = b0 + bb[u];
                         const double rD = 1.0 / (Dia + eps[jj[u]] - eps[o + B]);
-                        const T t = rD * s1[bb[u] * ld + jj[u]];
-                        const T tx = rD * s2[bb[u] * ld + jj[u]];
+                        const T k1 = s1[bb[u] * ld + jj[u]], k2 = s2[bb[u] * ld + jj[u]];
+                        if (HERM) { g[u] = scalar<T>::cj(k1); g2[u] = scalar<T>::cj(k2); }
+                        const T t = rD * k1;
+                        const T tx = rD * k2;
                         t2[((i * o + jj[u]) * v + a) * v + B] = t;
                         T ev;
                         if (SO_ENERGY) ev = t * (g[u] - 0.5 * g2[u]) + tx * (g2[u] - 0.5 * g[u]);
@@ -590,10 +618,15 @@ extern "C" int apyib_gather4(int dtype, const void *d_src, const int64_t src_dim
     g.c1 = c1; g.c2 = c2; g.spin = spin;
     if (total == 0) return APYIB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    APYIB_REQUIRE(out_dims[2] * out_dims[3] < 2147483647LL, "inner block too large");
+    // leading-index groups: (x0, x1) if that already gives >= 2 CTAs per SM, else (x0, x1, x2)
+    const int lead = (out_dims[0] * out_dims[1] >= 2 * 148 || out_dims[2] == 1) ? 2 : 3;
+    const int64_t nouter = lead == 3 ? out_dims[0] * out_dims[1] * out_dims[2] : out_dims[0] * out_dims[1];
+    const unsigned gridx = (unsigned)(nouter < 148 * 16 ? nouter : 148 * 16);
     if (dtype == APYIB_C128)
-        gather4_kernel<cplx><<<stream_grid(total), kThreads, 0, st>>>((const cplx *)d_src, (cplx *)d_out, g);
+        gather4_kernel<cplx><<<gridx, kThreads, 0, st>>>((const cplx *)d_src, (cplx *)d_out, g, lead);
     else
-        gather4_kernel<double><<<stream_grid(total), kThreads, 0, st>>>((const double *)d_src, (double *)d_out, g);
+        gather4_kernel<double><<<gridx, kThreads, 0, st>>>((const double *)d_src, (double *)d_out, g, lead);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
@@ -629,6 +662,9 @@ extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, i
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(d_eri_mo && d_eps && d_t2 && d_E && d_partials, "null pointer");
     APYIB_REQUIRE(n > 0 && o >= 0 && o <= n, "sizes");
+    APYIB_REQUIRE(spin_orbital >= 0 && spin_orbital <= 3, "flags: bit 0 = spin-orbital, bit 1 = Hermitian integrals");
+    const bool hermitian = (spin_orbital & 2) != 0;
+    spin_orbital &= 1;
     APYIB_REQUIRE(!spin_orbital || d_work, "spin-orbital MP2 needs a workspace of o*o*v*v elements");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t v = n - o;
@@ -648,12 +684,16 @@ extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, i
     const int64_t work = o * v;
     int grid = (int)(work < kReduceMaxBlocks ? work : kReduceMaxBlocks);
     void *t_spatial = spin_orbital ? d_work : d_t2;
+#define MP2_LAUNCH2(T, SOE, HM)                                                                                   \
+    do {                                                                                                          \
+        APYIB_CUDA_CHECK(cudaFuncSetAttribute(mp2_spatial_kernel<T, SOE, HM>,                                      \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));          \
+        mp2_spatial_kernel<T, SOE, HM><<<grid, kMp2Threads, smem, st>>>((const T *)d_eri_mo, n, o, d_eps,          \
+                                                                        (T *)t_spatial, d_E, d_partials, bt);     \
+    } while (0)
 #define MP2_LAUNCH(T, SOE)                                                                                        \
     do {                                                                                                          \
-        APYIB_CUDA_CHECK(cudaFuncSetAttribute(mp2_spatial_kernel<T, SOE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              200 * 1024));                                                       \
-        mp2_spatial_kernel<T, SOE><<<grid, kMp2Threads, smem, st>>>((const T *)d_eri_mo, n, o, d_eps, (T *)t_spatial, \
-                                                                    d_E, d_partials, bt);                         \
+        if (hermitian) MP2_LAUNCH2(T, SOE, true); else MP2_LAUNCH2(T, SOE, false);                                \
     } while (0)
     if (dtype == APYIB_C128) {
         if (spin_orbital) MP2_LAUNCH(cplx, true); else MP2_LAUNCH(cplx, false);
@@ -661,6 +701,7 @@ extern "C" int apyib_mp2_t2_energy(int dtype, const void *d_eri_mo, int64_t n, i
         if (spin_orbital) MP2_LAUNCH(double, true); else MP2_LAUNCH(double, false);
     }
 #undef MP2_LAUNCH
+#undef MP2_LAUNCH2
     APYIB_LAUNCH_CHECK();
     if (spin_orbital) {
         const int64_t pairs = 4 * o * o;

@@ -39,7 +39,8 @@ class mp2_wfn(object):
         t2 = empty((O, O, V, V), ERI_MO.dtype)
         E = zeros((2,), torch.float64)
         work = empty((o, o, n - o, n - o), ERI_MO.dtype) if spin_orbital else None
-        check(lib.apyib_mp2_t2_energy(dtype_code(ERI_MO), ptr(ERI_MO), n, o, ptr(eps), int(spin_orbital),
+        # bit 1: ERI_MO comes from compute_ERI_MO on real AO integrals, hence (pq|rs) = conj((qp|sr))
+        check(lib.apyib_mp2_t2_energy(dtype_code(ERI_MO), ptr(ERI_MO), n, o, ptr(eps), int(spin_orbital) | 2,
                                       ptr(t2), ptr(E), ptr(reduce_scratch()), ptr(work), stream_ptr()))
         e = to_host(E)
         if ERI_MO.dtype == torch.complex128:

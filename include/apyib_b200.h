@@ -114,6 +114,9 @@ int apyib_gather2(int dtype, const void *d_src, const int64_t src_dims[2], int s
  * spatial:  t2[i,j,a,b] = (ai|bj)/D_ijab ,  E = sum (2(ia|jb) - (ib|ja)) t2
  * spin_orbital: same on the spin-blocked, antisymmetrised integrals,
  *           t2 = <ab||ij>/D , E = 1/4 sum <ij||ab> t2   (O = 2o, V = 2v)
+ * spin_orbital is a flag word: bit 0 = spin-orbital equations, bit 1 = the caller guarantees
+ * (pq|rs) = conj((qp|sr)) (any MO tensor transformed from real AO integrals, utils.py:274-277);
+ * the energy then reuses the integrals already read for t2 (2 reads + 1 write per amplitude).
  * d_eps: n orbital energies (double).  d_E: 2 doubles (re, im), written.
  * d_work: spin_orbital only, scratch of o*o*v*v elements (the spatial amplitudes).
  * d_partials: zero-initialised scratch of apyib_reduce_scratch_len() doubles.         */
@@ -207,6 +210,22 @@ int apyib_det_matvec(const void *d_S, int ns, int n,
                      const int32_t *d_cols, int64_t ncol,
                      const void *d_Y, int ny, void *d_Z, void *d_work, void *stream);
 int64_t apyib_det_matvec_work_len(int64_t nrow, int64_t ncol, int ny, int n);
+/* Factorisation reuse.  The thread-per-matrix kernel runs a left-looking LU, which touches column j only
+ * after the columns before it: two consecutive column lists that start with the same columns share those
+ * panels, their L factors, the pivoting and the partial determinant, and only the last panel is redone.
+ * apyib_det_sort_lists (host) re-orders an enumeration for that: inside every list the substituted
+ * entries (value >= n) go last, the lists are sorted; sign[c] = +-1 relates the determinants and index[c]
+ * is the position in the original enumeration.  The *_sorted entry points take the re-ordered lists and
+ * still index d_Y / d_out by the ORIGINAL enumeration, so results equal apyib_det_outer / apyib_det_matvec
+ * (same partial-pivoting LU of a column-permuted matrix).  2 <= n <= 12 only (APYIB_ERR_UNSUPPORTED).   */
+int apyib_det_sort_lists(int n, const int32_t *h_lists, int64_t count, int32_t *h_sorted, double *h_sign,
+                         int32_t *h_index);
+int apyib_det_outer_sorted(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                           const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
+                           int64_t ncol, void *d_out, void *stream);
+int apyib_det_matvec_sorted(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                            const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
+                            int64_t ncol, const void *d_Y, int ny, void *d_Z, void *d_work, void *stream);
 /* Which LU kernel apyib_det_outer / apyib_det_matvec launch: 0 (default) = one thread per matrix,
  * column panels in registers + L in shared memory, for 2 <= n <= 12 and the sub-warp kernel above
  * that; 1 = the sub-warp (one lane per row) kernel for every n.  Same results either way.       */

@@ -182,6 +182,43 @@ def test_det_matvec_vs_numpy(n, det_kernel):
     assert np.abs(to_host(Z) - want).max() < 1e-11 * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize("n,nv", [(4, 5), (7, 6), (9, 5), (12, 4)])
+def test_det_sorted_lists_reuse_matches_plain(n, nv):
+    """Factorisation reuse: sorted column lists (apyib_det_sort_lists) through the *_sorted entry points give
+    the tables / products of the plain entry points, and both match numpy; generic O(1) overlap."""
+    from apyib_b200._lib import lib, check
+    from apyib_b200.aats import _Tables, _det_matvec, _det_outer
+    from apyib_b200.device import to_device, to_host
+    import apyib_b200
+    rng = np.random.default_rng(300 + n)
+    ns = n + nv
+    S = np.eye(ns) + 0.3 * (rng.standard_normal((ns, ns)) + 1j * rng.standard_normal((ns, ns)))
+    T = _Tables.get(n, 0, nv)
+    dS = to_device(S, torch.complex128)
+    assert T.LS[1] is not None and T.LS[2] is not None
+    # the sort is a permutation of the enumeration and only moves substituted entries to the end
+    cs, sg, ix = (x.cpu().numpy() for x in T.LS[2])
+    assert sorted(ix.tolist()) == list(range(T.n2)) and set(np.unique(sg)) <= {-1.0, 1.0}
+    assert (np.sort(cs, axis=1) == np.sort(T.L[2].cpu().numpy()[ix], axis=1)).all() and (cs[:, :n - 2] < n).all()
+    for ck in (1, 2):
+        rows, cols = T.L[2 if ck == 1 else 1], T.L[ck]
+        want = np.linalg.det(S[rows.cpu().numpy()[:, None, :, None], cols.cpu().numpy()[None, :, None, :]])
+        got_plain = to_host(_det_outer(dS, n, rows, cols))
+        got_sorted = to_host(_det_outer(dS, n, rows, cols, T.LS[ck]))
+        scale = max(1.0, np.abs(want).max())
+        assert np.abs(got_plain - want).max() < 1e-11 * scale
+        assert np.abs(got_sorted - want).max() < 1e-11 * scale
+        Y = rng.standard_normal((3, cols.shape[0])) + 1j * rng.standard_normal((3, cols.shape[0]))
+        Z = to_host(_det_matvec(dS, n, rows, cols, to_device(Y, torch.complex128), T.LS[ck]))
+        assert np.abs(Z - Y @ want.T).max() < 1e-10 * max(1.0, np.abs(Y @ want.T).max())
+    old = apyib_b200.config.LU_REUSE
+    apyib_b200.config.LU_REUSE = False
+    try:
+        assert np.abs(to_host(_det_outer(dS, n, T.L[1], T.L[2], T.LS[2])) - to_host(_det_outer(dS, n, T.L[1], T.L[2]))).max() == 0
+    finally:
+        apyib_b200.config.LU_REUSE = old
+
+
 def test_det_kernels_agree_on_fd_overlap():
     """Finite-difference-like overlap (I + O(h)): the thread-per-matrix and the sub-warp LU give the
     same doubles x doubles products to rounding (the O(h^2)..O(h^4) determinants of aats.py:581-618)."""

@@ -54,9 +54,9 @@ eri = rnd(nmo, nmo, nmo, nmo)
 eps = torch.linspace(-2, 3, nmo, dtype=torch.float64, device="cuda")
 v = nmo - o
 t2 = torch.empty(o, o, v, v, dtype=c128, device="cuda")
-timeit("mp2_t2_energy spatial (o=12,v=70)", lambda: check(lib.apyib_mp2_t2_energy(1, ptr(eri), nmo, o, ptr(eps), 0, ptr(t2), ptr(E), ptr(scr), None, stream_ptr())), 4 * o * o * v * v * 16)
+timeit("mp2_t2_energy spatial (o=12,v=70)", lambda: check(lib.apyib_mp2_t2_energy(1, ptr(eri), nmo, o, ptr(eps), 2, ptr(t2), ptr(E), ptr(scr), None, stream_ptr())), 3 * o * o * v * v * 16)
 t2so = torch.empty(2 * o, 2 * o, 2 * v, 2 * v, dtype=c128, device="cuda")
-timeit("mp2_t2_energy spin-orbital (O=24,V=140)", lambda: check(lib.apyib_mp2_t2_energy(1, ptr(eri), nmo, o, ptr(eps), 1, ptr(t2so), ptr(E), ptr(scr), ptr(t2), stream_ptr())), (16 * o * o * v * v + 4 * o * o * v * v) * 16)
+timeit("mp2_t2_energy spin-orbital (O=24,V=140)", lambda: check(lib.apyib_mp2_t2_energy(1, ptr(eri), nmo, o, ptr(eps), 3, ptr(t2so), ptr(E), ptr(scr), ptr(t2), stream_ptr())), (16 * o * o * v * v + 3 * o * o * v * v) * 16)
 timeit("gather4 <ab||cd> SO block (V=140)", lambda: gather4(eri, 1, [2 * v] * 4, [0, 2, 1, 3], [2 * o] * 4, 1.0, [0, 3, 1, 2], [2 * o] * 4, -1.0), ((2 * v) ** 4 + 2 * v ** 4) * 16, reps=2)
 del eri, t2, t2so
 torch.cuda.empty_cache()
@@ -66,8 +66,8 @@ eri = torch.randn(nmo, nmo, nmo, nmo, dtype=torch.float64, device="cuda")
 eps = torch.linspace(-2, 3, nmo, dtype=torch.float64, device="cuda")
 v = nmo - o
 t2 = torch.empty(o, o, v, v, dtype=torch.float64, device="cuda")
-timeit("mp2_t2_energy spatial f64 (o=40,v=160)", lambda: check(lib.apyib_mp2_t2_energy(0, ptr(eri), nmo, o, ptr(eps), 0, ptr(t2), ptr(E), ptr(scr), None, stream_ptr())), 4 * o * o * v * v * 8)
+timeit("mp2_t2_energy spatial f64 (o=40,v=160)", lambda: check(lib.apyib_mp2_t2_energy(0, ptr(eri), nmo, o, ptr(eps), 2, ptr(t2), ptr(E), ptr(scr), None, stream_ptr())), 3 * o * o * v * v * 8)
 t2so = torch.empty(2 * o, 2 * o, 2 * v, 2 * v, dtype=torch.float64, device="cuda")
-timeit("mp2_t2_energy spin-orbital f64 (O=80,V=320)", lambda: check(lib.apyib_mp2_t2_energy(0, ptr(eri), nmo, o, ptr(eps), 1, ptr(t2so), ptr(E), ptr(scr), ptr(t2), stream_ptr())), (16 * o * o * v * v + 4 * o * o * v * v) * 8, reps=3)
+timeit("mp2_t2_energy spin-orbital f64 (O=80,V=320)", lambda: check(lib.apyib_mp2_t2_energy(0, ptr(eri), nmo, o, ptr(eps), 3, ptr(t2so), ptr(E), ptr(scr), ptr(t2), stream_ptr())), (16 * o * o * v * v + 3 * o * o * v * v) * 8, reps=3)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/streaming_roofline.json", "w"), indent=1)
