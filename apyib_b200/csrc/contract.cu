@@ -291,12 +291,18 @@ __global__ void __launch_bounds__(kDotThreads) contract_dot_kernel(const Contrac
 #pragma unroll
     for (int e = 0; e < kDotMaxOut; ++e) { accr[e] = 0.0; if (CPLX) acci[e] = 0.0; }
     const double sa = p.conj_a ? -1.0 : 1.0, sb = p.conj_b ? -1.0 : 1.0;
+    int64_t am[kDotMaxOut], bn[kDotMaxOut];            // per-output operand offsets, hoisted out of the k loop
+#pragma unroll
+    for (int e = 0; e < kDotMaxOut; ++e) {
+        am[e] = (e < MN) ? p.a_m[e / N] : 0;
+        bn[e] = (e < MN) ? p.b_n[e % N] : 0;
+    }
     for (int64_t k = k0 + threadIdx.x; k < k1; k += kDotThreads) {
         const int64_t ak = p.a_k[k], bk = p.b_k[k];
 #pragma unroll
         for (int e = 0; e < kDotMaxOut; ++e) {
             if (e >= MN) break;
-            const T av = A[p.a_m[e / N] + ak], bv = B[bk + p.b_n[e % N]];     // repeats hit L1
+            const T av = A[am[e] + ak], bv = B[bk + bn[e]];     // repeats hit L1
             if constexpr (CPLX) {
                 const double ar = av.x, ai = sa * av.y, br = bv.x, bi = sb * bv.y;
                 accr[e] = fma(ar, br, fma(-ai, bi, accr[e]));

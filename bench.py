@@ -398,12 +398,32 @@ def main():
             nrow, ncol = (int(x) for x in name.split(",")[1].rstrip("]").split("x"))
             ndet = nrow * ncol
             kern = "det_tpm_kernel<N=%d,B=3> (fused LU + table x vector) " % n if n <= 12 else "det_kernel<N=%d,fused> " % n
-            # (8/3) n^3 real flop per substituted n x n complex LU -- all of them executed
+            # (8/3) n^3 real flop per substituted n x n complex LU (algorithmic count)
             flops = ndet * (8.0 / 3.0) * n ** 3
             extra = {"determinants_per_s": ndet / (avg_ms * 1e-3)}
-            note = ("FP64 compute roofline (LU on the FP64 FMA pipe, every flop of the (8/3)n^3 count executed); "
-                    "peak = own DMMA/DFMA microbenchmark measured in this run (MEASURED_PEAKS.json holds bf16/HBM only, %s)"
-                    % peak_src)
+            note = ("FP64 compute roofline (LU on the FP64 FMA pipe); achieved = ALGORITHMIC (8/3)n^3 flops per "
+                    "determinant / measured time; peak = own DMMA/DFMA microbenchmark measured in this run "
+                    "(MEASURED_PEAKS.json holds bf16/HBM only, %s)" % peak_src)
+            if apyib_b200.config.LU_REUSE and 2 <= n <= 12 and nrow == ncol:
+                # factorisation reuse: determinants whose column list shares its leading panels with the previous
+                # one only redo the last panel (left-looking update + 3 pivots); count what was really executed
+                from apyib_b200.aats import _Tables
+                Tb = _Tables.get(n, wl["nfzc"], wl["nbf"] - n)
+                cs = Tb.LS[2][0].cpu().numpy()
+                nchunk = int(_lib.lib.apyib_det_matvec_work_len(nrow, ncol, 1, n)) // nrow
+                clen = -(-ncol // nchunk)
+                nl = ((n + 2) // 3 - 1) * 3
+                same = np.concatenate([[False], (cs[1:, :nl] == cs[:-1, :nl]).all(axis=1)])
+                same[np.arange(0, ncol, clen)] = False
+                reuse_frac = float(same.mean())
+                last = sum(n - 1 - k for k in range(nl)) * (n - nl) + sum((n - 1 - j) * (n - 1 - j) for j in range(nl, n))
+                exec_flops = ndet * ((1 - reuse_frac) * (8.0 / 3.0) * n ** 3 + reuse_frac * 8.0 * last)
+                extra.update({"reuse_fraction": reuse_frac, "executed_tflops": exec_flops / (avg_ms * 1e-3) / 1e12,
+                              "executed_frac": exec_flops / (avg_ms * 1e-3) / 1e12 / fp64_peak})
+                note += ("; with factorisation reuse %.0f %% of the determinants only redo their last panel, so the "
+                         "flops actually executed are lower: executed_frac is the FP64-pipe utilisation, frac the "
+                         "algorithmic rate (profiles/: plain LU without reuse = 38 %% of peak, every flop executed)"
+                         % (100 * reuse_frac))
             tkey = "det_tpm_kernel"
         elif name.startswith("lemma_matvec"):
             dims = name.split(",")[1]
