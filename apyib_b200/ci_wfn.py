@@ -396,8 +396,9 @@ class _CISDOperator:
         self.Wovoo, self.Wvooo = blk("kbij", "kijb"), blk("akij", "kija")
         self.Woooo, self.Wvvvv = blk("klij"), blk("abcd")
 
-    def apply(self, t1, t2, r1, r2, half=False):
-        """r += (linear part of the CISD residual)(t1, t2).
+    def apply(self, t1, t2, r1, r2, half=False, singles=True):
+        """r += (linear part of the CISD residual)(t1, t2).  singles=False keeps only the doubles <- doubles
+        terms (t1, r1 unused): the CID residual in the 12-term form of analytic_aats.py:1588-1600.
 
         half=True: r2 receives only h with (linear part) = h + P h, P = (i<->j, a<->b): the reference's 16
         r_T2 terms (ci_wfn.py:467-482) are the ladder and the oooo term, which are P-symmetric, and seven
@@ -407,15 +408,16 @@ class _CISDOperator:
         It halves the ring and coupling work of every iteration."""
         o = self
         c = 0.5 if half else 1.0
-        contract("sji,sja->sia", o.Foo, t1, r1, -1.0, 1.0)                  # :458
-        contract("sab,sib->sia", o.Fvv, t1, r1, 1.0, 1.0)                   # :459
-        contract("sjaib,sjb->sia", o.Lovvo, t1, r1, 1.0, 1.0)               # :460
-        contract("sjb,sijab->sia", o.Fov, t2, r1, 2.0, 1.0)                 # :461  F.(2 t2 - t2^T)
-        contract("sjb,sijba->sia", o.Fov, t2, r1, -1.0, 1.0)
-        contract("sajbc,sijbc->sia", o.Lvovv, t2, r1, 1.0, 1.0)             # :462
-        contract("skjib,skjab->sia", o.Looov, t2, r1, -1.0, 1.0)            # :463
-        contract("sjabc,sic->sijab", o.Wvvvo, t1, r2, 1.0, 1.0)             # :467
-        contract("skijb,ska->sijab", o.Wovoo, t1, r2, -1.0, 1.0)            # :469
+        if singles:
+            contract("sji,sja->sia", o.Foo, t1, r1, -1.0, 1.0)              # :458
+            contract("sab,sib->sia", o.Fvv, t1, r1, 1.0, 1.0)               # :459
+            contract("sjaib,sjb->sia", o.Lovvo, t1, r1, 1.0, 1.0)           # :460
+            contract("sjb,sijab->sia", o.Fov, t2, r1, 2.0, 1.0)             # :461  F.(2 t2 - t2^T)
+            contract("sjb,sijba->sia", o.Fov, t2, r1, -1.0, 1.0)
+            contract("sajbc,sijbc->sia", o.Lvovv, t2, r1, 1.0, 1.0)         # :462
+            contract("skjib,skjab->sia", o.Looov, t2, r1, -1.0, 1.0)        # :463
+            contract("sjabc,sic->sijab", o.Wvvvo, t1, r2, 1.0, 1.0)         # :467
+            contract("skijb,ska->sijab", o.Wovoo, t1, r2, -1.0, 1.0)        # :469
         contract("sac,sijcb->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :471
         contract("ski,skjab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :473
         contract("sklij,sklab->sijab", o.Woooo, t2, r2, c, 1.0)             # :475
@@ -425,8 +427,9 @@ class _CISDOperator:
         contract("skbic,skjac->sijab", o.Wovov, t2, r2, -1.0, 1.0)          # :479
         if half:
             return
-        contract("siabc,sjc->sijab", o.Wvvov, t1, r2, 1.0, 1.0)             # :468
-        contract("skija,skb->sijab", o.Wvooo, t1, r2, -1.0, 1.0)            # :470
+        if singles:
+            contract("siabc,sjc->sijab", o.Wvvov, t1, r2, 1.0, 1.0)         # :468
+            contract("skija,skb->sijab", o.Wvooo, t1, r2, -1.0, 1.0)        # :470
         contract("sbc,sijac->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :472
         contract("skj,sikab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :474
         contract("skaic,skjbc->sijab", o.Wovvo, t2, r2, -1.0, 1.0)          # :480
@@ -460,33 +463,49 @@ def solve_perturbed_CISD(parameters, ci, t1, t2, E_CISD, dF_MO, dERI_MO, dE_gues
 
     The part of the residual that only involves the unperturbed amplitudes is built once (the
     reference rebuilds it every iteration); each iteration then costs one CISD contraction set."""
+    return _solve_perturbed(parameters, ci, t1, t2, E_CISD, dF_MO, dERI_MO, dE_guess, print_level, True)
+
+
+def solve_perturbed_CID(parameters, ci, t2, E_CID, dF_MO, dERI_MO, dE_guess=0.0, print_level=0):
+    """The CID variant, analytic_aats.py:1553-1649 (magnetic field) and :1754-1850 (nuclear
+    displacement): the same iteration restricted to the doubles <- doubles terms (:1588-1614),
+    convergence on the energy derivative and rms(dt2) only (:1636-1639).  Returns (dE_proj, dt2)."""
+    dE, _, dt2 = _solve_perturbed(parameters, ci, None, t2, E_CID, dF_MO, dERI_MO, dE_guess, print_level, False)
+    return dE, dt2
+
+
+def _solve_perturbed(parameters, ci, t1, t2, E_CI, dF_MO, dERI_MO, dE_guess, print_level, singles):
     pt = ci.point()
     dt_ = pt.ERI.dtype
     cast = lambda x: to_device(np.asarray(x), dt_)
     dF, dERI = cast(dF_MO), cast(dERI_MO)
-    eng, O, V, bd = _make_engine(parameters, [pt], True, False)
+    eng, O, V, bd = _make_engine(parameters, [pt], singles, False)
     n1, L = eng.n1, eng.len
     op0 = _CISDOperator([pt.F], [pt.ERI], O, V, bd, dt_)
     op1 = _CISDOperator([dF], [dERI], O, V, bd, dt_)
     tfix = zeros((1, L), dt_)
-    tfix[:, :n1].copy_(cast(t1).reshape(1, -1))
+    if singles:
+        tfix[:, :n1].copy_(cast(t1).reshape(1, -1))
     tfix[:, n1:].copy_(cast(t2).reshape(1, -1))
     # constant part: dF_ai | d<ab|ij>  +  (perturbed integrals) x (unperturbed amplitudes)
-    eng.r0[:, :n1].copy_(op1.Fai)
+    t1v = (lambda x=None: eng.t1(x)) if singles else (lambda x=None: None)
+    if singles:
+        eng.r0[:, :n1].copy_(op1.Fai)
+        eng.w[:, :n1].copy_(op0.w1)
     eng.r0[:, n1:].copy_(op1.K)
-    op1.apply(eng.t1(tfix), eng.t2(tfix), eng.t1(eng.r0), eng.t2(eng.r0))
-    eng.w[:, :n1].copy_(op0.w1)
+    op1.apply(t1v(tfix), eng.t2(tfix), t1v(eng.r0), eng.t2(eng.r0), singles=singles)
     eng.w[:, n1:].copy_(op0.w2)
     # constant part of the projected energy derivative: 2 t1.dF_ov + t2.(2 d<ij|ab> - d<ij|ba>)  (:774, :868)
     wd = zeros((1, L), dt_)
-    wd[:, :n1].copy_(op1.w1)
+    if singles:
+        wd[:, :n1].copy_(op1.w1)
     wd[:, n1:].copy_(op1.w2)
     c0 = zeros((2,), torch.float64)
     check(lib.apyib_dots(eng.code, ptr(wd), 0, 1, ptr(tfix), L, 0, ptr(c0), ptr(eng.scratch), stream_ptr()))
     E2_off = zeros((1, 6), torch.float64)
     E2_off[0, :2].copy_(c0)
     E_fixed = zeros((1, 6), torch.float64)
-    Ec = complex(E_CISD)
+    Ec = complex(E_CI)
     E_fixed[0, 0], E_fixed[0, 1] = Ec.real, Ec.imag
     c0h = to_host(c0)
     c0v = complex(c0h[0], c0h[1]) if eng.code else float(c0h[0])
@@ -500,7 +519,8 @@ def solve_perturbed_CISD(parameters, ci, t1, t2, E_CISD, dF_MO, dERI_MO, dE_gues
         a = lambda alpha, x, y: check(lib.apyib_axpby(eng.code, x.numel(), alpha.real, alpha.imag, ptr(x), 0, 1.0, 0.0,
                                                      ptr(y), stream_ptr()))
         cons = zeros((1, L), dt_)
-        cons[:, :n1].copy_(op1.Fai)
+        if singles:
+            cons[:, :n1].copy_(op1.Fai)
         cons[:, n1:].copy_(op1.K)
         a(complex(-1.0), cons, eng.r)
         a(-g, tfix, eng.r)
@@ -512,13 +532,13 @@ def solve_perturbed_CISD(parameters, ci, t1, t2, E_CISD, dF_MO, dERI_MO, dE_gues
 
     eng.custom_guess = guess
     eng.lr = (E_fixed, E2_off, tfix)
-    residual = lambda _: op0.apply(eng.t1(), eng.t2(), eng.t1(eng.r), eng.t2(eng.r))
+    residual = lambda _: op0.apply(t1v(), eng.t2(), t1v(eng.r), eng.t2(eng.r), singles=singles)
     E = eng.run(residual, print_level)
     dE = E[0] + c0v
     ci.iterations = eng.iterations[0]
     if config.RETURN_DEVICE:
-        return dE, eng.t1()[0].clone(), eng.t2()[0].clone()
-    return dE, to_host(eng.t1())[0].copy(), to_host(eng.t2())[0].copy()
+        return dE, (eng.t1()[0].clone() if singles else None), eng.t2()[0].clone()
+    return dE, (to_host(eng.t1())[0].copy() if singles else None), to_host(eng.t2())[0].copy()
 
 
 _SOLVERS = {"CID": (_solve_CID, False), "CID_SO": (_solve_CID_SO, False),

@@ -865,3 +865,35 @@ def solve_perturbed_CISD(parameters, wfn, t1, t2, E_CISD, dF_MO, dERI_MO, dE_gue
             break
         it += 1
     return (dE, dt1, dt2, min(it, parameters["max_iterations"])) if return_iters else (dE, dt1, dt2)
+
+
+def solve_perturbed_CID(parameters, wfn, t2, E_CID, dF_MO, dERI_MO, dE_guess=0.0, return_iters=False):
+    """dt2/dlambda of the CID amplitudes, analytic_aats.py:1553-1649 (magnetic field) and :1754-1850
+    (nuclear displacement): the doubles <- doubles terms of the CISD loop (:1588-1614), convergence on
+    the energy derivative and rms(dt2) (:1636-1639)."""
+    ci = _CI(parameters, wfn)
+    o, v = ci.I_list[1], ci.I_list[2]
+    F, W, D2 = ci.F_MO, ci.ERI_MO.swapaxes(1, 2), ci.D_ijab
+    dF, dW = dF_MO, dERI_MO.swapaxes(1, 2)
+    L = 2.0 * W[o, o, v, v] - W.swapaxes(2, 3)[o, o, v, v]
+    dL = 2.0 * dW[o, o, v, v] - dW.swapaxes(2, 3)[o, o, v, v]
+    dK = dW.swapaxes(0, 2).swapaxes(1, 3)[o, o, v, v]
+    z1 = np.zeros(ci.D_ia.shape, dtype=t2.dtype)
+    lin = lambda f, w, x: _cisd_linear(f, w, o, v, z1, x)[1]
+    p2 = lin(dF, dW, t2)
+    dt2 = (-dE_guess * t2 + p2) / D2                                        # :1553-1567
+    proj = lambda dt2: np.einsum("ijab,ijab->", t2, dL) + np.einsum("ijab,ijab->", dt2, L)   # :1570-1571
+    dE = proj(dt2)
+    diis = _Diis(parameters["DIIS"])
+    it = 1
+    while it <= parameters["max_iterations"]:
+        dE_old, o2 = dE, dt2.copy()
+        r2 = dK - dE * t2 + p2 - E_CID * dt2 + lin(F, W, dt2)               # :1581-1614
+        dt2 = dt2 + r2 / D2
+        (dt2,) = diis(it, [r2], [dt2])
+        dE = proj(dt2)
+        rms2 = np.sqrt(np.einsum("ijab,ijab->", o2 - dt2, o2 - dt2))
+        if _converged(parameters, it, dE_old - dE, [rms2]):
+            break
+        it += 1
+    return (dE, dt2, min(it, parameters["max_iterations"])) if return_iters else (dE, dt2)

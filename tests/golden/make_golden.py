@@ -195,11 +195,37 @@ def linear_response(ns):
     np.savez_compressed(os.path.join(HERE, "synthetic_linear_response.npz"), **out)
 
 
+def linear_response_cid(ns):
+    """a21, CID variant (analytic_aats.py:1577-1649): central finite differences of the UNMODIFIED
+    reference solve_CID under F_MO + lam dF, ERI_MO + lam dERI (same cases and perturbations)."""
+    out = {}
+    lam = 1e-4
+    for name, nbf, no, nf, cplx, seed in PERT_CASES:
+        w = orc.rotated_wfn(nbf, no, seed, cplx, nf)
+        p = par("CID", nf > 0, maxit=300, conv=1e-14)
+        dF, dG = perturbation(nbf - nf, cplx, seed + 50)
+
+        def solve(l):
+            r = ns.ci_wfn.ci_wfn(p, w)
+            r.F_MO = r.F_MO + l * dF
+            r.ERI_MO = r.ERI_MO + l * dG
+            return quiet(r.solve_CID)
+        (Ep, t2p), (Em, t2m), (E0, t2) = solve(lam), solve(-lam), solve(0.0)
+        out[name + "/dE"] = np.asarray((Ep - Em) / (2 * lam))
+        out[name + "/dt2"] = (t2p - t2m) / (2 * lam)
+        out[name + "/E0"], out[name + "/t2"] = np.asarray(E0), t2
+    np.savez_compressed(os.path.join(HERE, "synthetic_linear_response_cid.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--only-cid-response" in sys.argv:
+        linear_response_cid(ref_harness.load())
+        sys.exit(0)
     lit = extract_literals()
     json.dump(lit, open(os.path.join(HERE, "reference_literals.json"), "w"), indent=1)
     print("literals:", [(c["test"], sorted(c["arrays"])) for c in lit["cases"]])
     ns = ref_harness.load()
     synthetic(ns)
     linear_response(ns)
+    linear_response_cid(ns)
     print("wrote", sorted(os.listdir(HERE)))

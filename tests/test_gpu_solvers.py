@@ -153,3 +153,27 @@ def test_perturbed_cisd_amplitudes(nbf, no, nf, cplx, seed):
     G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synthetic_linear_response.npz"))
     name = {901: "r7", 902: "c6", 903: "r8fc"}[seed]
     assert abs(dE - G[name + "/dE"]) < 1e-8 and np.abs(dt2 - G[name + "/dt2"]).max() < 1e-8
+
+
+@pytest.mark.parametrize("nbf,no,nf,cplx,seed", [(7, 3, 0, False, 901), (6, 2, 0, True, 902), (8, 3, 1, False, 903)])
+def test_perturbed_cid_amplitudes(nbf, no, nf, cplx, seed):
+    """a21, CID variant (analytic_aats.py:1577-1649 / 1778-1850): GPU linear-response iterations vs the oracle
+    and vs finite differences of the unmodified reference solve_CID (synthetic_linear_response_cid.npz)."""
+    import os
+    import apyib_b200
+    from apyib_b200.ci_wfn import solve_perturbed_CID
+    from golden.make_golden import perturbation
+    w = orc.rotated_wfn(nbf, no, seed, cplx, nf)
+    p = par("CID", nf > 0, maxit=300, conv=1e-14)
+    dF, dG = perturbation(nbf - nf, cplx, seed + 50)
+    ci = apyib_b200.ci_wfn(p, w)
+    E0, t2 = ci.solve_CID()
+    for guess in (0.0, 0.3):
+        dE, dt2 = solve_perturbed_CID(p, ci, t2, E0, dF, dG, dE_guess=guess)
+        oE, o2, its = orc.solve_perturbed_CID(p, w, t2, E0, dF, dG, guess, True)
+        assert ci.iterations == its
+        assert abs(dE - oE) < E_TOL and np.abs(dt2 - o2).max() < T_TOL
+        assert dt2.dtype == o2.dtype and dt2.shape == o2.shape
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synthetic_linear_response_cid.npz"))
+    name = {901: "r7", 902: "c6", 903: "r8fc"}[seed]
+    assert abs(dE - G[name + "/dE"]) < 1e-8 and np.abs(dt2 - G[name + "/dt2"]).max() < 1e-8

@@ -149,3 +149,18 @@ def test_linear_response_matches_finite_differences_of_reference_solver(name, nb
     assert abs(dE - LRG[name + "/dE"]) < 1e-8
     assert np.abs(dt1 - LRG[name + "/dt1"]).max() < 1e-8
     assert np.abs(dt2 - LRG[name + "/dt2"]).max() < 1e-8
+
+
+LRG_CID = np.load(os.path.join(HERE, "golden", "synthetic_linear_response_cid.npz"))
+
+
+@pytest.mark.parametrize("name,nbf,no,nf,cplx,seed", PERT_CASES)
+def test_cid_linear_response_matches_finite_differences_of_reference_solver(name, nbf, no, nf, cplx, seed):
+    """analytic_aats.py:1577-1649 restated (CID variant of a21); pinned by central differences of the
+    unmodified reference solve_CID under perturbed MO integrals."""
+    w = orc.rotated_wfn(nbf, no, seed, cplx, nf)
+    p = par("CID", nf > 0, maxit=300, conv=1e-14)
+    dF, dG = perturbation(nbf - nf, cplx, seed + 50)
+    dE, dt2 = orc.solve_perturbed_CID(p, w, LRG_CID[name + "/t2"], LRG_CID[name + "/E0"], dF, dG)
+    assert abs(dE - LRG_CID[name + "/dE"]) < 1e-8
+    assert np.abs(dt2 - LRG_CID[name + "/dt2"]).max() < 1e-8
