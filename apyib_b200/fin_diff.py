@@ -1,5 +1,5 @@
 """Finite-difference driver -- drop-in for apyib/fin_diff.py (compute_AAT, compute_APT,
-compute_Hessian; fin_diff.py:12-372).
+compute_Hessian, compute_Nuclear_Gradient, compute_Magnetic_Field_Gradient; fin_diff.py:12-510).
 
 The reference walks the displacement / field points in one serial Python loop.  Here the list
 of points is explicit (`aat_points`, `apt_points`), so that the same driver can (a) run them
@@ -8,12 +8,11 @@ a box (parallel.py); every point is a full, independent solve -- no data-path co
 """
 from __future__ import annotations
 
-import copy
-
 import numpy as np
 
-from .energy import energy, phase_corrected_energy, scf_point, correlated_many
+from .energy import scf_point, correlated_many
 from .hostchem import Molecule
+from .utils import release_ao
 
 
 def aat_points(natom):
@@ -88,23 +87,60 @@ class finite_difference(object):
         (mpC, mpB, mpT), (mnC, mnB, mnT) = res[("B", +1)], res[("B", -1)]
         return npC, nnC, npB, nnB, npT, nnT, mpC, mnC, mpB, mnB, mpT, mnT
 
+    # -- energy-only double differences ---------------------------------------------------------
+    # AO integrals + ERI_MO of a point live on the device while its batch is being solved; bound the batch.
+    BATCH_BYTES = 24 << 30
+
+    def _total_energies(self, settings):
+        """Total energies E_SCF + E_corr + E_nuc of a list of points, each given as
+        (geometry shifts [(coordinate, delta), ...], F_el increments [(axis, delta), ...]).
+        What the reference does with one `energy(parameters)` call per point (fin_diff.py:53, 70, 174, ...)
+        is split into the host SCFs of all points followed by batched device solves (shared launches;
+        bit-identical to the point-by-point solves, tests/test_gpu_solvers.py)."""
+        out = [None] * len(settings)
+        wfns, idx = [], []
+
+        def flush():
+            if wfns:
+                for k, w, (E, _) in zip(idx, wfns, correlated_many(self.parameters, wfns)):
+                    out[k] = w.E_SCF + E + w.H.E_nuc
+                    release_ao(w)
+            wfns.clear()
+            idx.clear()
+
+        for k, (shifts, fields) in enumerate(settings):
+            if shifts:
+                self.parameters["geom"] = self._displaced(shifts)
+            for b, d in fields:
+                self.parameters["F_el"][b] += d
+            w = scf_point(self.parameters)
+            for b, d in fields:
+                self.parameters["F_el"][b] -= d
+            if shifts:
+                self._reset()
+            wfns.append(w)
+            idx.append(k)
+            if len(wfns) * 3 * 16 * w.nbf ** 4 >= self.BATCH_BYTES:
+                flush()
+        flush()
+        return out
+
     # -- fin_diff.py:151-263 ------------------------------------------------------------------
     def apt_points(self):
         return [(a, sr, b, sf) for sr in (+1, -1) for a in range(3 * self.natom) for sf in (+1, -1) for b in range(3)]
 
     def solve_apt_point(self, point, h_R, h_F):
-        a, sr, b, sf = point
-        self.parameters["geom"] = self._displaced([(a, sr * h_R)])
-        self.parameters["F_el"][b] += sf * h_F
-        E_list, T_list, C, basis = energy(self.parameters)
-        self.parameters["F_el"][b] -= sf * h_F
-        self._reset()
-        return E_list[0] + E_list[1] + E_list[2]
+        return self.solve_apt_points([point], h_R, h_F)[0]
+
+    def solve_apt_points(self, points, h_R, h_F):
+        """Total energies of a subset of the 36N (R +- h_R, F +- h_F) points (sharding: parallel.py)."""
+        return self._total_energies([([(a, sr * h_R)], [(b, sf * h_F)]) for a, sr, b, sf in points])
 
     def compute_APT(self, nuc_pert_strength, elec_pert_strength, energies=None):
         n3 = 3 * self.natom
         if energies is None:
-            energies = {pt: self.solve_apt_point(pt, nuc_pert_strength, elec_pert_strength) for pt in self.apt_points()}
+            pts = self.apt_points()
+            energies = dict(zip(pts, self.solve_apt_points(pts, nuc_pert_strength, elec_pert_strength)))
         mu = {}
         for sr in (+1, -1):
             mu[sr] = np.array([[-(energies[(a, sr, b, +1)] - energies[(a, sr, b, -1)]) / (2 * elec_pert_strength)
@@ -112,20 +148,44 @@ class finite_difference(object):
         return (mu[+1] - mu[-1]) / (2 * nuc_pert_strength)
 
     # -- fin_diff.py:27-147 -------------------------------------------------------------------
-    def compute_Hessian(self, nuc_pert_strength):
+    def hessian_points(self):
+        n3 = 3 * self.natom
+        return [(a, sa, b, sb) for sa in (+1, -1) for a in range(n3) for sb in (+1, -1) for b in range(n3)]
+
+    def compute_Hessian(self, nuc_pert_strength, energies=None):
         n3 = 3 * self.natom
         h = nuc_pert_strength
-        g = {}
-        for sa in (+1, -1):
-            rows = []
-            for a in range(n3):
-                e = {}
-                for sb in (+1, -1):
-                    for b in range(n3):
-                        self.parameters["geom"] = self._displaced([(a, sa * h), (b, sb * h)])
-                        E_list, T_list, C, basis = energy(self.parameters)
-                        e[(b, sb)] = E_list[0] + E_list[1] + E_list[2]
-                rows.append([(e[(b, +1)] - e[(b, -1)]) / (2 * h) for b in range(n3)])
-                self._reset()
-            g[sa] = np.array(rows)
+        if energies is None:
+            pts = self.hessian_points()
+            energies = dict(zip(pts, self._total_energies([([(a, sa * h), (b, sb * h)], []) for a, sa, b, sb in pts])))
+        g = {sa: np.array([[(energies[(a, sa, b, +1)] - energies[(a, sa, b, -1)]) / (2 * h) for b in range(n3)]
+                           for a in range(n3)]) for sa in (+1, -1)}
         return (g[+1] - g[-1]) / (2 * h)
+
+    # -- fin_diff.py:376-447, 451-510 -----------------------------------------------------------
+    def _gradient(self, kind, n, h_R, h_B):
+        """Central-difference energy gradient over the R (n = 3N) or B (n = 3) points of compute_AAT,
+        phase-corrected like them; returns (E+ - E-)/2h and the per-point C / basis / T lists."""
+        pts = [(kind, i, +1) for i in range(n)] + [(kind, i, -1) for i in range(n)]
+        wfns = [self.scf_aat_point(pt, h_R, h_B) for pt in pts]
+        solved = correlated_many(self.parameters, wfns)
+        E = [w.E_SCF + e + w.H.E_nuc for w, (e, _) in zip(wfns, solved)]
+        h = h_R if kind == "R" else h_B
+        grad = np.zeros(n)
+        for i in range(n):
+            grad[i] = np.real(E[i] - E[n + i]) / (2 * h)     # the reference stores into a float array
+        C = [w.C for w in wfns]
+        B = [w.H.basis_set for w in wfns]
+        T = [t for _, t in solved]
+        return grad, C[:n], C[n:], B[:n], B[n:], T[:n], T[n:]
+
+    def compute_Nuclear_Gradient(self, nuc_pert_strength):
+        """fin_diff.py:376-447: returns (gradient (N,3), nuc_pos_C, nuc_neg_C, nuc_pos_basis, nuc_neg_basis,
+        nuc_pos_T, nuc_neg_T)."""
+        out = self._gradient("R", 3 * self.natom, nuc_pert_strength, 0.0)
+        return (out[0].reshape(self.natom, 3),) + out[1:]
+
+    def compute_Magnetic_Field_Gradient(self, mag_pert_strength):
+        """fin_diff.py:451-510: returns (gradient (3,), mag_pos_C, mag_neg_C, mag_pos_basis, mag_neg_basis,
+        mag_pos_T, mag_neg_T)."""
+        return self._gradient("B", 3, 0.0, mag_pert_strength)

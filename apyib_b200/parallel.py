@@ -181,3 +181,31 @@ def compute_parallel_aats(parameters, nuc_pert_strength, mag_pert_strength, norm
     if config.VERBOSE and rank == 0:
         print(I, "\n")
     return I
+
+
+def gather_energies(dist, values, owner, rank, world):
+    """Energy-only drivers: every rank holds the energies of the points it owns; a sum-all-reduce of the
+    disjointly filled float64 vector (real, imaginary parts) is the gather.  values[k] is None for points
+    of other ranks."""
+    n = len(owner)
+    buf = np.zeros((n, 2))
+    for k in range(n):
+        if owner[k] == rank:
+            buf[k] = (np.real(values[k]), np.imag(values[k]))
+    buf = gather_tensor(dist, buf, world)
+    return [complex(re, im) if im != 0.0 else float(re) for re, im in buf]
+
+
+def compute_parallel_apts(parameters, nuc_pert_strength, elec_pert_strength):
+    """Sharded counterpart of finite_difference.compute_APT (fin_diff.py:151-263): the 36N
+    (R +- h_R) x (F +- h_F) energy points are partitioned over the ranks, every rank runs its solves
+    batched on its GPU, the energies are gathered with one all-reduce and differenced on the host.
+    Returns the (3N, 3) tensor on every rank."""
+    dist, rank, world = _dist()
+    fd = finite_difference(parameters, None, None)
+    pts = fd.apt_points()
+    owner = partition(pts, [1.0] * len(pts), world)
+    mine = [p for p, o in zip(pts, owner) if o == rank]
+    solved = dict(zip(mine, fd.solve_apt_points(mine, nuc_pert_strength, elec_pert_strength)))
+    energies = gather_energies(dist, [solved.get(p) for p in pts], owner, rank, world)
+    return fd.compute_APT(nuc_pert_strength, elec_pert_strength, energies=dict(zip(pts, energies)))

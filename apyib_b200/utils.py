@@ -59,6 +59,14 @@ def ao_on_device(wfn, want_complex):
     return cache[key]
 
 
+def release_ao(wfn):
+    """Drop the device copy of a point's AO integrals (energy-only drivers: thousands of points)."""
+    try:
+        wfn.H.__dict__.pop("_apyib_b200_dev", None)
+    except AttributeError:
+        pass
+
+
 def _is_complex(wfn):
     return bool(np.iscomplexobj(wfn.C) or np.iscomplexobj(wfn.H.T) or np.iscomplexobj(wfn.H.V)
                 or np.iscomplexobj(wfn.H.ERI))

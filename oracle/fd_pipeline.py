@@ -141,3 +141,46 @@ def compute_APT(parameters, h_R, h_F):                                   # fin_d
         mu[sr] = np.array(rows)
     parameters["geom"] = saved
     return (mu[+1] - mu[-1]) / (2 * h_R)
+
+
+def compute_Hessian(parameters, h):                                      # fin_diff.py:27-147
+    mol = hc.Molecule.from_string(parameters["geom"])
+    geom0, saved = mol.geometry(), parameters["geom"]
+    n3 = 3 * mol.natom()
+    g = {}
+    for sa in (+1, -1):
+        rows = []
+        for a in range(n3):
+            e = {}
+            for sb in (+1, -1):
+                for b in range(n3):
+                    x = geom0.copy()
+                    x[a // 3][a % 3] += sa * h
+                    x[b // 3][b % 3] += sb * h
+                    mol.set_geometry(x)
+                    parameters["geom"] = mol.create_psi4_string_from_molecule()
+                    E_list = energy(parameters)[0]
+                    e[(b, sb)] = E_list[0] + E_list[1] + E_list[2]
+            rows.append([(e[(b, +1)] - e[(b, -1)]) / (2 * h) for b in range(n3)])
+        g[sa] = np.array(rows)
+    parameters["geom"] = saved
+    return (g[+1] - g[-1]) / (2 * h)
+
+
+def compute_Nuclear_Gradient(parameters, basis0, C0, h):                 # fin_diff.py:376-447
+    pts = fd_points(parameters, basis0, C0, h, 0.0)
+    n3 = 3 * hc.Molecule.from_string(parameters["geom"]).natom()
+    tot = lambda p: p[0][0] + p[0][1] + p[0][2]
+    grad = np.zeros(n3)
+    for a in range(n3):
+        grad[a] = np.real(tot(pts[("R", a, +1)]) - tot(pts[("R", a, -1)])) / (2 * h)
+    return grad.reshape(-1, 3), [pts[("R", a, +1)][1] for a in range(n3)], [pts[("R", a, -1)][1] for a in range(n3)]
+
+
+def compute_Magnetic_Field_Gradient(parameters, basis0, C0, h):          # fin_diff.py:451-510
+    pts = fd_points(parameters, basis0, C0, 0.0, h)
+    tot = lambda p: p[0][0] + p[0][1] + p[0][2]
+    grad = np.zeros(3)
+    for b in range(3):
+        grad[b] = np.real(tot(pts[("B", b, +1)]) - tot(pts[("B", b, -1)])) / (2 * h)
+    return grad, [pts[("B", b, +1)][1] for b in range(3)], [pts[("B", b, -1)][1] for b in range(3)]

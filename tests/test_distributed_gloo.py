@@ -56,7 +56,19 @@ def _worker(rank, world, port, natom, q):
             I[a, b] = 100 * a + b + 0.5
         I = gather_tensor(d, I, world)
         want = np.array([[100 * a + b + 0.5 for b in range(3)] for a in range(n3)])
-        q.put((rank, bool(np.array_equal(I, want)), len(mine)))
+        # energy-only drivers (APT): disjointly filled energies, one all-reduce, identical on every rank
+        from apyib_b200.parallel import gather_energies
+        from apyib_b200.fin_diff import finite_difference
+        fd = finite_difference.__new__(finite_difference)
+        fd.natom = natom
+        apts = fd.apt_points()
+        aown = partition(apts, [1.0] * len(apts), world)
+        ecode = lambda p: -76.0 + 1e-3 * p[0] + 1e-4 * p[1] + 1e-5 * p[2] + 1e-6 * p[3]
+        E = gather_energies(d, [ecode(p) if o == rank else None for p, o in zip(apts, aown)], aown, rank, world)
+        ok_apt = len(apts) == 36 * natom and E == [ecode(p) for p in apts] and abs(aown.count(0) - aown.count(1)) <= 1
+        apt = fd.compute_APT(1e-3, 1e-4, energies=dict(zip(apts, E)))
+        ok_apt = ok_apt and apt.shape == (n3, 3)
+        q.put((rank, bool(np.array_equal(I, want)) and ok_apt, len(mine)))
     finally:
         dist.destroy_process_group()
 

@@ -162,6 +162,63 @@ def test_apt_pipeline_vs_oracle_pipeline():
     assert np.abs(got - want).max() < 1e-5       # reference's APT tolerance (test_010_APT.py)
 
 
+def _tiny(method="CISD", seed=8, natom=1):
+    from apyib_b200 import hostchem as hc
+    prov = hc.SyntheticProvider(6, 2, natom, seed=seed)
+    return lambda: {"geom": prov.geometry_string(), "basis": "synthetic", "method": method, "freeze_core": False,
+                    "F_el": [0.0] * 3, "F_mag": [0.0] * 3, "provider": prov, "DIIS": True, "max_iterations": 100,
+                    "e_convergence": 1e-13, "d_convergence": 1e-13}
+
+
+def test_parallel_apts_single_process_equals_compute_APT():
+    """compute_parallel_apts (sharded APT driver; one process here) == finite_difference.compute_APT, and the
+    caller's parameters come back unchanged (fin_diff.py mutates and restores them)."""
+    from apyib_b200.fin_diff import finite_difference
+    from apyib_b200.parallel import compute_parallel_apts
+    from oracle import fd_pipeline as fp
+    mk = _tiny("CID", seed=9)
+    p = mk()
+    got = compute_parallel_apts(p, 1e-3, 1e-4)
+    assert p["F_el"] == [0.0] * 3 and p["geom"].split() == mk()["geom"].split()
+    assert np.array_equal(got, finite_difference(mk(), None, None).compute_APT(1e-3, 1e-4))
+    assert np.abs(got - fp.compute_APT(mk(), 1e-3, 1e-4)).max() < 1e-5
+
+
+@pytest.mark.parametrize("method", ["CISD", "MP2"])
+def test_hessian_pipeline_vs_oracle_pipeline(method):
+    """fin_diff.py:27-147: 4 (3N)^2 energies, batched on the device, vs the oracle pipeline"""
+    from apyib_b200.fin_diff import finite_difference
+    from oracle import fd_pipeline as fp
+    mk = _tiny(method)
+    got = finite_difference(mk(), None, None).compute_Hessian(1e-3)
+    want = fp.compute_Hessian(mk(), 1e-3)
+    assert got.shape == (3, 3) and np.abs(got - got.T).max() < 1e-5
+    assert np.abs(got - want).max() < 1e-5       # second differences of energies that agree to ~1e-12
+
+
+def test_gradient_drivers_vs_oracle_pipeline():
+    """fin_diff.py:376-510: nuclear / magnetic-field gradients and the per-point (C, basis, T) lists"""
+    from apyib_b200.energy import energy
+    from apyib_b200.fin_diff import finite_difference
+    from oracle import fd_pipeline as fp
+    mk = _tiny("CISD")
+    p = mk()
+    E_list, T_list, C, basis = energy(p)
+    fd = finite_difference(p, basis, C)
+    g, pC, nC, pB, nB, pT, nT = fd.compute_Nuclear_Gradient(1e-4)
+    wg, wpT, wnT = fp.compute_Nuclear_Gradient(mk(), basis, C, 1e-4)
+    assert g.shape == (1, 3) and len(pC) == len(nB) == len(nT) == 3
+    assert np.abs(g - wg).max() < 1e-7
+    for a in range(3):
+        assert np.abs(pT[a][2] - wpT[a][2]).max() < 1e-9 and np.abs(nT[a][1] - wnT[a][1]).max() < 1e-9
+    g, pC, nC, pB, nB, pT, nT = fd.compute_Magnetic_Field_Gradient(1e-4)
+    wg, wpT, wnT = fp.compute_Magnetic_Field_Gradient(mk(), basis, C, 1e-4)
+    assert g.shape == (3,) and g.dtype == np.float64 and np.abs(g - wg).max() < 1e-7
+    for b in range(3):
+        assert pT[b][2].dtype == np.complex128 and np.abs(pT[b][2] - wpT[b][2]).max() < 1e-9
+    assert p["F_mag"] == [0.0] * 3
+
+
 @pytest.mark.parametrize("nbf,no,nf", [(9, 4, 1), (12, 5, 0), (7, 2, 0)])
 def test_lemma_tables_match_lu_tables(nbf, no, nf):
     """every determinant family of compute_all_dets: lemma kernel vs sub-warp LU kernel"""

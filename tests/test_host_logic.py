@@ -111,3 +111,46 @@ def test_synthetic_provider_is_hermitian_and_smooth():
     E, Cm = w.solve_SCF(p)
     assert abs(np.imag(E)) < 1e-12
     assert np.abs(Cm.conj().T @ H.S @ Cm - np.eye(6)).max() < 1e-12
+
+
+def _tiny(method="CISD", seed=8):
+    from apyib_b200 import hostchem as hc
+    prov = hc.SyntheticProvider(6, 2, 1, seed=seed)
+    return lambda: {"geom": prov.geometry_string(), "basis": "synthetic", "method": method, "freeze_core": False,
+                    "F_el": [0.0] * 3, "F_mag": [0.0] * 3, "provider": prov, "DIIS": True, "max_iterations": 100,
+                    "e_convergence": 1e-13, "d_convergence": 1e-13}
+
+
+def test_energy_only_drivers_host_logic(monkeypatch):
+    """Point enumeration, parameter mutation/restoration, batching and differencing of compute_APT /
+    compute_Hessian / compute_*_Gradient (fin_diff.py:27-263, 376-510) with the device solves replaced by
+    the oracle's (checker only): must reproduce the oracle's serial restatement of the reference loops."""
+    from apyib_b200 import fin_diff as fdm, parallel
+    from oracle import fd_pipeline as fp
+    calls = []
+
+    def fake_many(parameters, wfns, print_level=0):
+        calls.append(len(wfns))
+        return [fp._solve(parameters, w) for w in wfns]
+    monkeypatch.setattr(fdm, "correlated_many", fake_many)
+    import apyib_b200.energy as en          # the MO phase fix is a device GEMM in the product (utils.compute_phase)
+    monkeypatch.setattr(en, "compute_phase", lambda ndocc, nbf, ub, uC, b, C, ao_overlap=None: fp.compute_phase(ub, uC, b, C))
+    mk = _tiny("CID", seed=9)
+    p = mk()
+    fd = fdm.finite_difference(p, None, None)
+    monkeypatch.setattr(fdm.finite_difference, "BATCH_BYTES", 10 * 3 * 16 * 6 ** 4)      # force several batches
+    apt = fd.compute_APT(1e-3, 1e-4)
+    assert calls == [10, 10, 10, 6] and p["F_el"] == [0.0] * 3 and p["geom"].split() == mk()["geom"].split()
+    assert np.abs(apt - fp.compute_APT(mk(), 1e-3, 1e-4)).max() < 1e-12
+    assert np.array_equal(parallel.compute_parallel_apts(mk(), 1e-3, 1e-4), apt)
+    hess = fd.compute_Hessian(1e-3)
+    assert np.abs(hess - fp.compute_Hessian(mk(), 1e-3)).max() < 1e-12
+    E_list, T0, C, basis, wfn = fp.energy(mk())
+    fd = fdm.finite_difference(p, basis, C)
+    g, pC, nC, pB, nB, pT, nT = fd.compute_Nuclear_Gradient(1e-4)
+    wg, wpT, wnT = fp.compute_Nuclear_Gradient(mk(), basis, C, 1e-4)
+    assert g.shape == (1, 3) and np.array_equal(g, wg) and all(np.array_equal(pT[a][2], wpT[a][2]) for a in range(3))
+    g, pC, nC, pB, nB, pT, nT = fd.compute_Magnetic_Field_Gradient(1e-4)
+    wg, wpT, wnT = fp.compute_Magnetic_Field_Gradient(mk(), basis, C, 1e-4)
+    assert g.shape == (3,) and np.array_equal(g, wg) and all(np.array_equal(nT[b][2], wnT[b][2]) for b in range(3))
+    assert p["F_mag"] == [0.0] * 3 and len(pC) == len(nB) == 3
