@@ -24,10 +24,10 @@ import numpy as np
 import torch
 
 from . import config
-from ._lib import lib, check
+from ._lib import lib, check, LAUNCHES as _liblaunch
 from .contraction import contract, contract_new
 from .device import to_device, to_host, empty, zeros, ptr, stream_ptr, reduce_scratch, device
-from .utils import mo_overlap_dev, spin_block_2_dev, SO_METHODS
+from .utils import mo_overlaps_dev, spin_block_2_dev, SO_METHODS
 
 _C128 = torch.complex128
 _tables = {}
@@ -136,6 +136,65 @@ def _vdot(x, y, conj_x=True):
     return complex(h[0], h[1])
 
 
+
+# -------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the device part of AAT._blocks (config.AAT_USE_GRAPH)
+# -------------------------------------------------------------------------------------------------
+_block_graphs = {}          # stack shape -> _BlockGraph | "warm" (seen once, eager) | None (not capturable)
+GRAPH_MAX_BYTES = 256 << 20
+
+
+class _BlockGraph:
+    """`AAT._blocks_device` for one stack shape, captured over static input buffers.  Capture runs under
+    torch.cuda.graph so that the intermediates the launch sequence allocates come from a private pool that
+    stays reserved for the graph (their addresses are baked into the captured launches)."""
+
+    def __init__(self, aat, inputs):
+        self.inp = [None if t is None else t.clone() for t in inputs]
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _liblaunch[0]
+        with torch.cuda.graph(self.graph):
+            self.flat, self.meta = aat._blocks_device(*self.inp)
+        self.launches = _liblaunch[0] - n0
+        _liblaunch[0] = n0                                   # recorded, not executed
+
+    def run(self, inputs):
+        for dst, src in zip(self.inp, inputs):
+            if dst is not None:
+                dst.copy_(src)
+        self.graph.replay()
+        _liblaunch[0] += self.launches
+        return self.flat, self.meta
+
+
+def _run_blocks(aat, S, X1, X2, Y1, Y2):
+    inputs = (S, X1, X2, Y1, Y2)
+    if not config.AAT_USE_GRAPH or torch.cuda.is_current_stream_capturing():
+        return aat._blocks_device(*inputs)
+    o, nv = aat.ndocc - aat.nfzc, aat.nbf - aat.ndocc
+    nS, nx, ny = S.shape[0], X2.shape[0], Y2.shape[0]
+    if 16 * o * o * nv * nv * nS * (nx + ny + nx * ny) > GRAPH_MAX_BYTES:
+        return aat._blocks_device(*inputs)                   # large shapes are not launch-bound; keep the pool small
+    key = (config.AAT_ALGORITHM, config.LU_REUSE, config.USE_TMA, aat.nbf, aat.ndocc, aat.nfzc, nS, nx, ny, X1 is not None,
+           tuple(X2.shape), tuple(Y2.shape), torch.cuda.current_device())
+    g = _block_graphs.get(key, "new")
+    if g == "new":
+        # first sight of a shape: eager (builds the contraction offset tables and one-time function attributes)
+        _block_graphs[key] = "warm"
+        return aat._blocks_device(*inputs)
+    if g == "warm":
+        try:
+            g = _BlockGraph(aat, inputs)
+        except Exception as exc:                             # not capturable here: stay eager for this shape
+            if config.VERBOSE:
+                print("apyib_b200: CUDA-graph capture of the AAT block failed (%s); running eagerly" % exc)
+            g = None
+        _block_graphs[key] = g
+    if g is None:
+        return aat._blocks_device(*inputs)
+    return g.run(inputs)
+
+
 class AAT(object):
     """The atomic axial tensor object computed by finite difference (aats.py:19-115)."""
 
@@ -155,24 +214,37 @@ class AAT(object):
         self.parameters = parameters
         so = parameters["method"] in SO_METHODS
 
-        def ovl(bb, Cb, kb, Ck):          # utils.compute_mo_overlap (+ compute_so_overlap), utils.py:370-422
-            S = mo_overlap_dev(Cb, provider_ao_overlap(bb, kb), Ck)
-            if so:
-                S = spin_block_2_dev(S)
-            return to_host(S)
+        # utils.compute_mo_overlap (+ compute_so_overlap), utils.py:370-422, for all 1 + 6 + 6N + 36N (bra, ket)
+        # pairs at once: the AO overlaps are host inputs, the C^H S C products two batched launches per dtype
+        jobs = []
+
+        def ovl(bb, Cb, kb, Ck):
+            jobs.append((Cb, provider_ao_overlap(bb, kb), Ck))
+            return len(jobs) - 1
 
         U, Ub = self.unperturbed_wfn, unperturbed_basis
-        if parameters["method"] != "RHF":
-            self.overlap_uu = ovl(Ub, U, Ub, U)
-            self.overlap_up = [ovl(Ub, U, mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)]
-            self.overlap_un = [ovl(Ub, U, mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)]
-            self.overlap_pu = [ovl(nuc_pos_basis[a], nuc_pos_wfn[a], Ub, U) for a in range(3 * natom)]
-            self.overlap_nu = [ovl(nuc_neg_basis[a], nuc_neg_wfn[a], Ub, U) for a in range(3 * natom)]
         n3 = 3 * natom
-        self.overlap_pp = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
-        self.overlap_pn = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
-        self.overlap_np = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
-        self.overlap_nn = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
+        rhf = parameters["method"] == "RHF"
+        if not rhf:
+            uu = ovl(Ub, U, Ub, U)
+            up = [ovl(Ub, U, mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)]
+            un = [ovl(Ub, U, mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)]
+            pu = [ovl(nuc_pos_basis[a], nuc_pos_wfn[a], Ub, U) for a in range(n3)]
+            nu = [ovl(nuc_neg_basis[a], nuc_neg_wfn[a], Ub, U) for a in range(n3)]
+        pp = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
+        pn = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
+        np_ = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
+        nn = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
+        done = mo_overlaps_dev(jobs)
+        if so:
+            done = [spin_block_2_dev(S) for S in done]
+        # one device->host copy per dtype group would need a second bookkeeping pass; the matrices are nbf^2
+        host = [to_host(S) for S in done]
+        get = lambda x: [get(y) for y in x] if isinstance(x, list) else host[x]
+        if not rhf:
+            self.overlap_uu, self.overlap_up, self.overlap_un = get(uu), get(up), get(un)
+            self.overlap_pu, self.overlap_nu = get(pu), get(nu)
+        self.overlap_pp, self.overlap_pn, self.overlap_np, self.overlap_nn = get(pp), get(pn), get(np_), get(nn)
         self._cache = {}
 
     @classmethod
@@ -327,8 +399,23 @@ class AAT(object):
         """Contributions of a STACK of overlap matrices for nx bra and ny ket amplitude sets, all
         launches batched over the stack.  Returns one dict per overlap of [nx, ny] numpy arrays
         (before the +/- sign and the N factors of S0/0S).  config.AAT_ALGORITHM selects how the
-        substituted determinants are evaluated: "lu" (sub-warp LU of every n x n matrix,
-        csrc/dets.cu) or "lemma" (<= 4 x 4 determinants from S_oo^-1, csrc/lemma.cu)."""
+        substituted determinants are evaluated: "lu" (LU of every n x n matrix, csrc/dets_tpm.cu /
+        dets.cu), "lemma" (<= 4 x 4 determinants from S_oo^-1, csrc/lemma.cu) or "factorized".
+
+        The device part (`_blocks_device`: ~15 launches per overlap on the LU path) is a fixed launch
+        sequence for a given stack shape, so with config.AAT_USE_GRAPH it is captured once per shape as a
+        CUDA graph over static input buffers and replayed: the 12 (beta x pp/pn/np/nn) stacks of every
+        nuclear coordinate, and every later molecule of the same shape, cost one graph launch instead of
+        ~200 host-issued launches (the small-molecule assembly is launch-bound otherwise)."""
+        S = to_device(np.stack([np.asarray(x) for x in S_hosts]).astype(np.complex128), _C128)     # [nS, ns, ns]
+        nS, nx, ny = len(S_hosts), X2.shape[0], Y2.shape[0]
+        cisd = X1 is not None
+        flat, meta = _run_blocks(self, S, X1, X2, Y1, Y2)
+        return self._blocks_host(to_host(flat), meta, nS, nx, ny, cisd)
+
+    def _blocks_device(self, S, X1, X2, Y1, Y2):
+        """Device part of `_blocks`: returns (flat, meta) -- one flat complex128 device tensor holding det_S
+        of every overlap followed by all small result tensors, and meta = [(key, shape), ...]."""
         no, nf, nv = self.ndocc, self.nfzc, self.nbf - self.ndocc
         o = no - nf
         cisd = X1 is not None
@@ -336,8 +423,7 @@ class AAT(object):
         factorized = config.AAT_ALGORITHM == "factorized"
         T = _Tables.get(no, nf, nv)
         R0, R1, R2 = T.L
-        nS, ns = len(S_hosts), self.nbf
-        S = to_device(np.stack([np.asarray(x) for x in S_hosts]).astype(np.complex128), _C128)     # [nS, ns, ns]
+        nS, ns = S.shape[0], self.nbf
         nx, ny = X2.shape[0], Y2.shape[0]
         P, n1 = T.n2, T.n1
         cn = contract_new
@@ -437,15 +523,19 @@ class AAT(object):
             dd["sd3"] = cn("xia,sqia->sxq", X1, Gwy)
             dd["d0b"] = cn("sxjb,sjb->sx", uxp, A)
             dd["0db"] = cn("skc,sqkc->sq", B, wy)
-        # one device->host copy for all the small result tensors of the stack
+        # one flat tensor -> one device->host copy for all the small result tensors of the stack
         keys = list(dd)
         flat = torch.cat([dS.reshape(-1)] + [dd[k].reshape(-1) for k in keys])
-        fh = to_host(flat)
+        return flat, [(k, tuple(dd[k].shape)) for k in keys]
+
+    @staticmethod
+    def _blocks_host(fh, meta, nS, nx, ny, cisd):
+        """Host part of `_blocks`: signs, det(S_oo) factors and the assembly of the per-overlap terms."""
         dSh_all = fh[:nS]
         h, off = {}, nS
-        for k in keys:
-            n_el = dd[k].numel()
-            h[k] = fh[off:off + n_el].reshape(tuple(dd[k].shape))
+        for k, shape in meta:
+            n_el = int(np.prod(shape)) if len(shape) else 1
+            h[k] = fh[off:off + n_el].reshape(shape)
             off += n_el
         for k in ("c3", "c4", "ds1", "sd1"):          # closed forms are per det(S_oo), like c1f
             if k + "f" in h:

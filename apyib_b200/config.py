@@ -48,3 +48,8 @@ USE_TMA = True
 # columns last, lists sorted -> consecutive determinants share their leading panels).  Same results; False
 # factorises every matrix from scratch (what bench.py's roofline line for the LU kernel is quoted on).
 LU_REUSE = True
+
+# AAT assembly: replay the device part of every overlap stack (aats.AAT._blocks_device) from a CUDA graph
+# captured once per stack shape (static input buffers, private memory pool).  Same kernels, same order, same
+# results; removes the host launch overhead that bounds small molecules (~200 launches per stack on the LU path).
+AAT_USE_GRAPH = False

@@ -185,6 +185,29 @@ def mo_overlap_dev(C_bra, S_ao, C_ket):
     return contract_new("mp,mq->pq", Cb, tmp, conj_a=True)
 
 
+def mo_overlaps_dev(triples):
+    """[C_bra^H S_AO C_ket for (C_bra, S_AO, C_ket) in triples] with TWO batched contraction launches per
+    dtype group (real / complex) instead of two per matrix: the finite-difference AAT needs 1 + 6 + 6N + 36N
+    overlaps of identical shape (aats.py:53-115).  Returns device tensors, float64 where all three inputs
+    are real (like numpy would), complex128 otherwise."""
+    out = [None] * len(triples)
+    groups = {}
+    # MO coefficients that came through the NCCL exchange are device tensors; they are nbf^2 and join the host stack
+    triples = [tuple(x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x) for x in t) for t in triples]
+    for k, t in enumerate(triples):
+        cplx = any(np.iscomplexobj(x) for x in t)
+        groups.setdefault((cplx, np.shape(t[0]), np.shape(t[1]), np.shape(t[2])), []).append(k)
+    for (cplx, _, _, _), idx in groups.items():
+        dt, npdt = (torch.complex128, np.complex128) if cplx else (torch.float64, np.float64)
+        stack = lambda j: to_device(np.stack([np.asarray(triples[k][j]) for k in idx]).astype(npdt, copy=False), dt)
+        Cb, S, Ck = stack(0), stack(1), stack(2)
+        tmp = contract_new("smn,snq->smq", S, Ck)
+        res = contract_new("smp,smq->spq", Cb, tmp, conj_a=True)
+        for j, k in enumerate(idx):
+            out[k] = res[j]
+    return out
+
+
 def compute_mo_overlap(ndocc, nbf, bra_basis, bra_wfn, ket_basis, ket_wfn, ao_overlap=None):
     """Reference signature plus an explicit AO overlap: Psi4's mixed-basis `ao_overlap` is a host
     input (the integral provider supplies it)."""

@@ -101,6 +101,35 @@ def test_so_aats_vs_oracle(method, nbf, no, nf, seed, norm):
     assert np.abs(got - g).max() < 1e-8 * max(1.0, np.abs(g).max())
 
 
+@pytest.mark.parametrize("method", ["CISD", "CID"])
+def test_block_graph_replay_is_bit_identical_to_eager(method, algo):
+    """config.AAT_USE_GRAPH: the device part of every overlap stack replayed from a CUDA graph (captured at the
+    second sight of a stack shape, static input buffers) must give exactly the eager results -- for the stack
+    it was captured on AND for later molecules of the same shape with different overlaps and amplitudes."""
+    import apyib_b200
+    from apyib_b200 import aats
+    cfg = apyib_b200.config
+    mols = [orc.synthetic_aat_inputs(method, 7, 3, 1, 1, 520 + k, h=1e-3) for k in range(3)]
+    full = lambda A: (lambda G: np.array([[G.compute_spatial_aats(a, b) for b in range(3)] for a in range(3)]))(gpu_aat(A))
+    old = cfg.AAT_USE_GRAPH
+    try:
+        cfg.AAT_USE_GRAPH = False
+        eager = [full(A) for A in mols]
+        cfg.AAT_USE_GRAPH = True
+        aats._block_graphs.clear()
+        got = [full(A) for A in mols]          # molecule 0: warm + capture + replay; 1, 2: replays on new inputs
+        states = list(aats._block_graphs.values())
+        assert states and all(isinstance(g, aats._BlockGraph) for g in states), states
+        for e, g in zip(eager, got):
+            assert np.array_equal(e, g)
+        assert np.abs(got[0] - got[1]).max() > 0          # the replays really saw different inputs
+        want = np.array([[orc.compute_spatial_aats(mols[2], a, b) for b in range(3)] for a in range(3)])
+        assert np.abs(got[2] - want).max() < 1e-8 * max(1.0, np.abs(want).max())
+    finally:
+        cfg.AAT_USE_GRAPH = old
+        aats._block_graphs.clear()
+
+
 # ---- end to end on the reference's (H2)_2 molecule ------------------------------------------
 def _params(c):
     return dict(c["parameters"], geom=LIT["geom"], F_el=[0.0] * 3, F_mag=[0.0] * 3)
