@@ -11,7 +11,8 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libapyib_b200.so")
 SOURCES = ["contract.cu", "contract_tma.cu", "stream.cu", "dets.cu", "dets_tpm.cu", "lemma.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+OBJDIR = os.path.join(LIBDIR, "obj")
 
 
 def _stale():
@@ -25,16 +26,31 @@ def _stale():
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    flags = NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):                      # one nvcc per translation unit, all of them concurrently
+        obj = os.path.join(OBJDIR, os.path.splitext(src)[0] + ".o")
+        res = subprocess.run([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, res
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed compiling %s" % src)
+        if verbose:
+            print(res.stdout + res.stderr)
+    tmp = LIB + ".tmp"
+    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-shared"] + [obj for _, obj, _ in results] + ["-o", tmp],
+                         capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libapyib_b200.so")
-    if verbose:
-        print(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libapyib_b200.so")
+    os.replace(tmp, LIB)
     return LIB
 
 
