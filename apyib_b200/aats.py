@@ -153,7 +153,8 @@ class _BlockGraph:
         self.inp = [None if t is None else t.clone() for t in inputs]
         self.graph = torch.cuda.CUDAGraph()
         n0 = _liblaunch[0]
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads (NCCL watchdog, bench clock sampler) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.flat, self.meta = aat._blocks_device(*self.inp)
         self.launches = _liblaunch[0] - n0
         _liblaunch[0] = n0                                   # recorded, not executed

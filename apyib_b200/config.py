@@ -1,4 +1,5 @@
 """Runtime switches of the drop-in layer."""
+import os as _os
 
 # Replay iterations 2.. of the CI solvers from one captured CUDA graph.
 USE_CUDA_GRAPH = True
@@ -52,4 +53,4 @@ LU_REUSE = True
 # AAT assembly: replay the device part of every overlap stack (aats.AAT._blocks_device) from a CUDA graph
 # captured once per stack shape (static input buffers, private memory pool).  Same kernels, same order, same
 # results; removes the host launch overhead that bounds small molecules (~200 launches per stack on the LU path).
-AAT_USE_GRAPH = False
+AAT_USE_GRAPH = _os.environ.get("APYIB_B200_AAT_GRAPH", "0") == "1"

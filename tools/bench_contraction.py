@@ -59,11 +59,11 @@ for O, V in ((20, 80),) + (() if quick else ((40, 160),)):
     run("ladder SO (%d,%d)" % (O, V), "abcd,ijcd->ijab", (V, V, V, V), (O, O, V, V), (O, O, V, V), c128)
     run("ring SO (%d,%d)" % (O, V), "kbcj,ikac->ijab", (O, V, V, O), (O, O, V, V), (O, O, V, V), c128)
     run("oooo SO (%d,%d)" % (O, V), "klij,klab->ijab", (O, O, O, O), (O, O, V, V), (O, O, V, V), c128)
-# upper half of the config-5 sweep (--big): nso = 300 (O=60,V=240) whole, nso = 400 (O=80,V=320) as one quarter of the
-# <ab||cd> rows (a < V/4): the full V^4 block is 168 GB complex128, and the ladder is row-separable, so the kernel
-# sees the same N, K and tile stream; flops and time both cover the quarter.
+# upper half of the config-5 sweep (--big): nso = 300 (O=60,V=240) whole, nso = 400 (O=80,V=320) as one eighth of the
+# <ab||cd> rows (a < V/8): the full V^4 block is 168 GB complex128, and the ladder is row-separable, so the kernel
+# sees the same N, K and tile stream; flops and time both cover that slice.
 if "--big" in sys.argv:
-    for O, V, frac in ((60, 240, 1), (80, 320, 4)):
+    for O, V, frac in ((60, 240, 1), (80, 320, 8)):
         run("ladder SO (%d,%d)%s" % (O, V, "" if frac == 1 else " rows a<V/%d" % frac), "abcd,ijcd->ijab",
             (V // frac, V, V, V), (O, O, V, V), (O, O, V // frac, V), c128, reps=2)
         torch.cuda.empty_cache()
