@@ -142,6 +142,7 @@ def _vdot(x, y, conj_x=True):
 # -------------------------------------------------------------------------------------------------
 _block_graphs = {}          # stack shape -> _BlockGraph | "warm" (seen once, eager) | None (not capturable)
 GRAPH_MAX_BYTES = 256 << 20
+GRAPH_MAX_LIVE = 24
 
 
 class _BlockGraph:
@@ -184,6 +185,9 @@ def _run_blocks(aat, S, X1, X2, Y1, Y2):
         _block_graphs[key] = "warm"
         return aat._blocks_device(*inputs)
     if g == "warm":
+        live = [k for k, v in _block_graphs.items() if isinstance(v, _BlockGraph)]
+        if len(live) >= GRAPH_MAX_LIVE:                      # bound the memory held by private graph pools
+            _block_graphs.pop(live[0])
         try:
             g = _BlockGraph(aat, inputs)
         except Exception as exc:                             # not capturable here: stay eager for this shape
@@ -551,7 +555,7 @@ class AAT(object):
             c1 = g("c1")
             if "c1f" in h:                    # factorised: 16 x (restricted double sum) / det(S_oo)
                 c1 = dSh * h["c1f"][s] / 16.0
-            out = {"DD": 0.125 * (dSh * c1 + v1 * v2 + 4 * g("c3") + 2 * g("c4") + 8 * g("c6"))}
+            out = {"dS": dSh, "DD": 0.125 * (dSh * c1 + v1 * v2 + 4 * g("c3") + 2 * g("c4") + 8 * g("c6"))}
             if cisd:
                 xA, yB = g("s_xA").reshape(nx, 1), g("s_yB").reshape(1, ny)
                 out["SS"] = 2 * (dSh * g("s_xGy") + xA * yB)
@@ -625,9 +629,9 @@ class AAT(object):
             return complex(to_host(_det_outer(to_device(np.asarray(S), _C128), no, R0, R0))[0, 0]) ** 2
 
         a, b = alpha, beta
-        I["00"] = (d2(self.overlap_pp[a][b]) * N_np[a] * N_mp[b] - d2(self.overlap_pn[a][b]) * N_np[a] * N_mn[b]
-                   - d2(self.overlap_np[a][b]) * N_nn[a] * N_mp[b] + d2(self.overlap_nn[a][b]) * N_nn[a] * N_mn[b])
         if m == "RHF":
+            I["00"] = (d2(self.overlap_pp[a][b]) * N_np[a] * N_mp[b] - d2(self.overlap_pn[a][b]) * N_np[a] * N_mn[b]
+                       - d2(self.overlap_np[a][b]) * N_nn[a] * N_mp[b] + d2(self.overlap_nn[a][b]) * N_nn[a] * N_mn[b])
             return I
         cisd = m == "CISD"
         amps = self._spatial_amps(normalization)
@@ -667,6 +671,9 @@ class AAT(object):
                                                               self.overlap_nn)]
             self._cache[key] = self._blocks(stack, pick(A1, "tc"), A2["tc"], pick(A1, "t"), A2["t"])
         r4 = self._cache[key][4 * b:4 * b + 4]
+        # I_00 (aats.py:672-677) from det(S_oo) of the same four overlaps, which their stack has already evaluated
+        I["00"] = (r4[0]["dS"] ** 2 * N_np[a] * N_mp[b] - r4[1]["dS"] ** 2 * N_np[a] * N_mn[b]
+                   - r4[2]["dS"] ** 2 * N_nn[a] * N_mp[b] + r4[3]["dS"] ** 2 * N_nn[a] * N_mn[b])
         add(r4[0], +1, 0, 0, s0_N=N_mp[b], os_N=N_np[a], d0=True, od=True)
         add(r4[1], -1, 0, 0, s0_N=N_mn[b], os_N=N_np[a], d0=True, od=True)
         add(r4[2], -1, 0, 0, s0_N=N_mp[b], os_N=N_nn[a], d0=True, od=True)

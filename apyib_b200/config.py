@@ -52,5 +52,6 @@ LU_REUSE = True
 
 # AAT assembly: replay the device part of every overlap stack (aats.AAT._blocks_device) from a CUDA graph
 # captured once per stack shape (static input buffers, private memory pool).  Same kernels, same order, same
-# results; removes the host launch overhead that bounds small molecules (~200 launches per stack on the LU path).
-AAT_USE_GRAPH = _os.environ.get("APYIB_B200_AAT_GRAPH", "0") == "1"
+# results; removes the host launch overhead of ~200 launches per stack on the LU path (H2O2/6-31G shape: 0.2045 -> 0.196 s
+# per molecule; the step is then bound by the determinant kernels).
+AAT_USE_GRAPH = _os.environ.get("APYIB_B200_AAT_GRAPH", "1") == "1"
