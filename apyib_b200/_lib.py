@@ -50,6 +50,9 @@ SIGNATURES = {
     "apyib_pack_doubles": (_int, [_vp, _i64, _int, _int, _int, _int, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec_work_len": (_i64, [_i64, _i64, _int, _int]),
     "apyib_det_set_kernel": (_int, [_int]),
+    "apyib_det_matvec_pairs_work_len": (_i64, [_i64, _i64, _int, _int, _int, _int, _int]),
+    "apyib_det_matvec_pairs": (_int, [_vp, _int, _int, _int, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _int, _vp, _int,
+                                      _vp, _vp, _vp]),
     "apyib_det_sort_lists": (_int, [_int, _i32p, _i64, _i32p, _f64p, _i32p]),
     "apyib_det_outer_sorted": (_int, [_vp, _int, _int, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec_sorted": (_int, [_vp, _int, _int, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _int, _vp, _vp, _vp]),
@@ -71,17 +74,25 @@ class ApyibB200Error(RuntimeError):
     pass
 
 
+def _bind(path):
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
 def _load():
     path = _build.LIB
     if not os.path.exists(path):
         # built in-tree by __graft_entry__.build(); try once here (nvcc is part of the image)
         path = _build.build()
-    lib = C.CDLL(path)
-    for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)          # AttributeError if the .so is stale -> loud failure
-        fn.restype = res
-        fn.argtypes = args
-    return lib
+    try:
+        return _bind(path)
+    except AttributeError:
+        # a library from an older source tree: rebuild once, then fail loudly if a symbol is still missing
+        return _bind(_build.build(force=True))
 
 
 lib = _load()
@@ -92,7 +103,7 @@ _KERNELS_PER_CALL = {
     "apyib_contract": 1, "apyib_contract_tma": 1, "apyib_gather4": 1, "apyib_gather2": 1, "apyib_mp2_t2_energy": 2, "apyib_ci_update": 1,
     "apyib_symmetrize_ijab": 1, "apyib_dots": 1, "apyib_diis_push": 1, "apyib_diis_solve": 1,
     "apyib_lincomb_energy_rms": 1, "apyib_iter_advance": 1, "apyib_copy": 1, "apyib_axpby": 1,
-    "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_det_outer_sorted": 1, "apyib_det_matvec_sorted": 2, "apyib_pack_doubles": 1,
+    "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_det_outer_sorted": 1, "apyib_det_matvec_sorted": 2, "apyib_det_matvec_pairs": 2, "apyib_pack_doubles": 1,
     "apyib_lemma_prepare": 1, "apyib_lemma_outer": 1, "apyib_lemma_matvec": 2,
 }
 LAUNCHES = [0]

@@ -61,6 +61,7 @@ class _Tables:
         # column-side lists re-ordered for factorisation reuse in the thread-per-matrix LU kernel
         # (substituted columns last, lists sorted; include/apyib_b200.h: apyib_det_sort_lists)
         self.LS = [None, None, None]
+        self.PFX = [None, None, None]       # (group_len, candidate columns) when the sorted lists have the group structure
         if 2 <= no <= 12:
             for k, cnt in ((1, self.n1), (2, self.n2)):
                 if not cnt:
@@ -72,8 +73,34 @@ class _Tables:
                 check(lib.apyib_det_sort_lists(no, _i32_host(src)[1], cnt, _i32_host(srt)[1],
                                                sign.ctypes.data_as(C.POINTER(C.c_double)), _i32_host(idx)[1]))
                 self.LS[k] = tuple(torch.from_numpy(x.copy()).to(device()) for x in (srt, sign, idx))
+                self.PFX[k] = self._prefix_groups(srt, no, k)
         self.doubles_dev = torch.from_numpy(self.doubles.copy()).to(device())
         self.singles_dev = torch.from_numpy(self.singles.copy()).to(device())
+
+    @staticmethod
+    def _prefix_groups(srt, n, k):
+        """Structure the prefix-shared LU kernel (csrc/dets_pairs.cu) relies on, verified on the host: the sorted
+        lists come in groups of consecutive lists sharing their first n-k columns and ending in every candidate
+        column (k = 1) / every pair c < d in lexicographic order (k = 2) of one ascending candidate set."""
+        if n <= k or len(srt) == 0:
+            return None
+        cand = np.unique(srt[:, n - k:])
+        nc = len(cand)
+        if k == 1:
+            tails = cand.reshape(-1, 1)
+        else:
+            if nc < 2:
+                return None
+            tails = np.array([(cand[x], cand[y]) for x in range(nc) for y in range(x + 1, nc)], dtype=srt.dtype)
+        gl = len(tails)
+        if len(srt) % gl:
+            return None
+        grp = srt.reshape(-1, gl, n)
+        if not (np.array_equal(grp[:, :, :n - k], np.repeat(grp[:, :1, :n - k], gl, axis=1))
+                and np.array_equal(grp[:, :, n - k:], np.broadcast_to(tails, (grp.shape[0], gl, k)))
+                and (grp[:, :, :n - k] < n).all() and (cand >= n).all()):
+            return None
+        return gl, torch.from_numpy(np.ascontiguousarray(cand, dtype=np.int32)).to(device()), nc
 
     @staticmethod
     def get(no, nf, nv):
@@ -95,14 +122,28 @@ def _det_outer(S, n, rows, cols, sorted_cols=None):
     return out
 
 
-def _det_matvec(S, n, rows, cols, Y, sorted_cols=None):
-    """Z[q, r] = sum_c det(S[rows[r], cols[c]]) Y[q, c]; any number of vectors (<= 4 per launch)."""
+def _det_matvec(S, n, rows, cols, Y, sorted_cols=None, prefix=None, k=0):
+    """Z[q, r] = sum_c det(S[rows[r], cols[c]]) Y[q, c]; any number of vectors (<= 4 per launch).
+    prefix = (group_len, candidate columns, nc) of a k-fold substituted table routes the launch to the
+    prefix-shared LU kernel (config.LU_PREFIX)."""
     use_sorted = sorted_cols is not None and config.LU_REUSE
+    use_prefix = use_sorted and prefix is not None and config.LU_PREFIX
     Y = Y.contiguous()
     nq, nrow, ncol = Y.shape[0], rows.shape[0], cols.shape[0]
     Z = empty((nq, nrow), _C128)
     for q0 in range(0, nq, 4):
         q1 = min(nq, q0 + 4)
+        if use_prefix:
+            gl, cand, nc = prefix
+            cs, sg, ix = sorted_cols
+            work = empty((int(lib.apyib_det_matvec_pairs_work_len(nrow, ncol // gl, q1 - q0, n, k, S.shape[0], nc)),), _C128)
+            with config.timed("det_pairs[n=%d,k=%d,%dx%d]" % (n, k, nrow, ncol)):
+                rc = lib.apyib_det_matvec_pairs(ptr(S), S.shape[0], n, k, ptr(rows), nrow, ptr(cs), ptr(sg), ptr(ix), ncol, gl,
+                                                ptr(cand), nc, ptr(Y[q0:q1]), q1 - q0, ptr(Z[q0:q1]), ptr(work), stream_ptr())
+            if rc == 0:
+                continue
+            if rc != -3:          # APYIB_ERR_UNSUPPORTED -> the general kernel below
+                check(rc)
         work = empty((int(lib.apyib_det_matvec_work_len(nrow, ncol, q1 - q0, n)),), _C128)
         with config.timed("det_matvec[n=%d,%dx%d]" % (n, nrow, ncol)):
             if use_sorted:
@@ -177,7 +218,7 @@ def _run_blocks(aat, S, X1, X2, Y1, Y2):
     nS, nx, ny = S.shape[0], X2.shape[0], Y2.shape[0]
     if 16 * o * o * nv * nv * nS * (nx + ny + nx * ny) > GRAPH_MAX_BYTES:
         return aat._blocks_device(*inputs)                   # large shapes are not launch-bound; keep the pool small
-    key = (config.AAT_ALGORITHM, config.LU_REUSE, config.USE_TMA, aat.nbf, aat.ndocc, aat.nfzc, nS, nx, ny, X1 is not None,
+    key = (config.AAT_ALGORITHM, config.LU_REUSE, config.LU_PREFIX, config.USE_TMA, aat.nbf, aat.ndocc, aat.nfzc, nS, nx, ny, X1 is not None,
            tuple(X2.shape), tuple(Y2.shape), torch.cuda.current_device())
     g = _block_graphs.get(key, "new")
     if g == "new":
@@ -470,7 +511,7 @@ class AAT(object):
                 return torch.stack([_det_outer(S[s], no, L[rk], L[ck], T.LS[ck]) for s in range(nS)])
 
             def matvec(rk, ck, Y, per_overlap):
-                return torch.stack([_det_matvec(S[s], no, L[rk], L[ck], Y[s] if per_overlap else Y, T.LS[ck])
+                return torch.stack([_det_matvec(S[s], no, L[rk], L[ck], Y[s] if per_overlap else Y, T.LS[ck], T.PFX[ck], ck)
                                     for s in range(nS)])
 
         dS = outer(0, 0).reshape(nS)                                     # det_S

@@ -50,6 +50,12 @@ USE_TMA = True
 # factorises every matrix from scratch (what bench.py's roofline line for the LU kernel is quoted on).
 LU_REUSE = True
 
+# LU path: evaluate the fused table x vector products of singly / doubly column-substituted tables with the
+# prefix-shared LU kernel (csrc/dets_pairs.cu): one pivoted LU of the n-k unsubstituted columns per (row list,
+# group), one Schur-complement k-vector per candidate column, k x k determinants per list.  Same quantity as the
+# per-matrix LU (agreement ~1e-15 relative, not bitwise: the trailing k x k block is written out).
+LU_PREFIX = _os.environ.get("APYIB_B200_LU_PREFIX", "1") == "1"
+
 # AAT assembly: replay the device part of every overlap stack (aats.AAT._blocks_device) from a CUDA graph
 # captured once per stack shape (static input buffers, private memory pool).  Same kernels, same order, same
 # results; removes the host launch overhead of ~200 launches per stack on the LU path (H2O2/6-31G shape: 0.2045 -> 0.196 s

@@ -202,6 +202,12 @@ int launch_det_tpm(int n, cudaStream_t st, const cplx *S, int ns, const int32_t 
                    const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const double *csign,
                    const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer);
 int tpm_total_warps(int n);
+// prefix-shared LU (dets_pairs.cu), n <= 12, k = 1 or 2 trailing substituted columns
+int launch_det_pairs(int n, int k, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
+                     const int32_t *cols, int64_t ngroup, int64_t npair, const int32_t *cand, int nc, int64_t gchunk,
+                     int64_t nchunk, const double *csign, const int32_t *cindex, const cplx *Y, int ny, int64_t ncol,
+                     cplx *out);
+int pairs_total_warps(int n, int k, int ns, int nc);
 constexpr int kTpmMaxN = 12;
 static int g_det_kernel = 0;   // 0 = thread-per-matrix for 2 <= n <= 12, sub-warp above; 1 = sub-warp always
 static bool use_tpm(int n) { return g_det_kernel == 0 && n >= 2 && n <= kTpmMaxN; }
@@ -330,6 +336,50 @@ extern "C" int apyib_det_matvec_sorted(const void *d_S, int ns, int n, const int
                                        int64_t ncol, const void *d_Y, int ny, void *d_Z, void *d_work, void *stream) {
     APYIB_REQUIRE(d_col_sign && d_col_index, "null pointer");
     return det_matvec_impl(d_S, ns, n, d_rows, nrow, d_cols, ncol, d_col_sign, d_col_index, d_Y, ny, d_Z, d_work, stream);
+}
+
+static int64_t pairs_nchunk(int64_t nrow, int64_t ngroup, int n, int k, int ns, int nc) {
+    const int w = pairs_total_warps(n, k, ns, nc);
+    if (w <= 0) return 0;
+    return chunks_for((nrow + 31) / 32, ngroup, w, 4096);
+}
+
+extern "C" int64_t apyib_det_matvec_pairs_work_len(int64_t nrow, int64_t ngroup, int ny, int n, int k, int ns, int nc) {
+    const int64_t c = pairs_nchunk(nrow, ngroup, n, k, ns, nc);
+    return (c > 0 ? c : 1) * ny * nrow;
+}
+
+extern "C" int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,
+                                      const int32_t *d_cols_sorted, const double *d_col_sign,
+                                      const int32_t *d_col_index, int64_t ncol, int64_t group_len,
+                                      const int32_t *d_cand, int nc, const void *d_Y, int ny, void *d_Z, void *d_work,
+                                      void *stream) {
+    APYIB_REQUIRE(d_S && d_rows && d_cols_sorted && d_col_sign && d_col_index && d_cand && d_Y && d_Z && d_work, "null pointer");
+    APYIB_REQUIRE(ny >= 1 && ny <= 4, "1 <= ny <= 4");
+    APYIB_REQUIRE((k == 1 || k == 2) && n > k && ns >= n && nc >= k, "sizes");
+    APYIB_REQUIRE(group_len == (k == 1 ? (int64_t)nc : (int64_t)nc * (nc - 1) / 2), "group_len must be nc (k=1) or C(nc,2) (k=2)");
+    APYIB_REQUIRE(nrow >= 1 && ncol >= group_len && ncol % group_len == 0, "ncol must be a whole number of groups");
+    if (n > kTpmMaxN || g_det_kernel != 0) {
+        set_error("prefix-shared LU needs 2 <= n <= 12 and the thread-per-matrix kernel family");
+        return APYIB_ERR_UNSUPPORTED;
+    }
+    const int64_t ngroup = ncol / group_len;
+    const int64_t nchunk = pairs_nchunk(nrow, ngroup, n, k, ns, nc);
+    if (nchunk <= 0) {
+        set_error("prefix-shared LU: (n, k) = (%d, %d) with %d candidate columns does not fit", n, k, nc);
+        return APYIB_ERR_UNSUPPORTED;
+    }
+    const int64_t gchunk = (ngroup + nchunk - 1) / nchunk;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_det_pairs(n, k, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols_sorted, ngroup, group_len, d_cand, nc,
+                              gchunk, nchunk, d_col_sign, d_col_index, (const cplx *)d_Y, ny, ncol, (cplx *)d_work);
+    if (rc != APYIB_OK) return rc;
+    const int64_t len = (int64_t)ny * nrow;
+    int64_t b = (len + 7) / 8;
+    if (b > 148 * 8) b = 148 * 8;
+    chunk_reduce_kernel<<<(unsigned)b, 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
 }
 
 // Re-orders column index lists for factorisation reuse (host): inside every list the substituted entries

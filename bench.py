@@ -338,7 +338,10 @@ def main():
 
     if args.profile_step:
         timed_steps(max(1, args.warmup), True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()          # ncu --profile-from-start off: only this step is captured
         t, _ = timed_steps(1, True)
+        torch.cuda.profiler.stop()
         if rank == 0:
             print(json.dumps({"profile_step_s": t, "launches": _lib.LAUNCHES[0]}))
         return
@@ -352,7 +355,7 @@ def main():
     # kernels timed live (CUDA events on the launching stream): the LU kernel, or for the closed-form
     # algorithms the lemma kernel and the TMA-fed contractions (ladder); launches replayed from a CUDA
     # graph cannot carry events, so for those only the eager first iteration of every solve is timed
-    apyib_b200.config.TIMING_ONLY = "det_matvec" if args.aat_algorithm == "lu" else ("lemma_matvec", "contract_tma[")
+    apyib_b200.config.TIMING_ONLY = ("det_matvec", "det_pairs") if args.aat_algorithm == "lu" else ("lemma_matvec", "contract_tma[")
     _lib.LAUNCHES[0] = 0
     t_dev, I_dev = timed_steps(args.steps, True)
     launches = _lib.LAUNCHES[0] // max(args.steps, 1)
@@ -408,7 +411,32 @@ def main():
         share = (sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / timing_steps) / (t_dev / args.steps)
         n = wl["ndocc"]
         extra = {}
-        if name.startswith("det_matvec"):
+        if name.startswith("det_pairs"):
+            # prefix-shared LU (csrc/dets_pairs.cu): one pivoted LU of the n-k unsubstituted columns per (row list,
+            # group), one Schur k-vector per candidate column, k x k determinants per list
+            k_sub = int(name.split("k=")[1].split(",")[0])
+            nrow, ncol = (int(x) for x in name.split(",")[2].rstrip("]").split("x"))
+            ndet = nrow * ncol
+            nc = wl["nbf"] - n
+            gl = nc if k_sub == 1 else nc * (nc - 1) // 2
+            npre = n - k_sub
+            cmac = (sum((n - 1 - j) * (npre - j) for j in range(npre))          # prefix LU: L column + trailing update
+                    + k_sub * npre * (npre - 1) // 2 + k_sub * npre               # X = -L21 L11^-1
+                    + nc * k_sub * npre                                          # candidate columns
+                    + (gl * 4 + 2 * nc if k_sub == 2 else 2 * gl))               # k x k determinants + table x vector
+            exec_flops = nrow * (ncol // gl) * cmac * 8.0
+            flops = ndet * (8.0 / 3.0) * n ** 3
+            kern = "det_pairs_kernel<N=%d,K=%d> (prefix-shared LU + table x vector) " % (n, k_sub)
+            extra = {"determinants_per_s": ndet / (avg_ms * 1e-3), "executed_tflops": exec_flops / (avg_ms * 1e-3) / 1e12,
+                     "executed_frac": exec_flops / (avg_ms * 1e-3) / 1e12 / fp64_peak,
+                     "executed_complex_macs_per_determinant": cmac / gl}
+            note = ("FP64 compute roofline (LU on the FP64 FMA pipe); achieved = ALGORITHMIC (8/3)n^3 flops per determinant "
+                    "(SURVEY 8d U3) / measured time, so frac > 1 measures the algorithmic saving of sharing the prefix "
+                    "factorisation inside a group (%.1f complex MACs per determinant instead of n^3/3 = %.0f); executed_frac "
+                    "is the FP64-pipe utilisation on the flops really executed; peak = own DMMA/DFMA microbenchmark "
+                    "measured in this run (MEASURED_PEAKS.json holds bf16/HBM only, %s)" % (cmac / gl, n ** 3 / 3.0, peak_src))
+            tkey = "det_pairs_kernel"
+        elif name.startswith("det_matvec"):
             nrow, ncol = (int(x) for x in name.split(",")[1].rstrip("]").split("x"))
             ndet = nrow * ncol
             kern = "det_tpm_kernel<N=%d,B=3> (fused LU + table x vector) " % n if n <= 12 else "det_kernel<N=%d,fused> " % n

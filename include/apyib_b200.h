@@ -226,6 +226,22 @@ int apyib_det_outer_sorted(const void *d_S, int ns, int n, const int32_t *d_rows
 int apyib_det_matvec_sorted(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow,
                             const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
                             int64_t ncol, const void *d_Y, int ny, void *d_Z, void *d_work, void *stream);
+/* Prefix-shared LU (csrc/dets_pairs.cu): the re-ordered lists of a singly (k = 1) or doubly (k = 2)
+ * substituted table come in GROUPS of `group_len` consecutive lists that share their first n-k columns
+ * (the unsubstituted ones) and end in every candidate column (k = 1) / every pair c < d (k = 2,
+ * lexicographic) of the nc columns d_cand[] (ascending) -- what apyib_det_sort_lists produces for the
+ * enumeration of aats.py:581-618.  The prefix is factorised ONCE per (row list, group) with partial
+ * pivoting; every candidate column then costs one k-vector of the Schur complement (n k complex MACs) and
+ * every determinant of the group a k x k determinant of those vectors.  Same quantity as
+ * apyib_det_matvec_sorted (Z[q,r] = sum_c det(r,c) Y[q,c], Y indexed by the ORIGINAL enumeration), ~12x
+ * fewer flops at n = 9, nc = 13.  Replaces the same np.linalg.det calls (aats.py:587-618).  Returns
+ * APYIB_ERR_UNSUPPORTED when (n, k) is not instantiated (2 <= n <= 12) or the footprint does not fit.
+ * d_work: apyib_det_matvec_pairs_work_len(...) complex128 elements.                                      */
+int64_t apyib_det_matvec_pairs_work_len(int64_t nrow, int64_t ngroup, int ny, int n, int k, int ns, int nc);
+int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,
+                           const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
+                           int64_t ncol, int64_t group_len, const int32_t *d_cand, int nc, const void *d_Y, int ny,
+                           void *d_Z, void *d_work, void *stream);
 /* Which LU kernel apyib_det_outer / apyib_det_matvec launch: 0 (default) = one thread per matrix,
  * column panels in registers + L in shared memory, for 2 <= n <= 12 and the sub-warp kernel above
  * that; 1 = the sub-warp (one lane per row) kernel for every n.  Same results either way.       */

@@ -328,3 +328,52 @@ def test_contract_tma_batched_ladder():
     contract("sabcd,sijcd->sijab", dW, dt, dr, 0.5, 1.0)
     want = r + 0.5 * np.einsum("sabcd,sijcd->sijab", W, t2)
     assert np.abs(to_host(dr) - want).max() < 1e-11 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n,nv,nf", [(3, 4, 0), (4, 5, 1), (6, 3, 0), (7, 6, 2), (9, 5, 0), (9, 13, 0), (10, 4, 0), (12, 4, 1)])
+@pytest.mark.parametrize("kind", ["generic", "fd", "big_S"])
+def test_det_prefix_shared_lu_matches_per_matrix_lu(n, nv, nf, kind):
+    """csrc/dets_pairs.cu: one pivoted LU of the unsubstituted columns per (row list, group) + Schur-complement
+    vectors of the candidate columns  ==  an LU of every substituted matrix (numpy, and the thread-per-matrix
+    kernel), for singly (k = 1) and doubly (k = 2) substituted column tables, O(1) random overlaps (heavy
+    pivoting), finite-difference-like overlaps, and S too large for shared memory."""
+    import apyib_b200
+    from apyib_b200.aats import _Tables, _det_matvec
+    from apyib_b200.device import to_device, to_host
+    if kind == "big_S" and (n, nv) not in ((9, 5), (4, 5)):
+        pytest.skip("large-S variant checked for two sizes")
+    rng = np.random.default_rng(700 + 13 * n + nv)
+    ns = n + nv
+    pad = 110 if kind == "big_S" else 0               # ns^2 * 16 B > shared memory left over -> S through L1
+    h = 1e-4 if kind == "fd" else 0.3
+    S = np.eye(ns + pad) + h * (rng.standard_normal((ns + pad,) * 2) + 1j * rng.standard_normal((ns + pad,) * 2))
+    T = _Tables.get(n, nf, nv)
+    dS = to_device(S, torch.complex128)
+    cfg = apyib_b200.config
+    old = cfg.LU_PREFIX
+    try:
+        for ck in (1, 2):
+            if T.L[ck].shape[0] == 0:
+                continue
+            assert T.PFX[ck] is not None, "sorted lists must have the group structure"
+            gl, cand, nc = T.PFX[ck]
+            assert nc == nv and gl == (nv if ck == 1 else nv * (nv - 1) // 2)
+            for rk in (2, 1, 0):
+                rows, cols = T.L[rk], T.L[ck]
+                if rows.shape[0] == 0:
+                    continue
+                want_D = np.linalg.det(S[rows.cpu().numpy()[:, None, :, None], cols.cpu().numpy()[None, :, None, :]])
+                for ny in (1, 3):
+                    Y = rng.standard_normal((ny, cols.shape[0])) + 1j * rng.standard_normal((ny, cols.shape[0]))
+                    dY = to_device(Y, torch.complex128)
+                    want = Y @ want_D.T
+                    cfg.LU_PREFIX = False
+                    base = to_host(_det_matvec(dS, n, rows, cols, dY, T.LS[ck], T.PFX[ck], ck))
+                    cfg.LU_PREFIX = True
+                    got = to_host(_det_matvec(dS, n, rows, cols, dY, T.LS[ck], T.PFX[ck], ck))
+                    scale = max(np.abs(want).max(), 1e-300)
+                    tol = 1e-10 if kind != "fd" else 1e-9      # fd: O(h^k) determinants, relative to the largest
+                    assert np.abs(got - want).max() < tol * scale, (ck, rk, ny)
+                    assert np.abs(got - base).max() < tol * scale, (ck, rk, ny)
+    finally:
+        cfg.LU_PREFIX = old
