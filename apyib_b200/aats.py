@@ -391,19 +391,21 @@ class AAT(object):
             res = (1, [1] * n3, [1] * n3, [1] * 3, [1] * 3)
         else:
             cisd = m == "CISD"
-
-            def N(T):
-                t2 = _dev(T[2])
-                sw = zeros((1,), _C128)
-                contract("ijab,ijba->", t2, t2, sw.view(()), 1.0, 0.0, conj_a=True)
-                x = T[0] + (2 * _vdot(t2, t2) - complex(to_host(sw)[0]))
-                if cisd:
-                    t1 = _dev(T[1])
-                    x = x + 2 * _vdot(t1, t1)
-                return 1 / np.sqrt(x)
-
-            res = (N(self.unperturbed_T), [N(T) for T in self.nuc_pos_T], [N(T) for T in self.nuc_neg_T],
-                   [N(T) for T in self.mag_pos_T], [N(T) for T in self.mag_neg_T])
+            # all 6N+7 points as one stack: three batched dot-like contractions and ONE device->host copy
+            # (x = t0 + 2<t1|t1> + 2<t2|t2> - <t2|t2^T>, aats.py:652-669)
+            Ts = [self.unperturbed_T] + list(self.nuc_pos_T) + list(self.nuc_neg_T) + list(self.mag_pos_T) + list(self.mag_neg_T)
+            t2 = torch.stack([_dev(T[2]) for T in Ts])
+            npt = len(Ts)
+            acc = zeros((3, npt), _C128)
+            contract("sijab,sijab->s", t2, t2, acc[0], 1.0, 0.0, conj_a=True)
+            contract("sijab,sijba->s", t2, t2, acc[1], 1.0, 0.0, conj_a=True)
+            if cisd:
+                t1 = torch.stack([_dev(T[1]) for T in Ts])
+                contract("sia,sia->s", t1, t1, acc[2], 1.0, 0.0, conj_a=True)
+            h = to_host(acc)
+            Nall = [1 / np.sqrt(Ts[s][0] + (2 * complex(h[0, s]) - complex(h[1, s])) + (2 * complex(h[2, s]) if cisd else 0))
+                    for s in range(npt)]
+            res = (Nall[0], Nall[1:1 + n3], Nall[1 + n3:1 + 2 * n3], Nall[1 + 2 * n3:4 + 2 * n3], Nall[4 + 2 * n3:7 + 2 * n3])
         self._cache[key] = res
         return res
 
@@ -506,13 +508,56 @@ class AAT(object):
                 return Z
         else:
             L = {0: R0, 1: R1, 2: R2}
+            cnt = {0: 1, 1: n1, 2: P}
+            null = C.c_void_p(0)
+
+            def sorted_lists(ck):
+                """(column lists, sign, index) for table kind ck: re-ordered for factorisation reuse when available"""
+                if T.LS[ck] is not None and config.LU_REUSE:
+                    cs, sg, ix = T.LS[ck]
+                    return ptr(cs), ptr(sg), ptr(ix), True
+                return ptr(L[ck]), null, null, False
 
             def outer(rk, ck):
-                return torch.stack([_det_outer(S[s], no, L[rk], L[ck], T.LS[ck]) for s in range(nS)])
+                """D[s, r, c] for the whole stack in one launch (grid.y = overlap)"""
+                out = empty((nS, cnt[rk], cnt[ck]), _C128)
+                if cnt[rk] and cnt[ck]:
+                    cols, sg, ix, _ = sorted_lists(ck)
+                    check(lib.apyib_det_outer_stack(ptr(S), nS, ns, no, ptr(L[rk]), cnt[rk], cols, sg, ix, cnt[ck], ptr(out),
+                                                    stream_ptr()))
+                return out
 
             def matvec(rk, ck, Y, per_overlap):
-                return torch.stack([_det_matvec(S[s], no, L[rk], L[ck], Y[s] if per_overlap else Y, T.LS[ck], T.PFX[ck], ck)
-                                    for s in range(nS)])
+                """Z[s,q,r] = sum_c D_s[r,c] Y[(s,)q,c] for the whole stack, <= 4 vectors per launch"""
+                Y = Y.contiguous()
+                nq, nrow, ncol = Y.shape[-2], cnt[rk], cnt[ck]
+                Z = empty((nS, nq, nrow), _C128)
+                cols, sg, ix, is_sorted = sorted_lists(ck)
+                pfx = T.PFX[ck] if (is_sorted and config.LU_PREFIX) else None
+                for q0 in range(0, nq, 4):
+                    q1 = min(nq, q0 + 4)
+                    whole = q0 == 0 and q1 == nq
+                    Yq = Y if whole else Y[..., q0:q1, :].contiguous()
+                    Zq = Z if whole else empty((nS, q1 - q0, nrow), _C128)
+                    ystride = (q1 - q0) * ncol if per_overlap else 0
+                    rc = -3
+                    if pfx is not None:
+                        gl, cand, nc = pfx
+                        work = empty((nS * int(lib.apyib_det_matvec_pairs_work_len(nrow, ncol // gl, q1 - q0, no, ck, ns, nc)),), _C128)
+                        with config.timed("det_pairs[n=%d,k=%d,%dx%d,nS=%d]" % (no, ck, nrow, ncol, nS)):
+                            rc = lib.apyib_det_matvec_pairs_stack(ptr(S), nS, ns, no, ck, ptr(L[rk]), nrow, cols, sg, ix, ncol, gl,
+                                                                  ptr(cand), nc, ptr(Yq), ystride, q1 - q0, ptr(Zq), ptr(work),
+                                                                  stream_ptr())
+                        if rc not in (0, -3):      # -3 = APYIB_ERR_UNSUPPORTED -> the per-matrix LU below
+                            check(rc)
+                    if rc != 0:
+                        work = empty((nS * int(lib.apyib_det_matvec_work_len(nrow, ncol, q1 - q0, no)),), _C128)
+                        with config.timed("det_matvec[n=%d,%dx%d,nS=%d]" % (no, nrow, ncol, nS)):
+                            check(lib.apyib_det_matvec_stack(ptr(S), nS, ns, no, ptr(L[rk]), nrow, cols, sg, ix, ncol, ptr(Yq),
+                                                             ystride, q1 - q0, ptr(Zq), ptr(work), stream_ptr()))
+                    if Zq is not Z:
+                        Z[:, q0:q1].copy_(Zq)
+                return Z
 
         dS = outer(0, 0).reshape(nS)                                     # det_S
         A = outer(1, 0).reshape(nS, o, nv)                               # ia_S

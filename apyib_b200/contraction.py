@@ -89,8 +89,10 @@ def _plan(spec, A, B, out):
     # Tile shapes mirror apyib_contract's choice (csrc/contract.cu): 16-wide tiles for skinny sides.
     cplx = A.dtype == torch.complex128
     if M * N <= 16 and K >= 64:
-        # dot-product-like (contract_dot_kernel): one CTA of 256 threads per 4 Ki elements of k
-        ksplit = int(min(max(1, (K + 4095) // 4096), max(1, (4 * 148) // batch[0]), 65535 // batch[0]))
+        # dot-product-like (contract_dot_kernel): one CTA of 256 threads per 1 Ki elements of k -- every element
+        # costs a chain of two dependent gathers (offset table -> operand), so short per-thread trips hide the
+        # latency better than long ones (o^2 v^2 = 13689 at H2O2/6-31G: 34 -> ~12 us per contraction)
+        ksplit = int(min(max(1, (K + 1023) // 1024), 128, max(1, (4 * 148) // batch[0]), 65535 // batch[0]))
     else:
         if N <= 16 and M > 16:
             bm, bn = (64 if cplx else 128), 16

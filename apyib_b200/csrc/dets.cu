@@ -135,6 +135,8 @@ det_kernel(const cplx *__restrict__ S, int ns, int n, const int32_t *__restrict_
 // shuffle tree).  One warp per output element: the sum over up to 4096 chunks is spread over 32 lanes
 // instead of one thread walking it (32 us per call for the 117-row shapes before).
 __global__ void __launch_bounds__(256) chunk_reduce_kernel(const cplx *Zp, int nchunk, int64_t len, cplx *Z) {
+    Zp += (size_t)blockIdx.y * nchunk * len;                    // blockIdx.y = overlap of a stack
+    Z += (size_t)blockIdx.y * len;
     const int lane = threadIdx.x & 31;
     const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < len; i += nwarp) {
@@ -200,13 +202,14 @@ static int launch_det(int n, dim3 grid, cudaStream_t st, const cplx *S, int ns, 
 // thread-per-matrix LU (dets_tpm.cu), n <= 12
 int launch_det_tpm(int n, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
                    const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const double *csign,
-                   const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer);
+                   const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer, int nS, int64_t y_stride,
+                   int64_t out_stride);
 int tpm_total_warps(int n);
 // prefix-shared LU (dets_pairs.cu), n <= 12, k = 1 or 2 trailing substituted columns
 int launch_det_pairs(int n, int k, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
                      const int32_t *cols, int64_t ngroup, int64_t npair, const int32_t *cand, int nc, int64_t gchunk,
                      int64_t nchunk, const double *csign, const int32_t *cindex, const cplx *Y, int ny, int64_t ncol,
-                     cplx *out);
+                     cplx *out, int nS, int64_t y_stride, int64_t out_stride);
 int pairs_total_warps(int n, int k, int ns, int nc);
 constexpr int kTpmMaxN = 12;
 static int g_det_kernel = 0;   // 0 = thread-per-matrix for 2 <= n <= 12, sub-warp above; 1 = sub-warp always
@@ -233,15 +236,27 @@ extern "C" int apyib_det_set_kernel(int which) {
 }
 
 static int det_outer_impl(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow, const int32_t *d_cols,
-                          int64_t ncol, const double *d_csign, const int32_t *d_cindex, void *d_out, void *stream) {
+                          int64_t ncol, const double *d_csign, const int32_t *d_cindex, void *d_out, void *stream,
+                          int nS = 1) {
     APYIB_REQUIRE(d_S && d_rows && d_cols && d_out, "null pointer");
     APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
+    APYIB_REQUIRE(nS >= 1 && nS <= 65535, "stack size");
     if (nrow == 0 || ncol == 0) return APYIB_OK;
     if (use_tpm(n)) {
-        const int64_t nchunk = chunks_for((nrow + 31) / 32, ncol, tpm_total_warps(n), 1 << 20);
+        // a stack shares the device: size the chunks so that ALL overlaps together fill about one wave
+        const int64_t target = tpm_total_warps(n) / nS > 0 ? tpm_total_warps(n) / nS : 1;
+        const int64_t nchunk = chunks_for((nrow + 31) / 32, ncol, target, 1 << 20);
         const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
         return launch_det_tpm(n, (cudaStream_t)stream, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
-                              nchunk, d_csign, d_cindex, nullptr, 0, (cplx *)d_out, 1);
+                              nchunk, d_csign, d_cindex, nullptr, 0, (cplx *)d_out, 1, nS, 0, nrow * ncol);
+    }
+    if (nS > 1) {                                   // sub-warp kernel: one launch per overlap of the stack
+        for (int s = 0; s < nS; ++s) {
+            const int rc = det_outer_impl((const cplx *)d_S + (size_t)s * ns * ns, ns, n, d_rows, nrow, d_cols, ncol, d_csign,
+                                          d_cindex, (cplx *)d_out + (size_t)s * nrow * ncol, stream, 1);
+            if (rc != APYIB_OK) return rc;
+        }
+        return APYIB_OK;
     }
     if (d_csign || d_cindex) {
         set_error("sorted column lists need the thread-per-matrix LU kernel (2 <= n <= 12)");
@@ -281,7 +296,7 @@ extern "C" int64_t apyib_det_matvec_work_len(int64_t nrow, int64_t ncol, int ny,
 
 static int det_matvec_impl(const void *d_S, int ns, int n, const int32_t *d_rows, int64_t nrow, const int32_t *d_cols,
                            int64_t ncol, const double *d_csign, const int32_t *d_cindex, const void *d_Y, int ny,
-                           void *d_Z, void *d_work, void *stream) {
+                           void *d_Z, void *d_work, void *stream, int nS = 1, int64_t y_stride = 0) {
     APYIB_REQUIRE(d_S && d_rows && d_cols && d_Y && d_Z && d_work, "null pointer");
     if ((d_csign || d_cindex) && !use_tpm(n)) {
         set_error("sorted column lists need the thread-per-matrix LU kernel (2 <= n <= 12)");
@@ -289,26 +304,37 @@ static int det_matvec_impl(const void *d_S, int ns, int n, const int32_t *d_rows
     }
     APYIB_REQUIRE(n >= 1 && n <= 32 && ns >= n, "1 <= n <= 32 supported by the sub-warp LU");
     APYIB_REQUIRE(ny >= 1 && ny <= 4, "1 <= ny <= 4");
+    APYIB_REQUIRE(nS >= 1 && nS <= 65535, "stack size");
     if (nrow == 0) return APYIB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (ncol == 0) {
-        APYIB_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(cplx) * ny * nrow, st));
+        APYIB_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(cplx) * ny * nrow * nS, st));
         return APYIB_OK;
     }
     const int64_t gpb = groups_per_block(n);
     const int64_t rb = (nrow + gpb - 1) / gpb;
     const int64_t nchunk = apyib_det_matvec_nchunk(nrow, ncol, n);
     const int64_t chunk_len = (ncol + nchunk - 1) / nchunk;
+    const int64_t len = (int64_t)ny * nrow;
+    if (!use_tpm(n) && nS > 1) {                    // sub-warp kernel: one pass per overlap of the stack
+        for (int s = 0; s < nS; ++s) {
+            const int rc = det_matvec_impl((const cplx *)d_S + (size_t)s * ns * ns, ns, n, d_rows, nrow, d_cols, ncol, d_csign,
+                                           d_cindex, (const cplx *)d_Y + (size_t)s * y_stride, ny,
+                                           (cplx *)d_Z + (size_t)s * len, d_work, stream, 1, 0);
+            if (rc != APYIB_OK) return rc;
+        }
+        return APYIB_OK;
+    }
     dim3 grid((unsigned)rb, (unsigned)nchunk);
     int rc = use_tpm(n) ? launch_det_tpm(n, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len, nchunk,
-                                         d_csign, d_cindex, (const cplx *)d_Y, ny, (cplx *)d_work, 0)
+                                         d_csign, d_cindex, (const cplx *)d_Y, ny, (cplx *)d_work, 0, nS, y_stride,
+                                         nchunk * len)
                         : launch_det<false>(n, grid, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols, ncol, chunk_len,
                                (const cplx *)d_Y, ny, (cplx *)d_work);
     if (rc != APYIB_OK) return rc;
-    const int64_t len = (int64_t)ny * nrow;
     int64_t b = (len + 7) / 8;                       // one warp per output element, 8 warps per block
     if (b > 148 * 8) b = 148 * 8;
-    chunk_reduce_kernel<<<(unsigned)b, 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
+    chunk_reduce_kernel<<<dim3((unsigned)b, (unsigned)nS), 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
@@ -349,13 +375,13 @@ extern "C" int64_t apyib_det_matvec_pairs_work_len(int64_t nrow, int64_t ngroup,
     return (c > 0 ? c : 1) * ny * nrow;
 }
 
-extern "C" int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,
-                                      const int32_t *d_cols_sorted, const double *d_col_sign,
-                                      const int32_t *d_col_index, int64_t ncol, int64_t group_len,
-                                      const int32_t *d_cand, int nc, const void *d_Y, int ny, void *d_Z, void *d_work,
-                                      void *stream) {
+static int det_matvec_pairs_impl(const void *d_S, int nS, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,
+                                 const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
+                                 int64_t ncol, int64_t group_len, const int32_t *d_cand, int nc, const void *d_Y,
+                                 int64_t y_stride, int ny, void *d_Z, void *d_work, void *stream) {
     APYIB_REQUIRE(d_S && d_rows && d_cols_sorted && d_col_sign && d_col_index && d_cand && d_Y && d_Z && d_work, "null pointer");
     APYIB_REQUIRE(ny >= 1 && ny <= 4, "1 <= ny <= 4");
+    APYIB_REQUIRE(nS >= 1 && nS <= 65535, "stack size");
     APYIB_REQUIRE((k == 1 || k == 2) && n > k && ns >= n && nc >= k, "sizes");
     APYIB_REQUIRE(group_len == (k == 1 ? (int64_t)nc : (int64_t)nc * (nc - 1) / 2), "group_len must be nc (k=1) or C(nc,2) (k=2)");
     APYIB_REQUIRE(nrow >= 1 && ncol >= group_len && ncol % group_len == 0, "ncol must be a whole number of groups");
@@ -370,16 +396,54 @@ extern "C" int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, con
         return APYIB_ERR_UNSUPPORTED;
     }
     const int64_t gchunk = (ngroup + nchunk - 1) / nchunk;
+    const int64_t len = (int64_t)ny * nrow;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_det_pairs(n, k, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols_sorted, ngroup, group_len, d_cand, nc,
-                              gchunk, nchunk, d_col_sign, d_col_index, (const cplx *)d_Y, ny, ncol, (cplx *)d_work);
+                              gchunk, nchunk, d_col_sign, d_col_index, (const cplx *)d_Y, ny, ncol, (cplx *)d_work, nS,
+                              y_stride, nchunk * len);
     if (rc != APYIB_OK) return rc;
-    const int64_t len = (int64_t)ny * nrow;
     int64_t b = (len + 7) / 8;
     if (b > 148 * 8) b = 148 * 8;
-    chunk_reduce_kernel<<<(unsigned)b, 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
+    chunk_reduce_kernel<<<dim3((unsigned)b, (unsigned)nS), 256, 0, st>>>((const cplx *)d_work, (int)nchunk, len, (cplx *)d_Z);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
+}
+
+extern "C" int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,
+                                      const int32_t *d_cols_sorted, const double *d_col_sign,
+                                      const int32_t *d_col_index, int64_t ncol, int64_t group_len,
+                                      const int32_t *d_cand, int nc, const void *d_Y, int ny, void *d_Z, void *d_work,
+                                      void *stream) {
+    return det_matvec_pairs_impl(d_S, 1, ns, n, k, d_rows, nrow, d_cols_sorted, d_col_sign, d_col_index, ncol, group_len,
+                                 d_cand, nc, d_Y, 0, ny, d_Z, d_work, stream);
+}
+
+// ---- stacks of overlaps: the same index lists applied to nS overlap matrices in ONE launch (grid.y = overlap) ----
+// d_S: [nS][ns][ns]; outputs [nS][...] contiguous; d_Y: overlap s reads d_Y + s * y_stride (0 = one Y for all);
+// d_work: nS x the single-overlap work length.  d_col_sign / d_col_index may be NULL (plain lists).
+extern "C" int apyib_det_outer_stack(const void *d_S, int nS, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                                     const int32_t *d_cols, const double *d_col_sign, const int32_t *d_col_index,
+                                     int64_t ncol, void *d_out, void *stream) {
+    APYIB_REQUIRE((d_col_sign == nullptr) == (d_col_index == nullptr), "sign and index come together");
+    return det_outer_impl(d_S, ns, n, d_rows, nrow, d_cols, ncol, d_col_sign, d_col_index, d_out, stream, nS);
+}
+
+extern "C" int apyib_det_matvec_stack(const void *d_S, int nS, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                                      const int32_t *d_cols, const double *d_col_sign, const int32_t *d_col_index,
+                                      int64_t ncol, const void *d_Y, int64_t y_stride, int ny, void *d_Z, void *d_work,
+                                      void *stream) {
+    APYIB_REQUIRE((d_col_sign == nullptr) == (d_col_index == nullptr), "sign and index come together");
+    return det_matvec_impl(d_S, ns, n, d_rows, nrow, d_cols, ncol, d_col_sign, d_col_index, d_Y, ny, d_Z, d_work, stream, nS,
+                           y_stride);
+}
+
+extern "C" int apyib_det_matvec_pairs_stack(const void *d_S, int nS, int ns, int n, int k, const int32_t *d_rows,
+                                            int64_t nrow, const int32_t *d_cols_sorted, const double *d_col_sign,
+                                            const int32_t *d_col_index, int64_t ncol, int64_t group_len,
+                                            const int32_t *d_cand, int nc, const void *d_Y, int64_t y_stride, int ny,
+                                            void *d_Z, void *d_work, void *stream) {
+    return det_matvec_pairs_impl(d_S, nS, ns, n, k, d_rows, nrow, d_cols_sorted, d_col_sign, d_col_index, ncol, group_len,
+                                 d_cand, nc, d_Y, y_stride, ny, d_Z, d_work, stream);
 }
 
 // Re-orders column index lists for factorisation reuse (host): inside every list the substituted entries

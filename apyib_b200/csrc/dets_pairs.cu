@@ -44,8 +44,12 @@ det_pairs_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__
                  const int32_t *__restrict__ cols, int64_t ngroup, int64_t npair, const int32_t *__restrict__ cand,
                  int nc, int slots, int64_t gchunk, int64_t nchunk, const double *__restrict__ csign,
                  const int32_t *__restrict__ cindex, const cplx *__restrict__ Y, int ny, int64_t ncol,
-                 cplx *__restrict__ out) {
+                 cplx *__restrict__ out, int64_t y_stride, int64_t out_stride) {
     using cfg = pfx_cfg<N, K>;
+    // blockIdx.y = overlap of a stack (same index lists, own S / Y / output slab)
+    S += (size_t)blockIdx.y * ns * ns;
+    Y += (size_t)blockIdx.y * y_stride;
+    out += (size_t)blockIdx.y * out_stride;
     constexpr int NPRE = cfg::NPRE, B = cfg::B;
     constexpr int NPX = NPRE > 0 ? NPRE : 1;
     const int T = blockDim.x;
@@ -313,7 +317,7 @@ template <int N, int K>
 static int launch_pairs_nk(cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
                            const int32_t *cols, int64_t ngroup, int64_t npair, const int32_t *cand, int nc,
                            int64_t gchunk, int64_t nchunk, const double *csign, const int32_t *cindex, const cplx *Y,
-                           int ny, int64_t ncol, cplx *out) {
+                           int ny, int64_t ncol, cplx *out, int nS, int64_t y_stride, int64_t out_stride) {
     bool ssm;
     int slots;
     size_t smem;
@@ -331,8 +335,9 @@ static int launch_pairs_nk(cudaStream_t st, const cplx *S, int ns, const int32_t
         APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfxSmemMax));
         attr_done[ssm] = true;
     }
-    kern<<<(unsigned)blocks, T, smem, st>>>(S, ns, rows, nrow, cols, ngroup, npair, cand, nc, slots, gchunk, nchunk,
-                                            csign, cindex, Y, ny, ncol, out);
+    kern<<<dim3((unsigned)blocks, (unsigned)nS), T, smem, st>>>(S, ns, rows, nrow, cols, ngroup, npair, cand, nc, slots,
+                                                                gchunk, nchunk, csign, cindex, Y, ny, ncol, out, y_stride,
+                                                                out_stride);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
@@ -357,12 +362,12 @@ int pairs_total_warps(int n, int k, int ns, int nc) {
 int launch_det_pairs(int n, int k, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
                      const int32_t *cols, int64_t ngroup, int64_t npair, const int32_t *cand, int nc, int64_t gchunk,
                      int64_t nchunk, const double *csign, const int32_t *cindex, const cplx *Y, int ny, int64_t ncol,
-                     cplx *out) {
+                     cplx *out, int nS, int64_t y_stride, int64_t out_stride) {
     switch (n * 4 + k) {
 #define APYIB_PFX_CASE(NN, KK)                                                                                      \
     case NN * 4 + KK:                                                                                               \
         return launch_pairs_nk<NN, KK>(st, S, ns, rows, nrow, cols, ngroup, npair, cand, nc, gchunk, nchunk, csign, \
-                                       cindex, Y, ny, ncol, out);
+                                       cindex, Y, ny, ncol, out, nS, y_stride, out_stride);
         APYIB_PFX_CASE(3, 2) APYIB_PFX_CASE(4, 2) APYIB_PFX_CASE(5, 2) APYIB_PFX_CASE(6, 2) APYIB_PFX_CASE(7, 2)
         APYIB_PFX_CASE(8, 2) APYIB_PFX_CASE(9, 2) APYIB_PFX_CASE(10, 2) APYIB_PFX_CASE(11, 2) APYIB_PFX_CASE(12, 2)
         APYIB_PFX_CASE(2, 1) APYIB_PFX_CASE(3, 1) APYIB_PFX_CASE(4, 1) APYIB_PFX_CASE(5, 1) APYIB_PFX_CASE(6, 1)

@@ -54,8 +54,13 @@ __global__ void __launch_bounds__(tpm_threads(N), 1)
 det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ rows, int64_t nrow,
                const int32_t *__restrict__ cols, int64_t ncol, int64_t chunk_len, int64_t nchunk,
                const double *__restrict__ csign, const int32_t *__restrict__ cindex,
-               const cplx *__restrict__ Y, int ny, cplx *__restrict__ out, int outer) {
+               const cplx *__restrict__ Y, int ny, cplx *__restrict__ out, int outer, int64_t y_stride,
+               int64_t out_stride) {
     using cfg = tpm_cfg<N, B>;
+    // blockIdx.y = overlap of a stack (same index lists, own S / Y / output slab)
+    S += (size_t)blockIdx.y * ns * ns;
+    if (Y != nullptr) Y += (size_t)blockIdx.y * y_stride;
+    out += (size_t)blockIdx.y * out_stride;
     constexpr int T = tpm_threads(N);
     static_assert((size_t)cfg::per_thread_bytes * T <= kTpmSmemMax - 1024, "shared-memory footprint");
     extern __shared__ __align__(16) unsigned char tpm_smem[];
@@ -270,7 +275,8 @@ det_tpm_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ r
 template <int N>
 static int launch_tpm_n(cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
                         const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const double *csign,
-                        const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer) {
+                        const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer, int nS, int64_t y_stride,
+                        int64_t out_stride) {
     constexpr int B = tpm_panel(N);
     constexpr int T = tpm_threads(N);
     using cfg = tpm_cfg<N, B>;
@@ -287,8 +293,8 @@ static int launch_tpm_n(cudaStream_t st, const cplx *S, int ns, const int32_t *r
         APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTpmSmemMax));
         attr_done[ssm] = true;
     }
-    kern<<<(unsigned)blocks, T, smem, st>>>(S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, csign, cindex, Y, ny, out,
-                                            outer);
+    kern<<<dim3((unsigned)blocks, (unsigned)nS), T, smem, st>>>(S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, csign,
+                                                                cindex, Y, ny, out, outer, y_stride, out_stride);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }
@@ -299,10 +305,11 @@ int tpm_total_warps(int n) { return 148 * (tpm_threads(n) / 32); }
 
 int launch_det_tpm(int n, cudaStream_t st, const cplx *S, int ns, const int32_t *rows, int64_t nrow,
                    const int32_t *cols, int64_t ncol, int64_t chunk_len, int64_t nchunk, const double *csign,
-                   const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer) {
+                   const int32_t *cindex, const cplx *Y, int ny, cplx *out, int outer, int nS, int64_t y_stride,
+                   int64_t out_stride) {
     switch (n) {
 #define APYIB_TPM_CASE(NN) \
-    case NN: return launch_tpm_n<NN>(st, S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, csign, cindex, Y, ny, out, outer);
+    case NN: return launch_tpm_n<NN>(st, S, ns, rows, nrow, cols, ncol, chunk_len, nchunk, csign, cindex, Y, ny, out, outer, nS, y_stride, out_stride);
         APYIB_TPM_CASE(2) APYIB_TPM_CASE(3) APYIB_TPM_CASE(4) APYIB_TPM_CASE(5) APYIB_TPM_CASE(6) APYIB_TPM_CASE(7)
         APYIB_TPM_CASE(8) APYIB_TPM_CASE(9) APYIB_TPM_CASE(10) APYIB_TPM_CASE(11) APYIB_TPM_CASE(12)
 #undef APYIB_TPM_CASE

@@ -416,7 +416,8 @@ def main():
             # group), one Schur k-vector per candidate column, k x k determinants per list
             k_sub = int(name.split("k=")[1].split(",")[0])
             nrow, ncol = (int(x) for x in name.split(",")[2].rstrip("]").split("x"))
-            ndet = nrow * ncol
+            n_stack = int(name.split("nS=")[1].rstrip("]")) if "nS=" in name else 1
+            ndet = nrow * ncol * n_stack
             nc = wl["nbf"] - n
             gl = nc if k_sub == 1 else nc * (nc - 1) // 2
             npre = n - k_sub
@@ -424,9 +425,9 @@ def main():
                     + k_sub * npre * (npre - 1) // 2 + k_sub * npre               # X = -L21 L11^-1
                     + nc * k_sub * npre                                          # candidate columns
                     + (gl * 4 + 2 * nc if k_sub == 2 else 2 * gl))               # k x k determinants + table x vector
-            exec_flops = nrow * (ncol // gl) * cmac * 8.0
+            exec_flops = n_stack * nrow * (ncol // gl) * cmac * 8.0
             flops = ndet * (8.0 / 3.0) * n ** 3
-            kern = "det_pairs_kernel<N=%d,K=%d> (prefix-shared LU + table x vector) " % (n, k_sub)
+            kern = "det_pairs_kernel<N=%d,K=%d> (prefix-shared LU + table x vector, %d overlaps per launch) " % (n, k_sub, n_stack)
             extra = {"determinants_per_s": ndet / (avg_ms * 1e-3), "executed_tflops": exec_flops / (avg_ms * 1e-3) / 1e12,
                      "executed_frac": exec_flops / (avg_ms * 1e-3) / 1e12 / fp64_peak,
                      "executed_complex_macs_per_determinant": cmac / gl}
@@ -438,7 +439,7 @@ def main():
             tkey = "det_pairs_kernel"
         elif name.startswith("det_matvec"):
             nrow, ncol = (int(x) for x in name.split(",")[1].rstrip("]").split("x"))
-            ndet = nrow * ncol
+            ndet = nrow * ncol * (int(name.split("nS=")[1].rstrip("]")) if "nS=" in name else 1)
             kern = "det_tpm_kernel<N=%d,B=3> (fused LU + table x vector) " % n if n <= 12 else "det_kernel<N=%d,fused> " % n
             # (8/3) n^3 real flop per substituted n x n complex LU (algorithmic count)
             flops = ndet * (8.0 / 3.0) * n ** 3

@@ -242,6 +242,21 @@ int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, const int32_t 
                            const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
                            int64_t ncol, int64_t group_len, const int32_t *d_cand, int nc, const void *d_Y, int ny,
                            void *d_Z, void *d_work, void *stream);
+/* Stacks of overlaps: the same row / column lists applied to nS overlap matrices d_S[nS][ns][ns] in ONE launch
+ * (grid.y = overlap) -- the 12 (beta x pp/pn/np/nn) overlaps of one nuclear coordinate, the 6N pu/nu overlaps, ...
+ * (aats.py:714-1008 evaluates compute_all_dets overlap by overlap).  Outputs are [nS][...] contiguous; overlap s
+ * reads d_Y + s*y_stride (0: one Y for all); d_work is nS x the single-overlap work length; d_col_sign /
+ * d_col_index may both be NULL (plain lists, apyib_det_outer / apyib_det_matvec semantics).                  */
+int apyib_det_outer_stack(const void *d_S, int nS, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                          const int32_t *d_cols, const double *d_col_sign, const int32_t *d_col_index, int64_t ncol,
+                          void *d_out, void *stream);
+int apyib_det_matvec_stack(const void *d_S, int nS, int ns, int n, const int32_t *d_rows, int64_t nrow,
+                           const int32_t *d_cols, const double *d_col_sign, const int32_t *d_col_index, int64_t ncol,
+                           const void *d_Y, int64_t y_stride, int ny, void *d_Z, void *d_work, void *stream);
+int apyib_det_matvec_pairs_stack(const void *d_S, int nS, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,
+                                 const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
+                                 int64_t ncol, int64_t group_len, const int32_t *d_cand, int nc, const void *d_Y,
+                                 int64_t y_stride, int ny, void *d_Z, void *d_work, void *stream);
 /* Which LU kernel apyib_det_outer / apyib_det_matvec launch: 0 (default) = one thread per matrix,
  * column panels in registers + L in shared memory, for 2 <= n <= 12 and the sub-warp kernel above
  * that; 1 = the sub-warp (one lane per row) kernel for every n.  Same results either way.       */

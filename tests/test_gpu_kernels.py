@@ -377,3 +377,51 @@ def test_det_prefix_shared_lu_matches_per_matrix_lu(n, nv, nf, kind):
                     assert np.abs(got - base).max() < tol * scale, (ck, rk, ny)
     finally:
         cfg.LU_PREFIX = old
+
+
+@pytest.mark.parametrize("n,nv,nf", [(4, 5, 1), (9, 6, 0), (12, 4, 0), (14, 3, 0)])
+def test_det_stack_entry_points_match_single_overlap_calls(n, nv, nf):
+    """apyib_det_outer_stack / _matvec_stack / _matvec_pairs_stack (grid.y = overlap) == the single-overlap entry
+    points applied to every overlap of the stack, with one shared Y and with one Y per overlap; n = 14 goes
+    through the sub-warp kernel (host loop over the stack)."""
+    import ctypes as C
+    from apyib_b200._lib import lib, check
+    from apyib_b200.aats import _Tables, _det_matvec, _det_outer
+    from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
+    rng = np.random.default_rng(900 + n)
+    ns, nS = n + nv, 5
+    Ss = np.stack([np.eye(ns) + 0.3 * (rng.standard_normal((ns, ns)) + 1j * rng.standard_normal((ns, ns))) for _ in range(nS)])
+    dS = to_device(Ss, torch.complex128)
+    T = _Tables.get(n, nf, nv)
+    null = C.c_void_p(0)
+    for rk, ck in ((1, 1), (2, 1), (1, 2), (2, 2), (0, 2), (2, 0)):
+        rows, cols = T.L[rk], T.L[ck]
+        nrow, ncol = rows.shape[0], cols.shape[0]
+        if nrow == 0 or ncol == 0:
+            continue
+        variants = [(ptr(cols), null, null, None)]
+        if T.LS[ck] is not None:
+            cs, sg, ix = T.LS[ck]
+            variants.append((ptr(cs), ptr(sg), ptr(ix), T.LS[ck]))
+        for cp, sp, ip, ls in variants:
+            out = empty((nS, nrow, ncol), torch.complex128)
+            check(lib.apyib_det_outer_stack(ptr(dS), nS, ns, n, ptr(rows), nrow, cp, sp, ip, ncol, ptr(out), stream_ptr()))
+            want = np.stack([to_host(_det_outer(dS[s], n, rows, cols, ls)) for s in range(nS)])
+            assert np.abs(to_host(out) - want).max() <= 1e-13 * max(1.0, np.abs(want).max())
+            for ny, per in ((2, False), (3, True)):
+                Y = rng.standard_normal((nS, ny, ncol)) + 1j * rng.standard_normal((nS, ny, ncol))
+                dY = to_device(Y if per else Y[0], torch.complex128)
+                want = np.stack([to_host(_det_matvec(dS[s], n, rows, cols, dY[s] if per else dY, ls)) for s in range(nS)])
+                Z = empty((nS, ny, nrow), torch.complex128)
+                work = empty((nS * int(lib.apyib_det_matvec_work_len(nrow, ncol, ny, n)),), torch.complex128)
+                check(lib.apyib_det_matvec_stack(ptr(dS), nS, ns, n, ptr(rows), nrow, cp, sp, ip, ncol, ptr(dY),
+                                                 ny * ncol if per else 0, ny, ptr(Z), ptr(work), stream_ptr()))
+                scale = max(1.0, np.abs(want).max())
+                assert np.abs(to_host(Z) - want).max() <= 1e-12 * scale
+                if ls is not None and ck in (1, 2) and T.PFX[ck] is not None:
+                    gl, cand, nc = T.PFX[ck]
+                    work = empty((nS * int(lib.apyib_det_matvec_pairs_work_len(nrow, ncol // gl, ny, n, ck, ns, nc)),), torch.complex128)
+                    Z2 = empty((nS, ny, nrow), torch.complex128)
+                    check(lib.apyib_det_matvec_pairs_stack(ptr(dS), nS, ns, n, ck, ptr(rows), nrow, cp, sp, ip, ncol, gl, ptr(cand),
+                                                           nc, ptr(dY), ny * ncol if per else 0, ny, ptr(Z2), ptr(work), stream_ptr()))
+                    assert np.abs(to_host(Z2) - want).max() <= 1e-10 * scale
