@@ -33,6 +33,7 @@ SIGNATURES = {
     "apyib_contract_tma": (_int, [_int, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _int, _int,
                                   _dbl, _dbl, _dbl, _dbl, _int, _i64, _i64, _i64, _vp, _vp]),
     "apyib_gather4": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _dbl, _i32p, _i64p, _dbl, _vp]),
+    "apyib_gather4_batch": (_int, [_int, _vp, _i64p, _int, _int, _i64, _vp, _i64p, _i32p, _i64p, _dbl, _i32p, _i64p, _dbl, _vp]),
     "apyib_gather2": (_int, [_int, _vp, _i64p, _int, _vp, _i64p, _i32p, _i64p, _vp]),
     "apyib_mp2_t2_energy": (_int, [_int, _vp, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "apyib_reduce_scratch_len": (_i64, []),
@@ -104,7 +105,7 @@ lib = _load()
 # ---- launch accounting (bench.py reports `gpu_launches`) -------------------------------------
 # kernels launched per C-ABI call; everything not listed launches nothing on the device
 _KERNELS_PER_CALL = {
-    "apyib_contract": 1, "apyib_contract_tma": 1, "apyib_gather4": 1, "apyib_gather2": 1, "apyib_mp2_t2_energy": 2, "apyib_ci_update": 1,
+    "apyib_contract": 1, "apyib_contract_tma": 1, "apyib_gather4": 1, "apyib_gather4_batch": 1, "apyib_gather2": 1, "apyib_mp2_t2_energy": 2, "apyib_ci_update": 1,
     "apyib_symmetrize_ijab": 1, "apyib_dots": 1, "apyib_diis_push": 1, "apyib_diis_solve": 1,
     "apyib_lincomb_energy_rms": 1, "apyib_iter_advance": 1, "apyib_copy": 1, "apyib_axpby": 1,
     "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_det_outer_sorted": 1, "apyib_det_matvec_sorted": 2, "apyib_det_matvec_pairs": 2, "apyib_det_outer_stack": 1, "apyib_det_matvec_stack": 2, "apyib_det_matvec_pairs_stack": 2, "apyib_pack_doubles": 1,

@@ -29,9 +29,20 @@ from . import config
 from ._lib import lib, check
 from .contraction import contract
 from .device import (to_device, to_host, empty, zeros, ptr, stream_ptr, Graph)
-from .utils import (get_slices, compute_F_MO_dev, compute_ERI_MO_dev, spin_block_2_dev, gather4)
+from .utils import (get_slices, compute_F_MO_dev, compute_ERI_MO_dev, spin_block_2_dev, gather4, gather4_stack,
+                    mo_integrals_many)
 
 _NULL = C.c_void_p(0)
+
+
+def w_block_stack(Es, labels, out_labels, space, bounds, spin=0, c1=1.0, c2=0.0):
+    """w_block for a list of tensors -> [len(Es), ...]; one launch when they are slices of one stack"""
+    l0, l1, l2, l3 = labels
+    src1, src2 = (l0, l2, l1, l3), (l0, l3, l1, l2)
+    shape = [bounds[space[ch]][1] - bounds[space[ch]][0] for ch in out_labels]
+    perm = lambda src: [out_labels.index(ch) for ch in src]
+    start = lambda src: [bounds[space[ch]][0] for ch in src]
+    return gather4_stack(Es, spin, shape, perm(src1), start(src1), c1, perm(src2), start(src2), c2)
 
 
 def w_block(E, labels, out_labels, space, bounds, spin=0, c1=1.0, c2=0.0, out=None):
@@ -250,9 +261,7 @@ def _make_engine(parameters, points, has_singles, so, symmetrize=False):
 def _blocks(points, sp, bd, dt, spin):
     """returns blk(labels, out_labels=None, c1=1, c2=0): stacked [nb, ...] block of W (or <pq||rs>)"""
     def blk(lab, outl=None, c1=1.0, c2=0.0):
-        ol = outl or lab
-        return _stack(points, lambda pt, out: w_block(pt.ERI, lab, ol, sp, bd, spin, c1, c2, out=out),
-                      [bd[sp[ch]][1] - bd[sp[ch]][0] for ch in ol], dt)
+        return w_block_stack([pt.ERI for pt in points], lab, outl or lab, sp, bd, spin, c1, c2)
     return blk
 
 
@@ -371,9 +380,7 @@ class _CISDOperator:
         nb = len(ERIs)
         self.nb, self.O, self.V, self.n1 = nb, O, V, O * V
         sp = dict(i="o", j="o", k="o", l="o", a="v", b="v", c="v", d="v")
-        blk = lambda lab, outl=None, c1=1.0, c2=0.0: _stack(
-            ERIs, lambda E, out: w_block(E, lab, outl or lab, sp, bd, 0, c1, c2, out=out),
-            [bd[sp[ch]][1] - bd[sp[ch]][0] for ch in (outl or lab)], dt)
+        blk = lambda lab, outl=None, c1=1.0, c2=0.0: w_block_stack(list(ERIs), lab, outl or lab, sp, bd, 0, c1, c2)
         F = torch.stack(list(Fs))
         self.Foo, self.Fvv, self.Fov = F[:, :O, :O], F[:, O:, O:], F[:, :O, O:].contiguous()
         self.Fai = F[:, O:, :O].transpose(1, 2).reshape(nb, -1)                 # F_ai as [i,a]  ci_wfn.py:457
@@ -571,7 +578,7 @@ def solve_batch(method, parameters, points, print_level=0):
 class ci_wfn(object):
     """Reference: apyib/ci_wfn.py:19-575."""
 
-    def __init__(self, parameters, wfn):
+    def __init__(self, parameters, wfn, _integrals=None):
         self.parameters = parameters
         self.H = wfn.H
         self.wfn = wfn
@@ -583,10 +590,21 @@ class ci_wfn(object):
         self.D_ia = self.eps_o.reshape(-1, 1) - self.eps_v                                     # ci_wfn.py:42
         self.D_ijab = (self.eps_o.reshape(-1, 1, 1, 1) + self.eps_o.reshape(-1, 1, 1)
                        - self.eps_v.reshape(-1, 1) - self.eps_v)                               # ci_wfn.py:43
-        self._F_dev, self.E_fc = compute_F_MO_dev(self.parameters, self.wfn, self.C_list)      # ci_wfn.py:46
-        self._ERI_dev = compute_ERI_MO_dev(self.parameters, self.wfn, self.C_list)             # ci_wfn.py:47
+        if _integrals is None:
+            self._F_dev, self.E_fc = compute_F_MO_dev(self.parameters, self.wfn, self.C_list)  # ci_wfn.py:46
+            self._ERI_dev = compute_ERI_MO_dev(self.parameters, self.wfn, self.C_list)         # ci_wfn.py:47
+        else:                               # built for a whole stack of points at once (ci_wfn.many)
+            self._F_dev, self.E_fc, self._ERI_dev = _integrals
         self._F_host = self._ERI_host = None
         self.iterations = 0
+
+    @classmethod
+    def many(cls, parameters, wfns):
+        """[ci_wfn(parameters, w) for w in wfns] with the AO->MO transforms and Fock builds of all points of one
+        shape and dtype done by shared launches (utils.mo_integrals_many)."""
+        C_lists = [get_slices(parameters, w)[0] for w in wfns]
+        ints = mo_integrals_many(parameters, wfns, C_lists)
+        return [cls(parameters, w, _integrals=i) for w, i in zip(wfns, ints)]
 
     # numpy views of the MO integrals, as the reference exposes them (analytic_aats.py reads these)
     @property
@@ -640,7 +658,7 @@ def solve_many(method, parameters, wfns, print_level=0):
     """Batched counterpart of `[ci_wfn(parameters, w).solve_<method>() for w in wfns]`: the points
     are grouped by dtype (real nuclear-displacement points / complex field points) and each group
     is solved with shared launches.  Returns the per-point result tuples in input order."""
-    cis = [ci_wfn(parameters, w) for w in wfns]
+    cis = ci_wfn.many(parameters, wfns)
     groups = {}
     for k, c in enumerate(cis):
         groups.setdefault((c._ERI_dev.dtype, tuple(c._ERI_dev.shape), len(c.eps_o)), []).append(k)

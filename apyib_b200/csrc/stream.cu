@@ -33,7 +33,9 @@ __device__ __forceinline__ T fetch4(const T *src, const int64_t (&sd)[4], int sp
 // 32-bit index arithmetic and four independent elements in flight per thread.  (The first version
 // decomposed a flat int64 index per element: three 64-bit div/mod pairs per output made the one-off block
 // extraction run at 31 % of HBM peak.)
-template <typename T> __global__ void __launch_bounds__(kThreads) gather4_kernel(const T *__restrict__ src, T *__restrict__ out, Gather4Args g, int lead) {
+template <typename T> __global__ void __launch_bounds__(kThreads) gather4_kernel(const T *__restrict__ src, T *__restrict__ out, Gather4Args g, int lead, int64_t src_bstride, int64_t out_bstride) {
+    src += (size_t)blockIdx.y * src_bstride;                  // blockIdx.y = finite-difference point of a stack
+    out += (size_t)blockIdx.y * out_bstride;
     const int64_t nouter = (lead == 3) ? g.od[0] * g.od[1] * g.od[2] : g.od[0] * g.od[1];
     const unsigned od3 = (unsigned)g.od[3];
     const unsigned inner = (lead == 3) ? od3 : (unsigned)(g.od[2] * g.od[3]);
@@ -591,9 +593,11 @@ using namespace apyib;
 
 extern "C" int64_t apyib_reduce_scratch_len(void) { return (int64_t)kReduceMaxBlocks * kReduceMaxVals + 2; }
 
-extern "C" int apyib_gather4(int dtype, const void *d_src, const int64_t src_dims[4], int spin, void *d_out,
-                             const int64_t out_dims[4], const int32_t perm1[4], const int64_t start1[4], double c1,
-                             const int32_t perm2[4], const int64_t start2[4], double c2, void *stream) {
+static int gather4_impl(int dtype, const void *d_src, const int64_t src_dims[4], int spin, void *d_out,
+                        const int64_t out_dims[4], const int32_t perm1[4], const int64_t start1[4], double c1,
+                        const int32_t perm2[4], const int64_t start2[4], double c2, void *stream, int nb,
+                        int64_t src_bstride) {
+    APYIB_REQUIRE(nb >= 1 && nb <= 65535, "batch");
     APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
     APYIB_REQUIRE(d_src && d_out, "null pointer");
     Gather4Args g;
@@ -622,13 +626,30 @@ extern "C" int apyib_gather4(int dtype, const void *d_src, const int64_t src_dim
     // leading-index groups: (x0, x1) if that already gives >= 2 CTAs per SM, else (x0, x1, x2)
     const int lead = (out_dims[0] * out_dims[1] >= 2 * 148 || out_dims[2] == 1) ? 2 : 3;
     const int64_t nouter = lead == 3 ? out_dims[0] * out_dims[1] * out_dims[2] : out_dims[0] * out_dims[1];
-    const unsigned gridx = (unsigned)(nouter < 148 * 16 ? nouter : 148 * 16);
+    const int64_t cap = nb > 1 ? (148 * 16 + nb - 1) / nb : 148 * 16;
+    const dim3 grid((unsigned)(nouter < cap ? nouter : cap), (unsigned)nb);
     if (dtype == APYIB_C128)
-        gather4_kernel<cplx><<<gridx, kThreads, 0, st>>>((const cplx *)d_src, (cplx *)d_out, g, lead);
+        gather4_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_src, (cplx *)d_out, g, lead, src_bstride, total);
     else
-        gather4_kernel<double><<<gridx, kThreads, 0, st>>>((const double *)d_src, (double *)d_out, g, lead);
+        gather4_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_src, (double *)d_out, g, lead, src_bstride, total);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
+}
+
+extern "C" int apyib_gather4(int dtype, const void *d_src, const int64_t src_dims[4], int spin, void *d_out,
+                             const int64_t out_dims[4], const int32_t perm1[4], const int64_t start1[4], double c1,
+                             const int32_t perm2[4], const int64_t start2[4], double c2, void *stream) {
+    return gather4_impl(dtype, d_src, src_dims, spin, d_out, out_dims, perm1, start1, c1, perm2, start2, c2, stream, 1, 0);
+}
+
+// the same block of nb tensors that sit src_bstride elements apart (the MO integrals of a stack of
+// finite-difference points), out[nb][...] contiguous: one launch, grid.y = point
+extern "C" int apyib_gather4_batch(int dtype, const void *d_src, const int64_t src_dims[4], int spin, int nb,
+                                   int64_t src_bstride, void *d_out, const int64_t out_dims[4], const int32_t perm1[4],
+                                   const int64_t start1[4], double c1, const int32_t perm2[4], const int64_t start2[4],
+                                   double c2, void *stream) {
+    return gather4_impl(dtype, d_src, src_dims, spin, d_out, out_dims, perm1, start1, c1, perm2, start2, c2, stream, nb,
+                        src_bstride);
 }
 
 extern "C" int apyib_gather2(int dtype, const void *d_src, const int64_t src_dims[2], int spin, void *d_out,

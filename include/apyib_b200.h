@@ -103,6 +103,12 @@ int apyib_gather4(int dtype, const void *d_src, const int64_t src_dims[4], int s
                   const int32_t perm1[4], const int64_t start1[4], double c1,
                   const int32_t perm2[4], const int64_t start2[4], double c2,
                   void *stream);
+/* The same block of nb source tensors src_bstride elements apart (the MO integrals of a stack of
+ * finite-difference points: ci_wfn.py builds these slices once per point), d_out[nb][...] contiguous.       */
+int apyib_gather4_batch(int dtype, const void *d_src, const int64_t src_dims[4], int spin, int nb,
+                        int64_t src_bstride, void *d_out, const int64_t out_dims[4], const int32_t perm1[4],
+                        const int64_t start1[4], double c1, const int32_t perm2[4], const int64_t start2[4],
+                        double c2, void *stream);
 /* 2-index analogue (utils.py:283-313 compute_F_SO, :393-422 compute_so_overlap):
  * out[x0,x1] = src-or-spin-blocked(start + x[perm]).                                */
 int apyib_gather2(int dtype, const void *d_src, const int64_t src_dims[2], int spin,

@@ -121,14 +121,42 @@ def test_batched_solve_equals_single_solves(method):
     ws += [orc.rotated_wfn(7, 3, 310 + k, True, 0, scale=sc) for k, sc in enumerate((0.02, 0.008))]
     p = par(method)
     got = solve_many(method, p, ws)
-    for w, g in zip(ws, got):
+    from apyib_b200.ci_wfn import solve_batch
+    cis = [apyib_b200.ci_wfn(p, w) for w in ws]
+    shared = {}
+    for grp in ([0, 1, 2], [3, 4]):          # same MO integrals -> shared launches must change nothing at all
+        res, its = solve_batch(method, p, [cis[k].point() for k in grp])
+        for k, r, it in zip(grp, res, its):
+            shared[k] = (r, it)
+    for k, (w, g) in enumerate(zip(ws, got)):
         want = getattr(orc, "solve_" + method)(p, w)
         assert abs(g[0] - want[0]) < E_TOL
         for a, b in zip(g[1:], want[1:]):
             assert a.dtype == b.dtype and np.abs(a - b).max() < T_TOL
-        single = getattr(apyib_b200.ci_wfn(p, w), "solve_" + method)()
+        single = getattr(cis[k], "solve_" + method)()
+        for a, b in zip(shared[k][0], single):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), "batched and single iterations must be bit-identical"
+        assert shared[k][1] == cis[k].iterations
+        # solve_many also builds the MO integrals of a group with shared launches (different tile schedule):
         for a, b in zip(g, single):
-            assert np.array_equal(np.asarray(a), np.asarray(b)), "batched and single solves must be bit-identical"
+            assert np.abs(np.asarray(a) - np.asarray(b)).max() < 1e-12
+
+
+def test_stacked_mo_integrals_match_per_point_constructors():
+    """ci_wfn.many (AO->MO transform + Fock build of a stack of points by shared launches, utils.py:217-279)
+    vs one constructor per point and vs the oracle; frozen core, real and complex points mixed"""
+    import apyib_b200
+    ws = [orc.rotated_wfn(8, 3, 400 + k, k >= 3, 1) for k in range(5)]
+    p = par("CISD", True)
+    many = apyib_b200.ci_wfn.many(p, ws)
+    assert many[0]._ERI_dev.data_ptr() + many[0]._ERI_dev.numel() * 8 == many[1]._ERI_dev.data_ptr()   # one stack
+    for w, c in zip(ws, many):
+        one = apyib_b200.ci_wfn(p, w)
+        o = orc._CI(p, w)
+        assert c.F_MO.dtype == one.F_MO.dtype == o.F_MO.dtype and c.ERI_MO.shape == o.ERI_MO.shape
+        assert np.abs(c.F_MO - o.F_MO).max() < 1e-12 and np.abs(c.ERI_MO - o.ERI_MO).max() < 1e-13
+        assert np.abs(c.F_MO - one.F_MO).max() < 1e-13 and abs(c.E_fc - o.E_fc) < 1e-11 and abs(one.E_fc - o.E_fc) < 1e-11
+        assert np.array_equal(c.D_ijab, one.D_ijab)
 
 
 @pytest.mark.parametrize("nbf,no,nf,cplx,seed", [(7, 3, 0, False, 901), (6, 2, 0, True, 902), (8, 3, 1, False, 903)])
