@@ -281,11 +281,10 @@ class AAT(object):
         pn = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
         np_ = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
         nn = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
-        done = mo_overlaps_dev(jobs)
         if so:
-            done = [spin_block_2_dev(S) for S in done]
-        # one device->host copy per dtype group would need a second bookkeeping pass; the matrices are nbf^2
-        host = [to_host(S) for S in done]
+            host = [to_host(spin_block_2_dev(S)) for S in mo_overlaps_dev(jobs)]
+        else:
+            host = mo_overlaps_dev(jobs, host=True)
         get = lambda x: [get(y) for y in x] if isinstance(x, list) else host[x]
         if not rhf:
             self.overlap_uu, self.overlap_up, self.overlap_un = get(uu), get(up), get(un)

@@ -266,11 +266,11 @@ def mo_overlap_dev(C_bra, S_ao, C_ket):
     return contract_new("mp,mq->pq", Cb, tmp, conj_a=True)
 
 
-def mo_overlaps_dev(triples):
+def mo_overlaps_dev(triples, host=False):
     """[C_bra^H S_AO C_ket for (C_bra, S_AO, C_ket) in triples] with TWO batched contraction launches per
     dtype group (real / complex) instead of two per matrix: the finite-difference AAT needs 1 + 6 + 6N + 36N
     overlaps of identical shape (aats.py:53-115).  Returns device tensors, float64 where all three inputs
-    are real (like numpy would), complex128 otherwise."""
+    are real (like numpy would), complex128 otherwise; host=True returns numpy arrays instead (one copy per group)."""
     out = [None] * len(triples)
     groups = {}
     # MO coefficients that came through the NCCL exchange are device tensors; they are nbf^2 and join the host stack
@@ -284,6 +284,8 @@ def mo_overlaps_dev(triples):
         Cb, S, Ck = stack(0), stack(1), stack(2)
         tmp = contract_new("smn,snq->smq", S, Ck)
         res = contract_new("smp,smq->spq", Cb, tmp, conj_a=True)
+        if host:
+            res = to_host(res)                       # ONE device->host copy per dtype group
         for j, k in enumerate(idx):
             out[k] = res[j]
     return out

@@ -499,6 +499,10 @@ def main():
                 "traffic": traffic_tab.get(tkey, {}).get("dram_bytes_per_launch"), "kernel": kern + name,
                 "launches_timed": len(evs), "avg_ms": avg_ms, "share_of_step": share, "note": note}
         roof.update(extra)
+        if "nS=" in name and not name.endswith("nS=1]") and roof["traffic"] is not None:
+            # the ncu capture is of a single-overlap launch; a stack launch adds one S and one Y per further overlap
+            roof["traffic_single_overlap_launch"] = roof["traffic"]
+            roof["traffic"] = None
         if use_graph:
             roof["note"] += ("; the timed steps replay the AAT stacks from CUDA graphs (no per-launch events), so the "
                              "kernel was timed in one extra eager step of the same workload right after them; "
