@@ -226,9 +226,10 @@ def _run_blocks(aat, S, X1, X2, Y1, Y2):
         _block_graphs[key] = "warm"
         return aat._blocks_device(*inputs)
     if g == "warm":
-        live = [k for k, v in _block_graphs.items() if isinstance(v, _BlockGraph)]
-        if len(live) >= GRAPH_MAX_LIVE:                      # bound the memory held by private graph pools
-            _block_graphs.pop(live[0])
+        live = sum(1 for v in _block_graphs.values() if isinstance(v, _BlockGraph))
+        if live >= GRAPH_MAX_LIVE:                           # bound the memory held by private graph pools:
+            _block_graphs[key] = None                        # further shapes simply stay eager
+            return aat._blocks_device(*inputs)
         try:
             g = _BlockGraph(aat, inputs)
         except Exception as exc:                             # not capturable here: stay eager for this shape
