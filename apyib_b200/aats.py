@@ -38,6 +38,32 @@ def _i32_host(a):
     return a, a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
+def prefix_groups(srt, n, k):
+    """Structure the prefix-shared LU kernel (csrc/dets_pairs.cu) relies on, verified on the host: the sorted
+    lists come in groups of consecutive lists sharing their first n-k columns and ending in every candidate
+    column (k = 1) / every pair c < d in lexicographic order (k = 2) of one ascending candidate set.
+    Returns (group length, candidate columns int32[nc], nc) or None when the lists are not of that form."""
+    if n <= k or len(srt) == 0:
+        return None
+    cand = np.unique(srt[:, n - k:])
+    nc = len(cand)
+    if k == 1:
+        tails = cand.reshape(-1, 1)
+    else:
+        if nc < 2:
+            return None
+        tails = np.array([(cand[x], cand[y]) for x in range(nc) for y in range(x + 1, nc)], dtype=srt.dtype)
+    gl = len(tails)
+    if len(srt) % gl:
+        return None
+    grp = srt.reshape(-1, gl, n)
+    if not (np.array_equal(grp[:, :, :n - k], np.repeat(grp[:, :1, :n - k], gl, axis=1))
+            and np.array_equal(grp[:, :, n - k:], np.broadcast_to(tails, (grp.shape[0], gl, k)))
+            and (grp[:, :, :n - k] < n).all() and (cand >= n).all()):
+        return None
+    return gl, np.ascontiguousarray(cand, dtype=np.int32), nc
+
+
 class _Tables:
     """Index tables of compute_all_dets' enumeration (aats.py:581-618), built by the C library
     (bit-exact contract) and uploaded once per (ndocc, nfzc, nvirt)."""
@@ -73,34 +99,11 @@ class _Tables:
                 check(lib.apyib_det_sort_lists(no, _i32_host(src)[1], cnt, _i32_host(srt)[1],
                                                sign.ctypes.data_as(C.POINTER(C.c_double)), _i32_host(idx)[1]))
                 self.LS[k] = tuple(torch.from_numpy(x.copy()).to(device()) for x in (srt, sign, idx))
-                self.PFX[k] = self._prefix_groups(srt, no, k)
+                grp = prefix_groups(srt, no, k)
+                if grp is not None:
+                    self.PFX[k] = (grp[0], torch.from_numpy(grp[1]).to(device()), grp[2])
         self.doubles_dev = torch.from_numpy(self.doubles.copy()).to(device())
         self.singles_dev = torch.from_numpy(self.singles.copy()).to(device())
-
-    @staticmethod
-    def _prefix_groups(srt, n, k):
-        """Structure the prefix-shared LU kernel (csrc/dets_pairs.cu) relies on, verified on the host: the sorted
-        lists come in groups of consecutive lists sharing their first n-k columns and ending in every candidate
-        column (k = 1) / every pair c < d in lexicographic order (k = 2) of one ascending candidate set."""
-        if n <= k or len(srt) == 0:
-            return None
-        cand = np.unique(srt[:, n - k:])
-        nc = len(cand)
-        if k == 1:
-            tails = cand.reshape(-1, 1)
-        else:
-            if nc < 2:
-                return None
-            tails = np.array([(cand[x], cand[y]) for x in range(nc) for y in range(x + 1, nc)], dtype=srt.dtype)
-        gl = len(tails)
-        if len(srt) % gl:
-            return None
-        grp = srt.reshape(-1, gl, n)
-        if not (np.array_equal(grp[:, :, :n - k], np.repeat(grp[:, :1, :n - k], gl, axis=1))
-                and np.array_equal(grp[:, :, n - k:], np.broadcast_to(tails, (grp.shape[0], gl, k)))
-                and (grp[:, :, :n - k] < n).all() and (cand >= n).all()):
-            return None
-        return gl, torch.from_numpy(np.ascontiguousarray(cand, dtype=np.int32)).to(device()), nc
 
     @staticmethod
     def get(no, nf, nv):

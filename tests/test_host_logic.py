@@ -154,3 +154,58 @@ def test_energy_only_drivers_host_logic(monkeypatch):
     wg, wpT, wnT = fp.compute_Magnetic_Field_Gradient(mk(), basis, C, 1e-4)
     assert g.shape == (3,) and np.array_equal(g, wg) and all(np.array_equal(nT[b][2], wnT[b][2]) for b in range(3))
     assert p["F_mag"] == [0.0] * 3 and len(pC) == len(nB) == 3
+
+
+@pytest.mark.parametrize("no,nf,nv", [(9, 0, 13), (9, 2, 13), (7, 2, 6), (3, 0, 4), (4, 1, 5), (12, 1, 4), (2, 0, 3), (5, 4, 3), (6, 0, 1)])
+def test_sorted_lists_have_the_group_structure_of_the_prefix_shared_lu(no, nf, nv):
+    """csrc/dets_pairs.cu consumes the sorted column lists of aats.py:581-618 in groups: same n-k unsubstituted
+    columns in front, then every candidate column (k = 1) / every pair c < d in lexicographic order (k = 2).
+    Host-only check of apyib_det_enumeration -> apyib_det_index_lists -> apyib_det_sort_lists -> prefix_groups,
+    including the parity sign and the index back into the reference's enumeration order."""
+    import ctypes as C
+    from apyib_b200._lib import lib, check
+    from apyib_b200.aats import prefix_groups
+
+    def i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+    ns, nd = C.c_int64(), C.c_int64()
+    check(lib.apyib_det_enumeration(no, nf, nv, None, C.byref(ns), None, C.byref(nd)))
+    singles, doubles = np.zeros((ns.value, 2), dtype=np.int32), np.zeros((nd.value, 4), dtype=np.int32)
+    check(lib.apyib_det_enumeration(no, nf, nv, i32(singles)[1], None, i32(doubles)[1], None))
+    o = no - nf
+    assert ns.value == o * nv and nd.value == (o * (o - 1) // 2) * (nv * (nv - 1) // 2)
+    for k, sub in ((1, singles), (2, doubles)):
+        cnt = len(sub)
+        if cnt == 0:
+            continue
+        L = np.zeros((cnt, no), dtype=np.int32)
+        check(lib.apyib_det_index_lists(no, i32(sub)[1], cnt, k, i32(L)[1]))
+        srt, sign, idx = np.zeros_like(L), np.zeros(cnt), np.zeros(cnt, dtype=np.int32)
+        check(lib.apyib_det_sort_lists(no, i32(L)[1], cnt, i32(srt)[1], sign.ctypes.data_as(C.POINTER(C.c_double)), i32(idx)[1]))
+        assert sorted(idx.tolist()) == list(range(cnt))
+        # sign = parity of the permutation that moves the substituted entries behind the others (a column permutation)
+        for c in range(0, cnt, max(1, cnt // 50)):
+            src = L[idx[c]].tolist()
+            perm = [src.index(x) for x in srt[c].tolist()]
+            inv = sum(1 for a in range(no) for b in range(a + 1, no) if perm[a] > perm[b])
+            assert sign[c] == (-1.0) ** inv
+        g = prefix_groups(srt, no, k)
+        if no <= k:
+            assert g is None
+            continue
+        assert g is not None
+        gl, cand, nc = g
+        assert nc == nv and cand.dtype == np.int32 and cand.tolist() == list(range(no, no + nv))
+        assert gl == (nv if k == 1 else nv * (nv - 1) // 2) and cnt % gl == 0
+        # one group per set of substituted occupied columns; frozen-core columns are never substituted
+        prefixes = {tuple(srt[c, :no - k]) for c in range(cnt)}
+        assert len(prefixes) == cnt // gl == (o if k == 1 else o * (o - 1) // 2)
+        assert all(set(range(nf)) <= set(p) for p in prefixes)
+    # a list set that is NOT of that form is rejected (the kernel is then not used)
+    if nd.value > 2:
+        assert prefix_groups(srt[:-1], no, 2) is None or len(srt[:-1]) % gl == 0
+        bad = srt.copy()
+        bad[0, 0], bad[0, 1] = bad[0, 1], bad[0, 0]
+        assert prefix_groups(bad, no, 2) is None or no - 2 < 2
