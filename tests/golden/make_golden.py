@@ -217,7 +217,37 @@ def linear_response_cid(ns):
     np.savez_compressed(os.path.join(HERE, "synthetic_linear_response_cid.npz"), **out)
 
 
+def fd_drivers(lit):
+    """a13 + SURVEY 8(f).4: the UNMODIFIED reference's finite_difference.compute_APT / compute_Hessian /
+    compute_Nuclear_Gradient / compute_Magnetic_Field_Gradient (fin_diff.py:27-263, 376-510) on its (H2)_2
+    molecule, STO-3G, run through oracle/mini_psi4.py (s-Gaussian integrals).  Numbers only."""
+    ns = ref_harness.load(with_mini_psi4=True)
+    out = {"molecule": "(H2)_2", "basis": "STO-3G", "cases": []}
+    for method, h_R, h_F, h_B in (("CISD", 1e-3, 1e-4, 1e-4), ("MP2", 1e-3, 1e-4, 1e-4), ("CID", 1e-3, 1e-4, 1e-4)):
+        mk = lambda: {"geom": lit["geom"], "basis": "STO-3G", "method": method, "freeze_core": False, "DIIS": True,
+                      "e_convergence": 1e-13, "d_convergence": 1e-13, "max_iterations": 120,
+                      "F_el": [0.0, 0.0, 0.0], "F_mag": [0.0, 0.0, 0.0]}
+        p = mk()
+        E_list, T_list, C, basis = quiet(ns.energy.energy, p)
+        fd = ns.fin_diff.finite_difference(p, basis, C)
+        case = {"method": method, "h_R": h_R, "h_F": h_F, "h_B": h_B, "E_tot": float(np.real(E_list[0] + E_list[1] + E_list[2]))}
+        case["APT"] = np.asarray(quiet(fd.compute_APT, h_R, h_F)).tolist()
+        if method != "CID":
+            case["Hessian"] = np.asarray(quiet(fd.compute_Hessian, h_R)).tolist()
+        g = quiet(fd.compute_Nuclear_Gradient, h_R)
+        case["nuclear_gradient"] = np.asarray(g[0]).tolist()
+        g = quiet(fd.compute_Magnetic_Field_Gradient, h_B)
+        case["magnetic_gradient"] = np.asarray(g[0]).tolist()
+        t2p = np.asarray(g[5][2][2])
+        case["mag_pos_T2_z_abs_sum"] = float(np.abs(t2p).sum())
+        out["cases"].append(case)
+    json.dump(out, open(os.path.join(HERE, "reference_fd_drivers.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if "--only-fd-drivers" in sys.argv:
+        fd_drivers(json.load(open(os.path.join(HERE, "reference_literals.json"))))
+        sys.exit(0)
     if "--only-cid-response" in sys.argv:
         linear_response_cid(ref_harness.load())
         sys.exit(0)
@@ -228,4 +258,5 @@ if __name__ == "__main__":
     synthetic(ns)
     linear_response(ns)
     linear_response_cid(ns)
+    fd_drivers(lit)
     print("wrote", sorted(os.listdir(HERE)))

@@ -164,3 +164,38 @@ def test_cid_linear_response_matches_finite_differences_of_reference_solver(name
     dE, dt2 = orc.solve_perturbed_CID(p, w, LRG_CID[name + "/t2"], LRG_CID[name + "/E0"], dF, dG)
     assert abs(dE - LRG_CID[name + "/dE"]) < 1e-8
     assert np.abs(dt2 - LRG_CID[name + "/dt2"]).max() < 1e-8
+
+
+# ---- a13 + 8(f).4: energy-only finite-difference drivers vs the UNMODIFIED reference on (H2)_2 ---------------
+FDG = json.load(open(os.path.join(HERE, "golden", "reference_fd_drivers.json")))
+
+
+@pytest.mark.parametrize("c", FDG["cases"], ids=lambda c: c["method"])
+def test_h2_2_fd_drivers_match_reference_outputs(c):
+    """fin_diff.py:151-263 (APT), :376-510 (gradients) restated in oracle/fd_pipeline.py; pinned by outputs of the
+    unmodified reference run through oracle/mini_psi4.py (tests/golden/make_golden.py --only-fd-drivers).
+    Tolerances: second differences of energies that agree to ~1e-13 (h_R h_F = 1e-7 -> 1e-6)."""
+    from oracle import fd_pipeline as fp
+    mk = lambda: {"geom": LIT["geom"], "basis": "STO-3G", "method": c["method"], "freeze_core": False, "DIIS": True,
+                  "e_convergence": 1e-13, "d_convergence": 1e-13, "max_iterations": 120,
+                  "F_el": [0.0] * 3, "F_mag": [0.0] * 3}
+    p = mk()
+    E_list, T0, C, basis, wfn = fp.energy(p)
+    assert abs(E_list[0] + E_list[1] + E_list[2] - c["E_tot"]) < 1e-12
+    apt = fp.compute_APT(mk(), c["h_R"], c["h_F"])
+    assert apt.shape == (12, 3) and np.abs(apt - np.array(c["APT"])).max() < 2e-6
+    g, pT, nT = fp.compute_Nuclear_Gradient(mk(), basis, C, c["h_R"])
+    assert np.abs(g - np.array(c["nuclear_gradient"])).max() < 1e-9
+    g, pT, nT = fp.compute_Magnetic_Field_Gradient(mk(), basis, C, c["h_B"])
+    assert np.abs(g - np.array(c["magnetic_gradient"])).max() < 1e-8
+    assert abs(np.abs(pT[2][2]).sum() - c["mag_pos_T2_z_abs_sum"]) < 1e-10
+
+
+def test_h2_2_hessian_matches_reference_output():
+    """fin_diff.py:27-147: 4 (3N)^2 = 576 energies (MP2 keeps the CPU suite short; the fixture also holds CISD)"""
+    from oracle import fd_pipeline as fp
+    c = [c for c in FDG["cases"] if c["method"] == "MP2"][0]
+    p = {"geom": LIT["geom"], "basis": "STO-3G", "method": "MP2", "freeze_core": False, "DIIS": True,
+         "e_convergence": 1e-13, "d_convergence": 1e-13, "max_iterations": 120, "F_el": [0.0] * 3, "F_mag": [0.0] * 3}
+    H = fp.compute_Hessian(p, c["h_R"])
+    assert H.shape == (12, 12) and np.abs(H - np.array(c["Hessian"])).max() < 2e-6
