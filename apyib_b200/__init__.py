@@ -10,4 +10,7 @@ from .mp2_wfn import mp2_wfn                            # noqa: F401
 from .ci_wfn import ci_wfn                              # noqa: F401
 from . import utils                                     # noqa: F401
 
+if config.PAIRS_SINGLE_VECTOR:                          # experimental kernel variant (config.py)
+    lib.apyib_det_set_pairs_variant(1)
+
 __version__ = "0.1.0"

@@ -58,6 +58,7 @@ SIGNATURES = {
     "apyib_det_matvec_stack": (_int, [_vp, _int, _int, _int, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _int, _vp, _vp, _vp]),
     "apyib_det_matvec_pairs_stack": (_int, [_vp, _int, _int, _int, _int, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _int,
                                             _vp, _i64, _int, _vp, _vp, _vp]),
+    "apyib_det_set_pairs_variant": (_int, [_int]),
     "apyib_det_sort_lists": (_int, [_int, _i32p, _i64, _i32p, _f64p, _i32p]),
     "apyib_det_outer_sorted": (_int, [_vp, _int, _int, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec_sorted": (_int, [_vp, _int, _int, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _int, _vp, _vp, _vp]),

@@ -211,6 +211,7 @@ int launch_det_pairs(int n, int k, cudaStream_t st, const cplx *S, int ns, const
                      int64_t nchunk, const double *csign, const int32_t *cindex, const cplx *Y, int ny, int64_t ncol,
                      cplx *out, int nS, int64_t y_stride, int64_t out_stride);
 int pairs_total_warps(int n, int k, int ns, int nc);
+extern int g_pairs_variant;
 constexpr int kTpmMaxN = 12;
 static int g_det_kernel = 0;   // 0 = thread-per-matrix for 2 <= n <= 12, sub-warp above; 1 = sub-warp always
 static bool use_tpm(int n) { return g_det_kernel == 0 && n >= 2 && n <= kTpmMaxN; }
@@ -373,6 +374,12 @@ static int64_t pairs_nchunk(int64_t nrow, int64_t ngroup, int n, int k, int ns, 
 extern "C" int64_t apyib_det_matvec_pairs_work_len(int64_t nrow, int64_t ngroup, int ny, int n, int k, int ns, int nc) {
     const int64_t c = pairs_nchunk(nrow, ngroup, n, k, ns, nc);
     return (c > 0 ? c : 1) * ny * nrow;
+}
+
+extern "C" int apyib_det_set_pairs_variant(int which) {
+    APYIB_REQUIRE(which == 0 || which == 1, "0 = generic (1..4 vectors, predicated), 1 = + single-vector specialisation");
+    g_pairs_variant = which;
+    return APYIB_OK;
 }
 
 static int det_matvec_pairs_impl(const void *d_S, int nS, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,

@@ -38,7 +38,9 @@ template <int N, int K> struct pfx_cfg {
     static constexpr int LCOUNT = NPRE * (N - 1) - NPRE * (NPRE - 1) / 2;   // sum_{k<NPRE} (N-1-k)
 };
 
-template <int N, int K, bool SSM>
+// NYT = 0: up to 4 amplitude vectors, count given at run time (predicated); NYT = 1: exactly one vector, no
+// predicated slots in the pair loop (the doubles x doubles table of every (beta x pp/pn/np/nn) stack has one).
+template <int N, int K, bool SSM, int NYT = 0>
 __global__ void __launch_bounds__(pfx_threads(N), 1)
 det_pairs_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__ rows, int64_t nrow,
                  const int32_t *__restrict__ cols, int64_t ngroup, int64_t npair, const int32_t *__restrict__ cand,
@@ -65,7 +67,7 @@ det_pairs_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__
     const int lane = threadIdx.x & 31;
     const int64_t nrg = (nrow + 31) >> 5;
     const int64_t ntask = nrg * nchunk;
-    constexpr int NYMAX = 4;
+    constexpr int NYMAX = NYT ? NYT : 4;
     auto ld = [&](int off) -> cplx { return SSM ? Ssm[off] : ldg(&S[off]); };
 
     for (int64_t task = (int64_t)blockIdx.x * (T / 32) + (threadIdx.x >> 5); task < ntask;
@@ -272,7 +274,7 @@ det_pairs_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__
                         d.y *= sg;
 #pragma unroll
                         for (int q = 0; q < NYMAX; ++q)
-                            if (q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + cc]);
+                            if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + cc]);
                     }
                 }
             } else {
@@ -285,17 +287,19 @@ det_pairs_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__
                     d.y *= sg;
 #pragma unroll
                     for (int q = 0; q < NYMAX; ++q)
-                        if (q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + cc]);
+                        if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + cc]);
                 }
             }
         }
         if (rvalid) {
 #pragma unroll
             for (int q = 0; q < NYMAX; ++q)
-                if (q < ny) out[(ch * ny + q) * nrow + r] = z[q];
+                if (NYT || q < ny) out[(ch * ny + q) * nrow + r] = z[q];
         }
     }
 }
+
+int g_pairs_variant = 0;      // 0 = one kernel for 1..4 vectors; 1 = + single-vector specialisation for K = 2
 
 // block size the shared-memory footprint allows (0 = does not fit: caller falls back to dets_tpm.cu)
 template <int N, int K> static int pfx_block(int ns, int nc, bool *ssm, int *slots, size_t *smem) {
@@ -330,10 +334,17 @@ static int launch_pairs_nk(cudaStream_t st, const cplx *S, int ns, const int32_t
     int64_t blocks = (ntask + T / 32 - 1) / (T / 32);
     if (blocks > 148) blocks = 148;
     auto kern = ssm ? det_pairs_kernel<N, K, true> : det_pairs_kernel<N, K, false>;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[ssm]) {
+    int slot = ssm ? 1 : 0;
+    if constexpr (K == 2) {
+        if (g_pairs_variant == 1 && ny == 1) {      // single-vector specialisation (apyib_det_set_pairs_variant)
+            kern = ssm ? det_pairs_kernel<N, K, true, 1> : det_pairs_kernel<N, K, false, 1>;
+            slot += 2;
+        }
+    }
+    static bool attr_done[4] = {false, false, false, false};
+    if (!attr_done[slot]) {
         APYIB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfxSmemMax));
-        attr_done[ssm] = true;
+        attr_done[slot] = true;
     }
     kern<<<dim3((unsigned)blocks, (unsigned)nS), T, smem, st>>>(S, ns, rows, nrow, cols, ngroup, npair, cand, nc, slots,
                                                                 gchunk, nchunk, csign, cindex, Y, ny, ncol, out, y_stride,

@@ -248,6 +248,10 @@ int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, const int32_t 
                            const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,
                            int64_t ncol, int64_t group_len, const int32_t *d_cand, int nc, const void *d_Y, int ny,
                            void *d_Z, void *d_work, void *stream);
+/* Kernel variant of the prefix-shared LU: 0 (default) = one kernel for 1..4 amplitude vectors (count predicated
+ * at run time); 1 = additionally a single-vector specialisation for k = 2 (no predicated issue slots in the
+ * pair loop).  Same results either way.                                                                   */
+int apyib_det_set_pairs_variant(int which);
 /* Stacks of overlaps: the same row / column lists applied to nS overlap matrices d_S[nS][ns][ns] in ONE launch
  * (grid.y = overlap) -- the 12 (beta x pp/pn/np/nn) overlaps of one nuclear coordinate, the 6N pu/nu overlaps, ...
  * (aats.py:714-1008 evaluates compute_all_dets overlap by overlap).  Outputs are [nS][...] contiguous; overlap s

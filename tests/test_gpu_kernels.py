@@ -1,6 +1,8 @@
 """GPU parity tests of the individual kernels (through the C-ABI) against numpy / the oracle."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -425,3 +427,31 @@ def test_det_stack_entry_points_match_single_overlap_calls(n, nv, nf):
                     check(lib.apyib_det_matvec_pairs_stack(ptr(dS), nS, ns, n, ck, ptr(rows), nrow, cp, sp, ip, ncol, gl, ptr(cand),
                                                            nc, ptr(dY), ny * ncol if per else 0, ny, ptr(Z2), ptr(work), stream_ptr()))
                     assert np.abs(to_host(Z2) - want).max() <= 1e-10 * scale
+
+
+@pytest.mark.skipif(os.environ.get("APYIB_B200_EXPERIMENTAL") != "1", reason="experimental kernel variant, not yet validated on a B200")
+@pytest.mark.parametrize("n,nv", [(4, 5), (9, 6), (9, 13), (12, 4)])
+def test_det_pairs_single_vector_variant_matches_generic(n, nv):
+    """apyib_det_set_pairs_variant(1): the single-vector specialisation of the prefix-shared LU kernel must give
+    bit-identical results to the generic kernel (same arithmetic, fewer predicated issue slots)."""
+    import apyib_b200
+    from apyib_b200._lib import lib, check
+    from apyib_b200.aats import _Tables, _det_matvec
+    from apyib_b200.device import to_device, to_host
+    rng = np.random.default_rng(40 + n)
+    ns = n + nv
+    S = to_device(np.eye(ns) + 0.3 * (rng.standard_normal((ns, ns)) + 1j * rng.standard_normal((ns, ns))), torch.complex128)
+    T = _Tables.get(n, 0, nv)
+    rows, cols = T.L[2], T.L[2]
+    Y = to_device(rng.standard_normal((1, cols.shape[0])) + 1j * rng.standard_normal((1, cols.shape[0])), torch.complex128)
+    old = apyib_b200.config.LU_PREFIX
+    apyib_b200.config.LU_PREFIX = True
+    try:
+        res = []
+        for variant in (0, 1):
+            check(lib.apyib_det_set_pairs_variant(variant))
+            res.append(to_host(_det_matvec(S, n, rows, cols, Y, T.LS[2], T.PFX[2], 2)))
+        assert np.array_equal(res[0], res[1])
+    finally:
+        check(lib.apyib_det_set_pairs_variant(1 if apyib_b200.config.PAIRS_SINGLE_VECTOR else 0))
+        apyib_b200.config.LU_PREFIX = old
