@@ -71,6 +71,27 @@ def test_argument_errors_are_reported_not_crashed():
     assert rc < 0 and b"null" in lib.apyib_last_error()
     b = (C.c_int32 * 16)()
     assert lib.apyib_get_slices(3, 5, 0, 0, b) < 0
+    # the entry points added for stacks / prefix sharing validate before they launch (no device needed for that)
+    one = C.c_void_p(8)                                     # non-null dummy, never dereferenced on these paths
+    assert lib.apyib_det_matvec_pairs(None, 22, 9, 2, one, 10, one, one, one, 78, 78, one, 13, one, 1, one, one, None) == -1
+    assert b"null" in lib.apyib_last_error()
+    assert lib.apyib_det_matvec_pairs(one, 22, 9, 2, one, 10, one, one, one, 78, 77, one, 13, one, 1, one, one, None) == -1
+    assert b"group_len" in lib.apyib_last_error()
+    assert lib.apyib_det_matvec_pairs(one, 22, 9, 2, one, 10, one, one, one, 100, 78, one, 13, one, 1, one, one, None) == -1
+    assert b"whole number of groups" in lib.apyib_last_error()
+    assert lib.apyib_det_matvec_pairs(one, 22, 9, 3, one, 10, one, one, one, 78, 78, one, 13, one, 1, one, one, None) == -1
+    assert lib.apyib_det_matvec_pairs(one, 22, 9, 2, one, 10, one, one, one, 78, 78, one, 13, one, 5, one, one, None) == -1
+    assert lib.apyib_det_matvec_pairs_stack(one, 0, 22, 9, 2, one, 10, one, one, one, 78, 78, one, 13, one, 0, 1, one, one, None) == -1
+    assert lib.apyib_det_matvec_pairs(one, 30, 14, 2, one, 10, one, one, one, 120, 120, one, 16, one, 1, one, one, None) == -3
+    assert b"n <= 12" in lib.apyib_last_error()             # APYIB_ERR_UNSUPPORTED: callers fall back to the per-matrix LU
+    assert lib.apyib_det_outer_stack(one, 3, 22, 9, one, 10, one, one, None, 10, one, None) == -1      # sign without index
+    assert lib.apyib_det_matvec_stack(one, 70000, 22, 9, one, 10, one, None, None, 10, one, 0, 1, one, one, None) == -1
+    assert lib.apyib_det_set_pairs_variant(2) == -1 and lib.apyib_det_set_pairs_variant(0) == 0
+    d4 = (C.c_int64 * 4)(3, 3, 3, 3)
+    p4, s4 = (C.c_int32 * 4)(0, 1, 2, 3), (C.c_int64 * 4)(0, 0, 0, 0)
+    assert lib.apyib_gather4_batch(0, one, d4, 0, 0, 81, one, d4, p4, s4, 1.0, p4, s4, 0.0, None) == -1       # nb = 0
+    s_bad = (C.c_int64 * 4)(1, 0, 0, 0)
+    assert lib.apyib_gather4_batch(0, one, d4, 0, 2, 81, one, d4, p4, s_bad, 1.0, p4, s4, 0.0, None) == -1    # block out of range
 
 
 def test_geometry_round_trip_and_units():
