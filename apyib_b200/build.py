@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libapyib_b200.so")
-SOURCES = ["contract.cu", "contract_tma.cu", "stream.cu", "dets.cu", "dets_tpm.cu", "dets_pairs.cu", "lemma.cu", "capi.cu"]
+SOURCES = ["contract.cu", "contract_tma.cu", "stream.cu", "dets.cu", "dets_tpm.cu", "dets_pairs.cu", "dets_pairs_k2_small.cu", "dets_pairs_k2_large.cu", "lemma.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 OBJDIR = os.path.join(LIBDIR, "obj")
