@@ -61,6 +61,10 @@ LU_PREFIX = _os.environ.get("APYIB_B200_LU_PREFIX", "1") == "1"
 # in its pair loop (155 SASS instructions per pair against 31).  apyib_det_set_pairs_variant(1).
 PAIRS_SINGLE_VECTOR = _os.environ.get("APYIB_B200_PAIRS_NY1", "0") == "1"
 
+# EXPERIMENTAL (not yet measured on a B200; off): solve the real and the complex batch of finite-difference points
+# concurrently (one host thread + one stream each) instead of one after the other (ci_wfn.solve_many).
+SOLVE_CONCURRENT = _os.environ.get("APYIB_B200_SOLVE_CONCURRENT", "0") == "1"
+
 # AAT assembly: replay the device part of every overlap stack (aats.AAT._blocks_device) from a CUDA graph
 # captured once per stack shape (static input buffers, private memory pool).  Same kernels, same order, same
 # results; removes the host launch overhead of ~200 launches per stack on the LU path (H2O2/6-31G shape: 0.2045 -> 0.196 s

@@ -1,6 +1,8 @@
 """GPU parity of the drop-in solver classes against the oracle (numpy restatement of the
 reference) on the same seeded synthetic inputs.  Tolerances are the north star's:
 energies 1e-10 Eh, amplitudes 1e-9 max-abs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -205,3 +207,29 @@ def test_perturbed_cid_amplitudes(nbf, no, nf, cplx, seed):
     G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synthetic_linear_response_cid.npz"))
     name = {901: "r7", 902: "c6", 903: "r8fc"}[seed]
     assert abs(dE - G[name + "/dE"]) < 1e-8 and np.abs(dt2 - G[name + "/dt2"]).max() < 1e-8
+
+
+@pytest.mark.skipif(os.environ.get("APYIB_B200_EXPERIMENTAL") != "1", reason="experimental path, not yet validated on a B200")
+@pytest.mark.parametrize("method", ["CISD", "CID_SO"])
+def test_concurrent_dtype_groups_equal_sequential(method):
+    """config.SOLVE_CONCURRENT: real and complex batches solved at the same time on two streams == sequential"""
+    import apyib_b200
+    from apyib_b200.ci_wfn import solve_many
+    ws = [orc.rotated_wfn(7, 3, 600 + k, k % 2 == 1, 0) for k in range(6)]
+    p = par(method)
+    cfg = apyib_b200.config
+    old = (cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE)
+    try:
+        for dev_out in (False, True):
+            cfg.RETURN_DEVICE = dev_out
+            cfg.SOLVE_CONCURRENT = False
+            seq = solve_many(method, p, ws)
+            cfg.SOLVE_CONCURRENT = True
+            con = solve_many(method, p, ws)
+            for a, b in zip(seq, con):
+                for x, y in zip(a, b):
+                    x = x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
+                    y = y.cpu().numpy() if hasattr(y, "cpu") else np.asarray(y)
+                    assert np.array_equal(x, y)
+    finally:
+        cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE = old
