@@ -65,6 +65,10 @@ PAIRS_SINGLE_VECTOR = _os.environ.get("APYIB_B200_PAIRS_NY1", "0") == "1"
 # concurrently (one host thread + one stream each) instead of one after the other (ci_wfn.solve_many).
 SOLVE_CONCURRENT = _os.environ.get("APYIB_B200_SOLVE_CONCURRENT", "0") == "1"
 
+# EXPERIMENTAL (not yet measured on a B200; off): (2J - K)[D] of the host SCF as one contraction launch per iteration
+# on a device copy of 2(mn|ls) - (ml|ns) (hostchem.hf_wfn._device_jk).
+SCF_DEVICE_JK = _os.environ.get("APYIB_B200_SCF_DEVICE_JK", "0") == "1"
+
 # AAT assembly: replay the device part of every overlap stack (aats.AAT._blocks_device) from a CUDA graph
 # captured once per stack shape (static input buffers, private memory pool).  Same kernels, same order, same
 # results; removes the host launch overhead of ~200 launches per stack on the LU path (H2O2/6-31G shape: 0.2045 -> 0.196 s

@@ -380,6 +380,14 @@ def _diis(res_vec, t_vec, e_iter, t_iter, iteration, max_DIIS=7):      # utils.p
     return t_iter @ c[:-1], e_iter, t_iter
 
 
+def _device_jk_enabled():
+    from . import config
+    if not config.SCF_DEVICE_JK:
+        return False
+    import torch
+    return torch.cuda.is_available()
+
+
 class hf_wfn(object):
     def __init__(self, H, charge=0):
         self.H = H
@@ -406,6 +414,7 @@ class hf_wfn(object):
                 except Exception:
                     pass
         GK = GK[1]
+        jk_dev = self._device_jk() if _device_jk_enabled() else None
         e, C_p = np.linalg.eigh(X @ H_core @ X)
         C = X @ C_p
         D = 2 * C[:, :nd] @ C[:, :nd].conj().T
@@ -414,7 +423,9 @@ class hf_wfn(object):
         while i <= parameters["max_iterations"]:
             E_old, D_old = E_SCF, D
             d = D.reshape(-1)
-            if np.iscomplexobj(d) and not np.iscomplexobj(GK):      # avoid upcasting the nbf^4 tensor
+            if jk_dev is not None:                                  # (2J - K)[D] on the device
+                jk = jk_dev(d)
+            elif np.iscomplexobj(d) and not np.iscomplexobj(GK):    # avoid upcasting the nbf^4 tensor
                 jk = (GK @ d.real) + 1j * (GK @ d.imag)
             else:
                 jk = GK @ d
@@ -438,3 +449,34 @@ class hf_wfn(object):
             i += 1
         self.E_SCF = E_SCF
         return E_SCF, self.C
+
+    def _device_jk(self):
+        """EXPERIMENTAL (config.SCF_DEVICE_JK, off): the nbf^4 part of the Fock build, (2J - K)[D] =
+        sum_ls D_ls (2 (mn|ls) - (ml|ns)) (hf_wfn.py:81-107, utils.py:249), as one launch of the contraction kernel
+        per SCF iteration on a device copy of 2(mn|ls) - (ml|ns) (one gather from the AO integrals, which the
+        correlated solver needs on the device anyway).  D goes up and (2J - K)[D] comes back as nbf^2 numbers;
+        DIIS, the nbf^3 algebra and the eigensolver stay on the host.  Real AO integrals only."""
+        import torch
+        from .contraction import contract_new
+        from .device import to_device, to_host
+        from .utils import gather4
+        H = self.H
+        if np.iscomplexobj(H.ERI):
+            return None
+        n = self.nbf
+        cache = H.__dict__.setdefault("_apyib_b200_dev", None) or {}
+        H._apyib_b200_dev = cache
+        if "r" in cache:
+            G = cache["r"][1]
+        else:
+            G = cache.get("eri_r")
+            if G is None:
+                G = cache["eri_r"] = to_device(np.asarray(H.ERI), torch.float64)
+        GK = gather4(G, 0, (n, n, n, n), [0, 1, 2, 3], [0, 0, 0, 0], 2.0, [0, 2, 1, 3], [0, 0, 0, 0], -1.0).reshape(n * n, n * n)
+
+        def jk(d):
+            parts = np.stack([d.real, d.imag]) if np.iscomplexobj(d) else d.reshape(1, -1)
+            out = to_host(contract_new("xy,qy->qx", GK, to_device(np.ascontiguousarray(parts), torch.float64)))
+            return out[0] + 1j * out[1] if np.iscomplexobj(d) else out[0]
+
+        return jk

@@ -55,7 +55,8 @@ def ao_on_device(wfn, want_complex):
         h = np.asarray(H.T) + np.asarray(H.V)
         if not want_complex and (np.iscomplexobj(h) or np.iscomplexobj(H.ERI)):
             raise TypeError("complex integrals need the complex path")
-        cache[key] = (to_device(h, dt), to_device(np.asarray(H.ERI), dt))
+        G = None if want_complex else cache.get("eri_r")      # uploaded by the device-assisted SCF already (hostchem)
+        cache[key] = (to_device(h, dt), G if G is not None else to_device(np.asarray(H.ERI), dt))
     return cache[key]
 
 

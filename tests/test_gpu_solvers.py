@@ -233,3 +233,29 @@ def test_concurrent_dtype_groups_equal_sequential(method):
                     assert np.array_equal(x, y)
     finally:
         cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE = old
+
+
+@pytest.mark.skipif(os.environ.get("APYIB_B200_EXPERIMENTAL") != "1", reason="experimental path, not yet validated on a B200")
+@pytest.mark.parametrize("field", [False, True])
+def test_scf_with_device_jk_equals_host_scf(field):
+    """config.SCF_DEVICE_JK: (2J - K)[D] of every SCF iteration on the device == the host GEMV"""
+    import apyib_b200
+    from apyib_b200 import hostchem as hc
+    prov = hc.SyntheticProvider(12, 4, 2, seed=21)
+    p = {"geom": prov.geometry_string(), "basis": "synthetic", "method": "CISD", "freeze_core": False,
+         "F_el": [0.0] * 3, "F_mag": [0.0, 1e-3 if field else 0.0, 0.0], "provider": prov, "DIIS": True,
+         "max_iterations": 100, "e_convergence": 1e-13, "d_convergence": 1e-13}
+    cfg = apyib_b200.config
+    old = cfg.SCF_DEVICE_JK
+    res = []
+    try:
+        for flag in (False, True):
+            cfg.SCF_DEVICE_JK = flag
+            w = hc.hf_wfn(hc.Hamiltonian(p))
+            E, C = w.solve_SCF(p)
+            res.append((E, np.abs(C), w.eps))
+    finally:
+        cfg.SCF_DEVICE_JK = old
+    assert abs(res[0][0] - res[1][0]) < 1e-11 and np.abs(res[0][2] - res[1][2]).max() < 1e-10
+    assert np.abs(res[0][1] - res[1][1]).max() < 1e-8         # |C|: eigenvector phases are arbitrary
+    assert np.iscomplexobj(res[1][0]) == np.iscomplexobj(res[0][0])

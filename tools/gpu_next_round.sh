@@ -3,12 +3,13 @@
 # round-1 GPU budget was spent (all OFF by default):
 #   APYIB_B200_PAIRS_NY1=1          single-vector specialisation of the prefix-shared LU kernel
 #   APYIB_B200_SOLVE_CONCURRENT=1   real and complex batches of a molecule solved concurrently on two streams
+#   APYIB_B200_SCF_DEVICE_JK=1      (2J - K)[D] of the host SCF on the device (untimed host part; test only)
 # gpurun --timeout 600 -- 'bash tools/gpu_next_round.sh'
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 leg() { name=$1; t=$2; shift 2; s=$(date +%s); timeout "$t" "$@" > gpurun_out/$name.log 2>&1; echo "$name rc=$? $(( $(date +%s) - s ))s" | tee -a gpurun_out/legs_next.txt; }
 : > gpurun_out/legs_next.txt
-APYIB_B200_EXPERIMENTAL=1 leg t_exp 240 python -m pytest tests -m gpu -x -q -k "single_vector or concurrent_dtype"
+APYIB_B200_EXPERIMENTAL=1 leg t_exp 240 python -m pytest tests -m gpu -x -q -k "single_vector or concurrent_dtype or device_jk"
 leg b_base 200 python bench.py
 APYIB_B200_PAIRS_NY1=1 leg b_ny1 200 python bench.py
 APYIB_B200_SOLVE_CONCURRENT=1 leg b_conc 200 python bench.py
