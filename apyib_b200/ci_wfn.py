@@ -663,51 +663,9 @@ def solve_many(method, parameters, wfns, print_level=0):
     for k, c in enumerate(cis):
         groups.setdefault((c._ERI_dev.dtype, tuple(c._ERI_dev.shape), len(c.eps_o)), []).append(k)
     out = [None] * len(cis)
-    if config.SOLVE_CONCURRENT and len(groups) > 1:
-        _solve_groups_concurrently(method, parameters, cis, list(groups.values()), out, print_level)
-        return out
     for idx in groups.values():
         res, its = solve_batch(method, parameters, [cis[k].point() for k in idx], print_level)
         for k, r, it in zip(idx, res, its):
             out[k] = r
             cis[k].iterations = it
     return out
-
-
-def _solve_groups_concurrently(method, parameters, cis, items, out, print_level):
-    """EXPERIMENTAL (config.SOLVE_CONCURRENT, off): the real and the complex batch of a molecule are independent and
-    each is latency bound (a few dozen small launches and one 48-byte read-back per iteration), so they are solved
-    at the same time -- one host thread and one CUDA stream per batch, the unchanged `solve_batch` in each (ctypes
-    and the read-back release the GIL).  Results are identical to the sequential path."""
-    import threading
-    dev = torch.cuda.current_device()
-    cur = torch.cuda.current_stream()
-    errors = []
-
-    def work(idx, stream):
-        try:
-            torch.cuda.set_device(dev)
-            with torch.cuda.stream(stream):
-                res, its = solve_batch(method, parameters, [cis[k].point() for k in idx], print_level)
-            for k, r, it in zip(idx, res, its):
-                out[k] = r
-                cis[k].iterations = it
-        except BaseException as exc:           # re-raised on the calling thread
-            errors.append(exc)
-
-    streams = [torch.cuda.Stream() for _ in items]
-    for st in streams:
-        st.wait_stream(cur)                    # the MO integrals were produced on the caller's stream
-    threads = [threading.Thread(target=work, args=(idx, st)) for idx, st in zip(items, streams)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    for st in streams:
-        cur.wait_stream(st)
-    if errors:
-        raise errors[0]
-    for r in out:                              # device-resident results were allocated on a side stream
-        for x in (r or ()):
-            if isinstance(x, torch.Tensor) and x.is_cuda:
-                x.record_stream(cur)

@@ -56,17 +56,14 @@ LU_REUSE = True
 # per-matrix LU (agreement ~1e-15 relative, not bitwise: the trailing k x k block is written out).
 LU_PREFIX = _os.environ.get("APYIB_B200_LU_PREFIX", "1") == "1"
 
-# EXPERIMENTAL (not yet measured on a B200; off): single-vector specialisation of the prefix-shared LU kernel for the
-# doubles x doubles table -- the generic kernel carries predicated-off issue slots for up to 4 amplitude vectors
-# in its pair loop (155 SASS instructions per pair against 31).  apyib_det_set_pairs_variant(1).
-PAIRS_SINGLE_VECTOR = _os.environ.get("APYIB_B200_PAIRS_NY1", "0") == "1"
+# Single-vector specialisation of the prefix-shared LU kernel for the doubles x doubles table -- the generic kernel
+# carries predicated-off issue slots for up to 4 amplitude vectors in its pair loop (155 SASS instructions per pair
+# against 31).  apyib_det_set_pairs_variant(1).  Validated on a B200 in round 2 (bit-identical to the generic kernel;
+# 0.726 -> 0.552 ms per 12-overlap stack at n = 9): ON.
+PAIRS_SINGLE_VECTOR = _os.environ.get("APYIB_B200_PAIRS_NY1", "1") == "1"
 
-# EXPERIMENTAL (not yet measured on a B200; off): solve the real and the complex batch of finite-difference points
-# concurrently (one host thread + one stream each) instead of one after the other (ci_wfn.solve_many).
-SOLVE_CONCURRENT = _os.environ.get("APYIB_B200_SOLVE_CONCURRENT", "0") == "1"
-
-# EXPERIMENTAL (not yet measured on a B200; off): (2J - K)[D] of the host SCF as one contraction launch per iteration
-# on a device copy of 2(mn|ls) - (ml|ns) (hostchem.hf_wfn._device_jk).
+# OPTIONAL (validated on a B200 in round 2 against the host GEMV; host SCF is untimed, so off by default): (2J - K)[D] of the host SCF as one contraction launch per iteration
+# on a device copy of 2(mn|ls) - (ml|ns) (hostchem._device_jk).
 SCF_DEVICE_JK = _os.environ.get("APYIB_B200_SCF_DEVICE_JK", "0") == "1"
 
 # AAT assembly: replay the device part of every overlap stack (aats.AAT._blocks_device) from a CUDA graph

@@ -1,0 +1,451 @@
+"""Host-side inputs of the hot path: geometry, AO integrals and the complex-HF SCF.
+
+The north star keeps "per-geometry AO integrals (Psi4/MintsHelper) and the complex-HF SCF"
+on the host; this module is that host side.  It mirrors apyib/hamiltonian.py:13-70 and
+apyib/hf_wfn.py:14-170 closely enough that `energy()` / `finite_difference` / `AAT` keep their
+reference signatures, and gets its AO integrals from an *integral provider*:
+
+  * Psi4Provider      -- the reference's own source (used automatically when psi4 imports);
+  * SGaussianProvider -- a closed-form integral engine for s-type contracted Gaussians
+                         (H/He with STO-3G / STO-6G), enough for the reference's (H2)_2 test
+                         molecule, so its golden energies / AAT tensors can be reproduced here
+                         without Psi4;
+  * SyntheticProvider -- the synthetic per-point model of SURVEY.md 8(d), extended so that
+                         the Hamiltonian depends smoothly on "nuclear" coordinates and on the
+                         magnetic / electric field (any nbf / ndocc / natom, for benchmarks).
+
+None of this is GPU work and none of it is timed as the hot path; it is numpy.  The package is
+neutral ground: the product (apyib_b200.hostchem re-exports it), the oracle and bench.py's reference arm
+all take their host inputs from here, so neither the oracle nor the reference arm imports the product.
+"""
+from __future__ import annotations
+
+import math
+import re
+
+import numpy as np
+
+BOHR2ANG = 0.52917721067
+_Z = {s: z for z, s in enumerate("X H HE LI BE B C N O F NE NA MG AL SI P S CL AR K CA SC TI V CR MN FE CO NI CU ZN GA GE AS SE BR KR "
+                                  "RB SR Y ZR NB MO TC RU RH PD AG CD IN SN SB TE I XE".split())}
+
+
+# ---------------------------------------------------------------------------------------------
+# molecule (the slice of psi4.core.Molecule that fin_diff.py:17-23, 286-307 uses)
+# ---------------------------------------------------------------------------------------------
+class Molecule:
+    def __init__(self, symbols, coords_bohr, directives=()):
+        self.symbols = list(symbols)
+        self._xyz = np.array(coords_bohr, dtype=float).reshape(-1, 3)
+        self.directives = list(directives)
+
+    @classmethod
+    def from_string(cls, geom):
+        syms, xyz, directives, unit = [], [], [], "angstrom"
+        for line in geom.strip().splitlines():
+            parts = line.split()
+            if not parts:
+                continue
+            if len(parts) == 4 and re.match(r"^[A-Za-z]+\d*$", parts[0]):
+                try:
+                    xyz.append([float(x) for x in parts[1:]])
+                    syms.append(re.sub(r"\d+$", "", parts[0]))
+                    continue
+                except ValueError:
+                    pass
+            directives.append(line.strip())
+            if parts[0].lower() == "units":
+                unit = parts[1].lower()
+        xyz = np.array(xyz, dtype=float).reshape(-1, 3)
+        if unit.startswith("ang"):
+            xyz = xyz / BOHR2ANG
+            directives = [d for d in directives if not d.lower().startswith("units")]
+        if not any(d.lower().startswith("units") for d in directives):
+            directives.append("units bohr")
+        return cls(syms, xyz, directives)
+
+    def natom(self):
+        return len(self.symbols)
+
+    def geometry(self):
+        return self._xyz.copy()
+
+    def set_geometry(self, xyz):
+        self._xyz = np.array(xyz, dtype=float).reshape(-1, 3)
+
+    def true_atomic_number(self, i):
+        return _Z[self.symbols[i].upper()]
+
+    def create_psi4_string_from_molecule(self):
+        lines = ["%s %s %s %s" % (s, repr(float(x)), repr(float(y)), repr(float(z)))
+                 for s, (x, y, z) in zip(self.symbols, self._xyz)]
+        return "\n".join(lines + self.directives) + "\n"
+
+    def nuclear_repulsion_energy(self, dipole_field=(0.0, 0.0, 0.0)):
+        Z = np.array([self.true_atomic_number(i) for i in range(self.natom())], dtype=float)
+        e = 0.0
+        for i in range(self.natom()):
+            for j in range(i):
+                e += Z[i] * Z[j] / np.linalg.norm(self._xyz[i] - self._xyz[j])
+        e += float(np.dot(np.asarray(dipole_field, dtype=float), (Z[:, None] * self._xyz).sum(0)))
+        return e
+
+
+# ---------------------------------------------------------------------------------------------
+# providers
+# ---------------------------------------------------------------------------------------------
+class BasisHandle:
+    """What the reference passes around as a psi4 BasisSet (energy.py:24, aats.py:56-105)."""
+
+    def __init__(self, provider, molecule, nbf, nfzc, payload=None):
+        self.provider, self.molecule, self._nbf, self._nfzc, self.payload = provider, molecule, nbf, nfzc, payload
+
+    def nbf(self):
+        return self._nbf
+
+    def n_frozen_core(self):
+        return self._nfzc
+
+
+def provider_ao_overlap(bra_basis, ket_basis):
+    """Mixed-geometry AO overlap <bra AO | ket AO> (mints.ao_overlap(b1, b2), utils.py:371-376)."""
+    return bra_basis.provider.ao_overlap(bra_basis, ket_basis)
+
+
+_STO = {   # s-type contractions for H / He, (exponents, coefficients) -- EMSL / Psi4 library values
+    ("STO-3G", "H"): ([3.42525091, 0.62391373, 0.16885540], [0.15432897, 0.53532814, 0.44463454]),
+    ("STO-3G", "HE"): ([6.36242139, 1.15892300, 0.31364979], [0.15432897, 0.53532814, 0.44463454]),
+    ("STO-6G", "H"): ([35.52322122, 6.513143725, 1.822142904, 0.625955266, 0.243076747, 0.100112428],
+                      [0.00916359628, 0.04936149294, 0.16853830490, 0.37056279970, 0.41649152980, 0.13033408410]),
+    ("STO-6G", "HE"): ([65.98456824, 12.09819836, 3.384639924, 1.162715163, 0.451516322, 0.185959356],
+                       [0.00916359628, 0.04936149294, 0.16853830490, 0.37056279970, 0.41649152980, 0.13033408410]),
+}
+
+
+def _boys0(t):
+    t = np.asarray(t, dtype=float)
+    out = np.empty_like(t)
+    small = t < 1e-8
+    ts = np.where(small, 1.0, t)
+    out = 0.5 * np.sqrt(np.pi / ts) * np.vectorize(math.erf)(np.sqrt(ts))
+    return np.where(small, 1.0 - t / 3.0, out)
+
+
+class SGaussianProvider:
+    """Closed-form integrals over contracted s-type Gaussians."""
+
+    def __init__(self, basis_name):
+        self.name = basis_name.upper()
+
+    def supports(self, molecule):
+        return all((self.name, s.upper()) in _STO for s in molecule.symbols)
+
+    def _shells(self, molecule):
+        """primitive arrays: center index, exponent, normalised contraction coefficient"""
+        cen, exps, cof, owner = [], [], [], []
+        for ia, s in enumerate(molecule.symbols):
+            e, c = _STO[(self.name, s.upper())]
+            e, c = np.array(e), np.array(c)
+            cn = c * (2 * e / np.pi) ** 0.75
+            p = e[:, None] + e[None, :]
+            norm = np.sqrt((cn[:, None] * cn[None, :] * (np.pi / p) ** 1.5).sum())
+            for ek, ck in zip(e, cn / norm):
+                cen.append(ia); exps.append(ek); cof.append(ck); owner.append(ia)
+        return np.array(cen), np.array(exps), np.array(cof), np.array(owner)
+
+    def basis(self, molecule):
+        return BasisHandle(self, Molecule(molecule.symbols, molecule.geometry(), molecule.directives),
+                           molecule.natom(), 0)
+
+    def _pair(self, mol_a, mol_b):
+        ca, ea, wa, oa = self._shells(mol_a)
+        cb, eb, wb, ob = self._shells(mol_b)
+        A, B = mol_a.geometry()[ca], mol_b.geometry()[cb]
+        p = ea[:, None] + eb[None, :]
+        mu = ea[:, None] * eb[None, :] / p
+        AB2 = ((A[:, None, :] - B[None, :, :]) ** 2).sum(-1)
+        P = (ea[:, None, None] * A[:, None, :] + eb[None, :, None] * B[None, :, :]) / p[:, :, None]
+        S = (np.pi / p) ** 1.5 * np.exp(-mu * AB2)
+        W = wa[:, None] * wb[None, :]
+        return dict(p=p, mu=mu, AB2=AB2, P=P, S=S, W=W, oa=oa, ob=ob, A=A, B=B, ea=ea, eb=eb)
+
+    @staticmethod
+    def _contract2(X, oa, ob, na, nb):
+        out = np.zeros((na, nb) + X.shape[2:])
+        np.add.at(out, (oa[:, None], ob[None, :]), X)
+        return out
+
+    def ao_overlap(self, bra, ket):
+        q = self._pair(bra.molecule, ket.molecule)
+        return self._contract2(q["S"] * q["W"], q["oa"], q["ob"], bra.nbf(), ket.nbf())
+
+    def integrals(self, molecule):
+        n = molecule.natom()
+        q = self._pair(molecule, molecule)
+        c2 = lambda X: self._contract2(X, q["oa"], q["ob"], n, n)
+        S, W, p, mu = q["S"], q["W"], q["p"], q["mu"]
+        out = {"S": c2(S * W), "T": c2(mu * (3 - 2 * mu * q["AB2"]) * S * W)}
+        V = np.zeros_like(S)
+        R = molecule.geometry()
+        for ic in range(n):
+            Z = molecule.true_atomic_number(ic)
+            PC2 = ((q["P"] - R[ic]) ** 2).sum(-1)
+            V += -Z * (2 * np.pi / p) * np.exp(-mu * q["AB2"]) * _boys0(p * PC2)
+        out["V"] = c2(V * W)
+        # electronic dipole (-r) and angular momentum -(r x grad)  [Psi4 ao_dipole / ao_angular_momentum]
+        out["dipole"] = [-c2(q["P"][:, :, k] * S * W) for k in range(3)]
+        AxB = np.cross(q["A"][:, None, :], q["B"][None, :, :])
+        out["angmom"] = [-c2(2 * mu * AxB[:, :, k] * S * W) for k in range(3)]
+        # ERIs over primitive pairs
+        npr = S.shape[0]
+        K = (np.exp(-mu * q["AB2"]) * W).reshape(-1)
+        pp = p.reshape(-1)
+        PP = q["P"].reshape(-1, 3)
+        PQ2 = ((PP[:, None, :] - PP[None, :, :]) ** 2).sum(-1)
+        alpha = pp[:, None] * pp[None, :] / (pp[:, None] + pp[None, :])
+        G = (2 * np.pi ** 2.5 / (pp[:, None] * pp[None, :] * np.sqrt(pp[:, None] + pp[None, :]))
+             * K[:, None] * K[None, :] * _boys0(alpha * PQ2))
+        G = G.reshape(npr, npr, npr, npr)
+        o = q["oa"]
+        eri = np.zeros((n, n, n, n))
+        np.add.at(eri, (o[:, None, None, None], o[None, :, None, None], o[None, None, :, None], o[None, None, None, :]), G)
+        out["ERI"] = eri
+        return out
+
+    def nelectron(self, molecule):
+        return sum(molecule.true_atomic_number(i) for i in range(molecule.natom()))
+
+    def n_frozen_core(self, molecule, freeze_core):
+        return 0
+
+
+class SyntheticProvider:
+    """Smooth synthetic 'molecule': orthonormal AOs (S = 1 for every pair of geometries),
+    H(R) = diag(eps) + sum_alpha (R - R0)_alpha dH_alpha, fixed Hermitian-symmetric (pq|rs) of the
+    SURVEY 8(d) generator, angular-momentum-like antisymmetric matrices for the magnetic field
+    and symmetric dipole-like matrices for the electric field."""
+
+    def __init__(self, nbf, ndocc, natom, seed=0, nfzc=0, scale=None):
+        if scale is None:                 # keep the two-electron part a perturbation of the 4 Eh gap
+            scale = 0.01 if nbf <= 30 else 0.25 / nbf
+        rng = np.random.default_rng(seed)
+        self.nbf, self.ndocc, self.natom_, self.nfzc = nbf, ndocc, natom, nfzc
+        g = scale * rng.standard_normal((nbf,) * 4)
+        g = g + g.transpose(2, 3, 0, 1)
+        g = g + g.transpose(1, 0, 3, 2)
+        g = g + g.transpose(1, 0, 2, 3)           # real orbitals: (pq|rs) = (qp|rs)
+        self.ERI = g
+        eps = np.sort(rng.standard_normal(nbf))
+        eps[ndocc:] += 4.0
+        self.h0 = np.diag(eps)
+        sym = lambda X: 0.5 * (X + X.T)
+        asym = lambda X: 0.5 * (X - X.T)
+        self.dH = [sym(0.3 * rng.standard_normal((nbf, nbf))) for _ in range(3 * natom)]
+        self.dip = [sym(0.5 * rng.standard_normal((nbf, nbf))) for _ in range(3)]
+        self.ang = [asym(0.5 * rng.standard_normal((nbf, nbf))) for _ in range(3)]
+        self.R0 = None
+
+    def geometry_string(self):
+        lines = ["X %d.0 0.0 0.0" % (2 * i) for i in range(self.natom_)]
+        return "\n".join(lines + ["no_com", "no_reorient", "symmetry c1", "units bohr"]) + "\n"
+
+    def supports(self, molecule):
+        return molecule.natom() == self.natom_
+
+    def basis(self, molecule):
+        return BasisHandle(self, Molecule(molecule.symbols, molecule.geometry(), molecule.directives), self.nbf,
+                           self.nfzc)
+
+    def ao_overlap(self, bra, ket):
+        return np.eye(self.nbf)
+
+    def integrals(self, molecule):
+        R = molecule.geometry().reshape(-1)
+        if self.R0 is None:
+            self.R0 = np.array([2.0 * (i // 3) if i % 3 == 0 else 0.0 for i in range(3 * self.natom_)])
+        d = R - self.R0
+        T = self.h0 + sum(d[k] * self.dH[k] for k in range(len(d)))
+        return {"S": np.eye(self.nbf), "T": T, "V": np.zeros_like(T), "ERI": self.ERI,
+                "dipole": self.dip, "angmom": self.ang}
+
+    def nelectron(self, molecule):
+        return 2 * self.ndocc
+
+    def n_frozen_core(self, molecule, freeze_core):
+        return self.nfzc if freeze_core else 0
+
+
+class Psi4Provider:
+    """The reference's own integral source (hamiltonian.py:17-35), used when psi4 is importable."""
+
+    def __init__(self, psi4, parameters):
+        self.psi4, self.parameters = psi4, parameters
+
+    def supports(self, molecule):
+        return True
+
+    def _psi_mol(self, molecule):
+        return self.psi4.geometry(molecule.create_psi4_string_from_molecule())
+
+    def basis(self, molecule):
+        psi4 = self.psi4
+        psi4.core.clean_options()
+        psi4.set_options({"basis": self.parameters["basis"], "freeze_core": self.parameters["freeze_core"]})
+        b = psi4.core.BasisSet.build(self._psi_mol(molecule))
+        return BasisHandle(self, Molecule(molecule.symbols, molecule.geometry(), molecule.directives), b.nbf(),
+                           b.n_frozen_core(), payload=b)
+
+    def ao_overlap(self, bra, ket):
+        mints = self.psi4.core.MintsHelper(bra.payload)
+        return np.asarray(mints.ao_overlap(bra.payload, ket.payload))
+
+    def integrals(self, molecule, basis=None):
+        b = (basis or self.basis(molecule)).payload
+        mints = self.psi4.core.MintsHelper(b)
+        return {"S": np.asarray(mints.ao_overlap()), "T": np.asarray(mints.ao_kinetic()),
+                "V": np.asarray(mints.ao_potential()), "ERI": np.asarray(mints.ao_eri()),
+                "dipole": [np.asarray(x) for x in mints.ao_dipole()],
+                "angmom": [np.asarray(x) for x in mints.ao_angular_momentum()]}
+
+    def nelectron(self, molecule):
+        return sum(molecule.true_atomic_number(i) for i in range(molecule.natom()))
+
+    def n_frozen_core(self, molecule, freeze_core):
+        return self.basis(molecule).n_frozen_core()
+
+
+def select_provider(parameters, molecule):
+    prov = parameters.get("provider")
+    if prov is not None:
+        return prov
+    try:
+        import psi4                                      # noqa: F401
+        if hasattr(psi4, "core") and hasattr(psi4.core, "MintsHelper"):
+            return Psi4Provider(psi4, parameters)
+    except Exception:
+        pass
+    sg = SGaussianProvider(parameters.get("basis", ""))
+    if sg.supports(molecule):
+        return sg
+    raise RuntimeError("no AO-integral provider for basis %r / atoms %s: install psi4, or pass "
+                       "parameters['provider']" % (parameters.get("basis"), sorted(set(molecule.symbols))))
+
+
+# ---------------------------------------------------------------------------------------------
+# Hamiltonian                                                      (apyib/hamiltonian.py:13-70)
+# ---------------------------------------------------------------------------------------------
+class Hamiltonian(object):
+    def __init__(self, parameters):
+        self.molecule = Molecule.from_string(parameters["geom"])
+        prov = select_provider(parameters, self.molecule)
+        self.provider = prov
+        self.basis_set = prov.basis(self.molecule)
+        if isinstance(prov, Psi4Provider):
+            ints = prov.integrals(self.molecule, self.basis_set)
+        else:
+            ints = prov.integrals(self.molecule)
+            self.basis_set._nfzc = prov.n_frozen_core(self.molecule, parameters.get("freeze_core", False))
+        self.T, self.V, self.ERI, self.S = ints["T"], ints["V"], ints["ERI"], ints["S"]
+        self.nelec = prov.nelectron(self.molecule)
+        F_el, F_mag = parameters["F_el"], parameters["F_mag"]
+        E_field = any(F_el[k] != 0.0 for k in range(3))
+        M_field = any(F_mag[k] != 0.0 for k in range(3))
+        if E_field:
+            self.mu_el = ints["dipole"]
+        if M_field:
+            self.mu_mag = [-0.5j * ints["angmom"][k] for k in range(3)]          # hamiltonian.py:57
+        self.E_nuc = self.molecule.nuclear_repulsion_energy([-F_el[k] for k in range(3)])
+        for k in range(3):
+            if E_field:
+                self.V = self.V - F_el[k] * self.mu_el[k]
+            if M_field:
+                self.V = self.V - F_mag[k] * self.mu_mag[k]
+
+
+# ---------------------------------------------------------------------------------------------
+# complex RHF                                                         (apyib/hf_wfn.py:9-170)
+# ---------------------------------------------------------------------------------------------
+def _diis(res_vec, t_vec, e_iter, t_iter, iteration, max_DIIS=7):      # utils.py:104-140
+    while e_iter.shape[1] > max_DIIS:
+        e_iter, t_iter = e_iter[:, 1:], t_iter[:, 1:]
+    if iteration != 1:
+        e_iter = np.hstack((e_iter, res_vec[:, None]))
+        t_iter = np.hstack((t_iter, t_vec[:, None]))
+    m = e_iter.shape[1]
+    B = np.zeros((m + 1, m + 1), dtype=np.result_type(e_iter.dtype, np.float64))
+    B[:m, :m] = e_iter.conj().T @ e_iter
+    B[-1, :] = -1
+    B[:, -1] = -1
+    B[-1, -1] = 0
+    rhs = np.zeros(m + 1)
+    rhs[-1] = -1
+    c = np.linalg.solve(B, rhs)
+    return t_iter @ c[:-1], e_iter, t_iter
+
+
+# optional accelerator for the nbf^4 part of the Fock build: callable(wfn) -> (d -> (2J - K)[d]) | None.
+# apyib_b200.hostchem installs the device version when config.SCF_DEVICE_JK is on; None = numpy.
+JK_HOOK = [None]
+
+
+class hf_wfn(object):
+    def __init__(self, H, charge=0):
+        self.H = H
+        self.nelec = H.nelec - charge
+        self.ndocc = self.nelec // 2
+        self.nbf = H.basis_set.nbf()
+        self.C = np.zeros((self.nbf, self.nbf))
+        self.eps = np.zeros((self.nbf))
+        self.E_SCF = 0
+
+    def solve_SCF(self, parameters, print_level=0):
+        import scipy.linalg as la
+        H = self.H
+        H_core = H.T + H.V
+        X = np.linalg.inv(la.sqrtm(H.S))
+        nd = self.ndocc
+        n = self.nbf
+        GK = getattr(H.provider, "_gk_cache", None) if hasattr(H, "provider") else None
+        if GK is None or GK[0] is not H.ERI:
+            GK = (H.ERI, np.ascontiguousarray((2 * H.ERI - H.ERI.swapaxes(1, 2)).reshape(n * n, n * n)))
+            if hasattr(H, "provider"):
+                try:
+                    H.provider._gk_cache = GK           # synthetic / fixed-geometry providers reuse it
+                except Exception:
+                    pass
+        GK = GK[1]
+        jk_dev = JK_HOOK[0](self) if JK_HOOK[0] is not None else None
+        e, C_p = np.linalg.eigh(X @ H_core @ X)
+        C = X @ C_p
+        D = 2 * C[:, :nd] @ C[:, :nd].conj().T
+        E_SCF = np.sum(0.5 * D * (H_core + H_core))
+        i = 1
+        while i <= parameters["max_iterations"]:
+            E_old, D_old = E_SCF, D
+            d = D.reshape(-1)
+            if jk_dev is not None:                                  # (2J - K)[D] on the device
+                jk = jk_dev(d)
+            elif np.iscomplexobj(d) and not np.iscomplexobj(GK):    # avoid upcasting the nbf^4 tensor
+                jk = (GK @ d.real) + 1j * (GK @ d.imag)
+            else:
+                jk = GK @ d
+            F = H_core + 0.5 * jk.reshape(n, n)
+            if parameters["DIIS"]:
+                SDF = H.S @ D @ F
+                res_vec = (X @ (SDF - SDF.conj().T) @ X).reshape(-1)
+                F_vec = F.reshape(-1)
+                if i == 1:
+                    F_iter, e_iter = F_vec[:, None].copy(), res_vec[:, None].copy()
+                F_vec, e_iter, F_iter = _diis(res_vec, F_vec, e_iter, F_iter, i)
+                F = F_vec.reshape(self.nbf, self.nbf)
+            self.eps, C_p = np.linalg.eigh(X @ F @ X)
+            C = self.C = X @ C_p
+            D = 2 * C[:, :nd] @ C[:, :nd].conj().T
+            E_SCF = np.sum(0.5 * D.T * (H_core + F))
+            delta_E = E_SCF - E_old
+            rms_D = np.sqrt(np.sum((D_old - D) ** 2))
+            if i > 1 and abs(delta_E) < parameters["e_convergence"] and rms_D < parameters["d_convergence"]:
+                break
+            i += 1
+        self.E_SCF = E_SCF
+        return E_SCF, self.C

@@ -2,7 +2,7 @@
 (energy.py:17-150, fin_diff.py:151-372, aats.py:23-115, parallel.py:16-48) on top of the
 oracle solvers.  TEST INFRASTRUCTURE / CPU BASELINE ONLY.
 
-Host inputs (geometry, AO integrals, SCF) come from apyib_b200.hostchem -- the same host
+Host inputs (geometry, AO integrals, SCF) come from hostinputs -- the same host
 code the product uses; everything the product does on the GPU is done here with
 oracle.apyib_oracle (numpy).
 """
@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from apyib_b200 import hostchem as hc
+import hostinputs as hc
 from oracle import apyib_oracle as orc
 
 

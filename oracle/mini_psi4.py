@@ -2,7 +2,7 @@
 UNMODIFIED reference (hamiltonian.py, hf_wfn.py, energy.py, fin_diff.py, aats.py, parallel.py)
 to run on H/He molecules such as its own (H2)_2 test case.  TEST INFRASTRUCTURE ONLY.
 
-Integrals come from apyib_b200.hostchem.SGaussianProvider (closed-form s-Gaussian formulas);
+Integrals come from hostinputs.SGaussianProvider (closed-form s-Gaussian formulas);
 that engine is itself pinned by the reference's hard-coded (H2)_2 energies and AAT tensors
 (tests/golden/reference_literals.py).
 """
@@ -12,7 +12,7 @@ import types
 
 import numpy as np
 
-from apyib_b200 import hostchem as hc
+import hostinputs as hc
 
 _options = {"basis": "STO-3G", "freeze_core": False}
 

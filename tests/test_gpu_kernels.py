@@ -429,7 +429,6 @@ def test_det_stack_entry_points_match_single_overlap_calls(n, nv, nf):
                     assert np.abs(to_host(Z2) - want).max() <= 1e-10 * scale
 
 
-@pytest.mark.skipif(os.environ.get("APYIB_B200_EXPERIMENTAL") != "1", reason="experimental kernel variant, not yet validated on a B200")
 @pytest.mark.parametrize("n,nv", [(4, 5), (9, 6), (9, 13), (12, 4)])
 def test_det_pairs_single_vector_variant_matches_generic(n, nv):
     """apyib_det_set_pairs_variant(1): the single-vector specialisation of the prefix-shared LU kernel must give

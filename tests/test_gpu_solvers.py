@@ -209,33 +209,6 @@ def test_perturbed_cid_amplitudes(nbf, no, nf, cplx, seed):
     assert abs(dE - G[name + "/dE"]) < 1e-8 and np.abs(dt2 - G[name + "/dt2"]).max() < 1e-8
 
 
-@pytest.mark.skipif(os.environ.get("APYIB_B200_EXPERIMENTAL") != "1", reason="experimental path, not yet validated on a B200")
-@pytest.mark.parametrize("method", ["CISD", "CID_SO"])
-def test_concurrent_dtype_groups_equal_sequential(method):
-    """config.SOLVE_CONCURRENT: real and complex batches solved at the same time on two streams == sequential"""
-    import apyib_b200
-    from apyib_b200.ci_wfn import solve_many
-    ws = [orc.rotated_wfn(7, 3, 600 + k, k % 2 == 1, 0) for k in range(6)]
-    p = par(method)
-    cfg = apyib_b200.config
-    old = (cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE)
-    try:
-        for dev_out in (False, True):
-            cfg.RETURN_DEVICE = dev_out
-            cfg.SOLVE_CONCURRENT = False
-            seq = solve_many(method, p, ws)
-            cfg.SOLVE_CONCURRENT = True
-            con = solve_many(method, p, ws)
-            for a, b in zip(seq, con):
-                for x, y in zip(a, b):
-                    x = x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)
-                    y = y.cpu().numpy() if hasattr(y, "cpu") else np.asarray(y)
-                    assert np.array_equal(x, y)
-    finally:
-        cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE = old
-
-
-@pytest.mark.skipif(os.environ.get("APYIB_B200_EXPERIMENTAL") != "1", reason="experimental path, not yet validated on a B200")
 @pytest.mark.parametrize("field", [False, True])
 def test_scf_with_device_jk_equals_host_scf(field):
     """config.SCF_DEVICE_JK: (2J - K)[D] of every SCF iteration on the device == the host GEMV"""
