@@ -83,3 +83,95 @@ def test_aat_element_full_size_three_algorithms_agree(method):
     for name, v in got.items():
         assert np.abs(np.array(v) - ref).max() < 1e-10 * max(1.0, np.abs(ref).max()), (name, v, ref)
     assert got["lu_graph"] == got["lu"]                    # same kernels, same order: bit-identical
+
+
+# -------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2-3] shape: (S)-methyloxirane/cc-pVDZ, nbf = 86, ndocc = 16, 4 frozen core orbitals
+# (o/v = 12/70, 16 x 16 substituted determinants, 159 390 x 159 390 doubles x doubles table per overlap).
+# The reference itself cannot run this size (8 TB tensor, aats.py:575); the solvers are checked against the
+# oracle directly, one AAT element against the streamed oracle (oracle/sparse_aat.py: the reference's sums
+# evaluated on the support of sparse amplitudes -- the GPU path runs its full dense machinery on the same
+# inputs), and a sampled block of the determinant table against numpy.linalg.det.
+# -------------------------------------------------------------------------------------------------
+T_NBF, T_NDOCC, T_NFZC = 86, 16, 4
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_cisd_target_shape_vs_oracle(cplx):
+    """ci_wfn.py:420-574 at (o, v) = (12, 70), frozen core: unbatched AO->MO transform (nbf^5), TMA ladder tiles,
+    graph-replayed iterations; energies 1e-10, amplitudes 1e-9, identical iteration counts"""
+    import apyib_b200
+    w = orc.rotated_wfn(T_NBF, T_NDOCC, 8600 + int(cplx), cplx, T_NFZC, scale=0.25 / T_NBF)
+    p = _par("CISD", True)
+    ci = apyib_b200.ci_wfn(p, w)
+    E, t1, t2 = ci.solve_CISD()
+    Eo, t1o, t2o, its = orc.solve_CISD(p, w, return_iters=True)
+    o, v = T_NDOCC - T_NFZC, T_NBF - T_NDOCC
+    assert t2.shape == (o, o, v, v) and t2.dtype == t2o.dtype and t1.shape == (o, v)
+    assert ci.iterations == its
+    assert abs(E - Eo) < 1e-10 and np.abs(t1 - t1o).max() < 1e-9 and np.abs(t2 - t2o).max() < 1e-9
+
+
+@pytest.mark.parametrize("method,seed", [("CISD", 8611), ("CISD", 8612), ("CID", 8613)])
+def test_aat_element_target_shape_vs_streamed_oracle(method, seed):
+    """one (alpha, beta) element of the FD-AAT tensor at the target shape, all nine I_xy terms, closed-form
+    ("factorized", what bench.py runs at this size) and determinant-lemma kernels against the streamed oracle"""
+    import apyib_b200
+    from apyib_b200 import aats
+    from apyib_b200.aats import AAT
+    from oracle import sparse_aat as sp
+    cfg = apyib_b200.config
+    A = sp.sparse_aat_inputs(method, T_NBF, T_NDOCC, T_NFZC, 1, seed, h=1e-4, nnz2=40, nnz1=30)
+    want = {norm: sp.spatial_aat_terms_streamed(A, 1, 2, norm) for norm in ("full", "intermediate")}
+    old = (cfg.AAT_ALGORITHM, cfg.AAT_USE_GRAPH)
+    try:
+        for algo in ("factorized", "lemma"):
+            cfg.AAT_ALGORITHM = algo
+            aats._block_graphs.clear()
+            G = AAT.from_parts(A.method, A.nbf, A.ndocc, A.nfzc, A.nuc_pert_strength, A.mag_pert_strength,
+                               **{k: getattr(A, k) for k in PARTS if hasattr(A, k)})
+            G.prefetch_rows([1])
+            for norm in ("full", "intermediate"):
+                got = G._spatial_terms(1, 2, norm)
+                k = 1 / (4 * A.nuc_pert_strength * A.mag_pert_strength)
+                for name, ref in want[norm].items():
+                    # 1e-8 a.u. on the AAT element = 1e-8 * 4 h_R h_B on every term (north star tolerance)
+                    assert abs(k * np.imag(got[name] - ref)) < 1e-8 * max(1.0, abs(k * np.imag(ref))), (algo, norm, name, got[name], ref)
+                tot = G.compute_spatial_aats(1, 2, norm)
+                ref = k * np.imag(sum(want[norm].values()))
+                assert abs(tot - ref) < 1e-8 * max(1.0, abs(ref)), (algo, norm, tot, ref)
+    finally:
+        cfg.AAT_ALGORITHM, cfg.AAT_USE_GRAPH = old
+        aats._block_graphs.clear()
+
+
+def test_sampled_determinant_block_target_shape():
+    """300 x 300 sample of the 159 390 x 159 390 doubles x doubles table of one overlap at n = 16: the sub-warp LU
+    kernel (det_kernel<16>, the n > 12 path) and the determinant-lemma kernel against numpy.linalg.det"""
+    import ctypes as C
+    import torch
+    from apyib_b200._lib import lib, check
+    from apyib_b200.aats import _Tables, _det_outer
+    from apyib_b200.device import to_device, to_host, empty, ptr, stream_ptr
+    rng = np.random.default_rng(8620)
+    no, nf, nv = T_NDOCC, T_NFZC, T_NBF - T_NDOCC
+    T = _Tables.get(no, nf, nv)
+    assert T.n2 == 66 * 2415 and T.n1 == 12 * 70
+    for h, tol in ((1e-4, 1e-12), (0.3, 1e-10)):               # finite-difference-like and heavily pivoting overlaps
+        Sh = np.eye(T_NBF) + h * (rng.standard_normal((T_NBF, T_NBF)) + 0.1j * rng.standard_normal((T_NBF, T_NBF)))
+        S = to_device(Sh, torch.complex128)
+        ir, ic = np.sort(rng.choice(T.n2, 300, replace=False)), np.sort(rng.choice(T.n2, 300, replace=False))
+        sub = lambda idx: T.doubles[idx].reshape(-1, 2, 2)
+        want = orc._batched_sub_dets(Sh, no, sub(ir), sub(ic))
+        scale = np.abs(want).max()
+        rows = T.L[2][torch.from_numpy(ir).to(S.device)].contiguous()
+        cols = T.L[2][torch.from_numpy(ic).to(S.device)].contiguous()
+        got_lu = to_host(_det_outer(S, no, rows, cols))
+        assert np.abs(got_lu - want).max() <= tol * scale
+        prep = empty((1, int(lib.apyib_lemma_prep_len(T_NBF, no))), torch.complex128)
+        check(lib.apyib_lemma_prepare(ptr(S), 1, T_NBF, no, ptr(prep), stream_ptr()))
+        dr = T.doubles_dev[torch.from_numpy(ir).to(S.device)].contiguous()
+        dc = T.doubles_dev[torch.from_numpy(ic).to(S.device)].contiguous()
+        out = empty((1, 300, 300), torch.complex128)
+        check(lib.apyib_lemma_outer(ptr(prep), 1, T_NBF, no, 2, ptr(dr), 300, 2, ptr(dc), 300, ptr(out), stream_ptr()))
+        assert np.abs(to_host(out)[0] - want).max() <= 10 * tol * scale

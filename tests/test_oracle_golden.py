@@ -199,3 +199,17 @@ def test_h2_2_hessian_matches_reference_output():
          "e_convergence": 1e-13, "d_convergence": 1e-13, "max_iterations": 120, "F_el": [0.0] * 3, "F_mag": [0.0] * 3}
     H = fp.compute_Hessian(p, c["h_R"])
     assert H.shape == (12, 12) and np.abs(H - np.array(c["Hessian"])).max() < 2e-6
+
+
+@pytest.mark.parametrize("method,nbf,no,nf", [("CISD", 7, 3, 1), ("CISD", 6, 3, 0), ("CID", 7, 3, 1)])
+def test_streamed_aat_oracle_equals_dense_oracle(method, nbf, no, nf):
+    """oracle/sparse_aat.py (used at sizes where the 8-index tensor cannot exist) == the dense oracle, term by term,
+    on sparse and on dense amplitudes"""
+    from oracle import sparse_aat as sp
+    for A in (sp.sparse_aat_inputs(method, nbf, no, nf, 1, 11, h=1e-3, nnz2=6, nnz1=4),
+              orc.synthetic_aat_inputs(method, nbf, no, nf, 1, 5, h=1e-3)):
+        for norm in ("full", "intermediate"):
+            d = orc.spatial_aat_terms(A, 1, 2, norm)
+            s = sp.spatial_aat_terms_streamed(A, 1, 2, norm)
+            for k in d:
+                assert abs(d[k] - s[k]) < 1e-14 * max(1.0, abs(d[k])), (k, d[k], s[k])
