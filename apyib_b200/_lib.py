@@ -45,6 +45,11 @@ SIGNATURES = {
     "apyib_lincomb_energy_rms": (_int, [_int, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _int, _vp, _vp]),
     "apyib_iter_advance": (_int, [_vp, _vp]),
     "apyib_copy": (_int, [_int, _vp, _vp, _i64, _vp]),
+    "apyib_copy_rows": (_int, [_int, _vp, _i64, _vp, _i64, _i64, _int, _dbl, _vp, _vp]),
+    "apyib_widen": (_int, [_vp, _vp, _i64, _vp]),
+    "apyib_symmetrize_ijab_batch": (_int, [_int, _vp, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp]),
+    "apyib_pack_pairs": (_int, [_int, _vp, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp]),
+    "apyib_unpack_pairs_add": (_int, [_int, _vp, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp]),
     "apyib_axpby": (_int, [_int, _i64, _dbl, _dbl, _vp, _int, _dbl, _dbl, _vp, _vp]),
     "apyib_det_outer": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _vp]),
     "apyib_det_matvec": (_int, [_vp, _int, _int, _vp, _i64, _vp, _i64, _vp, _int, _vp, _vp, _vp]),
@@ -90,15 +95,12 @@ def _bind(path):
 
 
 def _load():
+    # built in-tree by __graft_entry__.build(); (re)built here when missing or when the sources have changed since
+    # (content hash, serialised across ranks).  A library that still lacks a symbol after that fails loudly.
     path = _build.LIB
-    if not os.path.exists(path):
-        # built in-tree by __graft_entry__.build(); try once here (nvcc is part of the image)
-        path = _build.build()
-    try:
-        return _bind(path)
-    except AttributeError:
-        # a library from an older source tree: rebuild once, then fail loudly if a symbol is still missing
-        return _bind(_build.build(force=True))
+    if _build._stale():
+        path = _build.build_locked()
+    return _bind(path)
 
 
 lib = _load()
@@ -108,7 +110,7 @@ lib = _load()
 _KERNELS_PER_CALL = {
     "apyib_contract": 1, "apyib_contract_tma": 1, "apyib_gather4": 1, "apyib_gather4_batch": 1, "apyib_gather2": 1, "apyib_mp2_t2_energy": 2, "apyib_ci_update": 1,
     "apyib_symmetrize_ijab": 1, "apyib_dots": 1, "apyib_diis_push": 1, "apyib_diis_solve": 1,
-    "apyib_lincomb_energy_rms": 1, "apyib_iter_advance": 1, "apyib_copy": 1, "apyib_axpby": 1,
+    "apyib_lincomb_energy_rms": 1, "apyib_iter_advance": 1, "apyib_copy": 1, "apyib_copy_rows": 1, "apyib_widen": 1, "apyib_symmetrize_ijab_batch": 1, "apyib_pack_pairs": 1, "apyib_unpack_pairs_add": 1, "apyib_axpby": 1,
     "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_det_outer_sorted": 1, "apyib_det_matvec_sorted": 2, "apyib_det_matvec_pairs": 2, "apyib_det_outer_stack": 1, "apyib_det_matvec_stack": 2, "apyib_det_matvec_pairs_stack": 2, "apyib_pack_doubles": 1,
     "apyib_lemma_prepare": 1, "apyib_lemma_outer": 1, "apyib_lemma_matvec": 2,
 }

@@ -250,7 +250,10 @@ class AAT(object):
 
     def __init__(self, parameters, wfn, unperturbed_wfn, unperturbed_basis, unperturbed_T, nuc_pos_wfn, nuc_neg_wfn,
                  nuc_pos_basis, nuc_neg_basis, nuc_pos_T, nuc_neg_T, mag_pos_wfn, mag_neg_wfn, mag_pos_basis,
-                 mag_neg_basis, mag_pos_T, mag_neg_T, nuc_pert_strength, mag_pert_strength):
+                 mag_neg_basis, mag_pos_T, mag_neg_T, nuc_pert_strength, mag_pert_strength, rows=None):
+        """`rows` (optional, not in the reference): the nuclear coordinates alpha this process is going to evaluate
+        (sharded driver, parallel.py).  Overlaps, norms and scaled amplitudes of other rows are then never built;
+        their list entries (C / basis / T) may be None."""
         from .hostchem import provider_ao_overlap
         self.nuc_pos_wfn, self.nuc_neg_wfn = nuc_pos_wfn, nuc_neg_wfn
         self.nuc_pos_T, self.nuc_neg_T = nuc_pos_T, nuc_neg_T
@@ -275,21 +278,27 @@ class AAT(object):
         U, Ub = self.unperturbed_wfn, unperturbed_basis
         n3 = 3 * natom
         rhf = parameters["method"] == "RHF"
+        if rows is not None:
+            self._rows = sorted(set(int(a) for a in rows))
+        mine = set(range(n3)) if rows is None else set(self._rows)
+        _ovl = ovl
+        ovl = lambda bb, Cb, kb, Ck: _ovl(bb, Cb, kb, Ck) if Cb is not None else None      # row not owned
+        sel = lambda lst, a: lst[a] if a in mine else None
         if not rhf:
             uu = ovl(Ub, U, Ub, U)
             up = [ovl(Ub, U, mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)]
             un = [ovl(Ub, U, mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)]
-            pu = [ovl(nuc_pos_basis[a], nuc_pos_wfn[a], Ub, U) for a in range(n3)]
-            nu = [ovl(nuc_neg_basis[a], nuc_neg_wfn[a], Ub, U) for a in range(n3)]
-        pp = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
-        pn = [[ovl(nuc_pos_basis[a], nuc_pos_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
-        np_ = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
-        nn = [[ovl(nuc_neg_basis[a], nuc_neg_wfn[a], mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
+            pu = [ovl(nuc_pos_basis[a], sel(nuc_pos_wfn, a), Ub, U) for a in range(n3)]
+            nu = [ovl(nuc_neg_basis[a], sel(nuc_neg_wfn, a), Ub, U) for a in range(n3)]
+        pp = [[ovl(nuc_pos_basis[a], sel(nuc_pos_wfn, a), mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
+        pn = [[ovl(nuc_pos_basis[a], sel(nuc_pos_wfn, a), mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
+        np_ = [[ovl(nuc_neg_basis[a], sel(nuc_neg_wfn, a), mag_pos_basis[b], mag_pos_wfn[b]) for b in range(3)] for a in range(n3)]
+        nn = [[ovl(nuc_neg_basis[a], sel(nuc_neg_wfn, a), mag_neg_basis[b], mag_neg_wfn[b]) for b in range(3)] for a in range(n3)]
         if so:
             host = [to_host(spin_block_2_dev(S)) for S in mo_overlaps_dev(jobs)]
         else:
             host = mo_overlaps_dev(jobs, host=True)
-        get = lambda x: [get(y) for y in x] if isinstance(x, list) else host[x]
+        get = lambda x: [get(y) for y in x] if isinstance(x, list) else (None if x is None else host[x])
         if not rhf:
             self.overlap_uu, self.overlap_up, self.overlap_un = get(uu), get(up), get(un)
             self.overlap_pu, self.overlap_nu = get(pu), get(nu)
@@ -383,9 +392,17 @@ class AAT(object):
     # ---------------------------------------------------------------------------------------
     # spatial route
     # ---------------------------------------------------------------------------------------
+    def _active_rows(self):
+        """nuclear coordinates whose norms / scaled amplitudes are built: the hinted rows (constructor `rows=`,
+        prefetch_rows) or all of them"""
+        n3 = len(self.nuc_pos_T)
+        rows = getattr(self, "_rows", None)
+        return list(range(n3)) if not rows else list(rows)
+
     def _spatial_norms(self, normalization):
-        """N, N_np[3N], N_nn[3N], N_mp[3], N_mn[3] of aats.py:652-669."""
-        key = ("norms", normalization)
+        """N, N_np[3N], N_nn[3N], N_mp[3], N_mn[3] of aats.py:652-669 (entries of rows that are not active: None)."""
+        rows = self._active_rows()
+        key = ("norms", normalization, tuple(rows))
         if key in self._cache:
             return self._cache[key]
         m = self.parameters["method"]
@@ -394,9 +411,10 @@ class AAT(object):
             res = (1, [1] * n3, [1] * n3, [1] * 3, [1] * 3)
         else:
             cisd = m == "CISD"
-            # all 6N+7 points as one stack: three batched dot-like contractions and ONE device->host copy
+            # all needed points as one stack: three batched dot-like contractions and ONE device->host copy
             # (x = t0 + 2<t1|t1> + 2<t2|t2> - <t2|t2^T>, aats.py:652-669)
-            Ts = [self.unperturbed_T] + list(self.nuc_pos_T) + list(self.nuc_neg_T) + list(self.mag_pos_T) + list(self.mag_neg_T)
+            Ts = ([self.unperturbed_T] + [self.nuc_pos_T[a] for a in rows] + [self.nuc_neg_T[a] for a in rows]
+                  + list(self.mag_pos_T) + list(self.mag_neg_T))
             t2 = torch.stack([_dev(T[2]) for T in Ts])
             npt = len(Ts)
             acc = zeros((3, npt), _C128)
@@ -408,19 +426,23 @@ class AAT(object):
             h = to_host(acc)
             Nall = [1 / np.sqrt(Ts[s][0] + (2 * complex(h[0, s]) - complex(h[1, s])) + (2 * complex(h[2, s]) if cisd else 0))
                     for s in range(npt)]
-            res = (Nall[0], Nall[1:1 + n3], Nall[1 + n3:1 + 2 * n3], Nall[1 + 2 * n3:4 + 2 * n3], Nall[4 + 2 * n3:7 + 2 * n3])
+            nr = len(rows)
+            N_np, N_nn = [None] * n3, [None] * n3
+            for k, a in enumerate(rows):
+                N_np[a], N_nn[a] = Nall[1 + k], Nall[1 + nr + k]
+            res = (Nall[0], N_np, N_nn, Nall[1 + 2 * nr:4 + 2 * nr], Nall[4 + 2 * nr:7 + 2 * nr])
         self._cache[key] = res
         return res
 
     def _spatial_amps(self, normalization):
-        """Scaled amplitude combinations of aats.py:690-711 for ALL alpha / beta, on the device:
-        kets  Y_t (1), Y_dH (3);  bras X_c (1), X_dR (3N)."""
-        key = ("amps", normalization)
+        """Scaled amplitude combinations of aats.py:690-711 for the active alpha / all beta, on the device:
+        kets  Y_t (1), Y_dH (3);  bras X_c (1), X_dR (active rows; "pos" maps alpha -> position in the stack)."""
+        rows = self._active_rows()
+        key = ("amps", normalization, tuple(rows))
         if key in self._cache:
             return self._cache[key]
         cisd = self.parameters["method"] == "CISD"
         N, N_np, N_nn, N_mp, N_mn = self._spatial_norms(normalization)
-        n3 = len(self.nuc_pos_T)
 
         def build(idx):
             if idx == 1 and not cisd:
@@ -432,14 +454,14 @@ class AAT(object):
             for b in range(3):
                 x = _axpby(N_mp[b], _dev(self.mag_pos_T[b][idx]), 0.0, torch.empty_like(T0))
                 dH.append(_axpby(-N_mn[b], _dev(self.mag_neg_T[b][idx]), 1.0, x))
-            for a in range(n3):
+            for a in rows:
                 x = _axpby(np.conj(N_np[a]), _dev(self.nuc_pos_T[a][idx]), 0.0,
                            torch.empty_like(T0), conj_x=True)
                 dR.append(_axpby(-np.conj(N_nn[a]), _dev(self.nuc_neg_T[a][idx]), 1.0, x,
                                  conj_x=True))
             return dict(t=t[None], tc=tc[None], dH=torch.stack(dH), dR=torch.stack(dR))
 
-        res = {1: build(1), 2: build(2)}
+        res = {1: build(1), 2: build(2), "pos": {a: k for k, a in enumerate(rows)}}
         self._cache[key] = res
         return res
 
@@ -723,12 +745,15 @@ class AAT(object):
                        - d2(self.overlap_np[a][b]) * N_nn[a] * N_mp[b] + d2(self.overlap_nn[a][b]) * N_nn[a] * N_mn[b])
             return I
         cisd = m == "CISD"
+        if getattr(self, "_rows", None) and alpha not in self._rows:
+            self._rows = sorted(set(self._rows) | {int(alpha)})       # a row outside the hint: widen the active set
         amps = self._spatial_amps(normalization)
         A1, A2 = amps[1], amps[2]
+        ar = amps["pos"][alpha]                                       # position of alpha in the stacked dR amplitudes
         pick = lambda Am, k: None if Am is None else Am[k]
 
         def cached(name, S, bra, ket):
-            key = ("blk", name, normalization)
+            key = ("blk", name, normalization, tuple(self._active_rows()))
             if key not in self._cache:
                 self._fill_family(name, normalization, A1, A2)
             if key not in self._cache:
@@ -749,9 +774,9 @@ class AAT(object):
                 if od:
                     I["0D"] += sign * res["0D"][ix, iq]
 
-        add(cached("uu", self.overlap_uu, "dR", "dH"), +1, a, b)
-        add(cached(("up", b), self.overlap_up[b], "dR", "t"), +1, a, 0, s0_N=N_mp[b], d0=True)
-        add(cached(("un", b), self.overlap_un[b], "dR", "t"), -1, a, 0, s0_N=N_mn[b], d0=True)
+        add(cached("uu", self.overlap_uu, "dR", "dH"), +1, ar, b)
+        add(cached(("up", b), self.overlap_up[b], "dR", "t"), +1, ar, 0, s0_N=N_mp[b], d0=True)
+        add(cached(("un", b), self.overlap_un[b], "dR", "t"), -1, ar, 0, s0_N=N_mn[b], d0=True)
         add(cached(("pu", a), self.overlap_pu[a], "tc", "dH"), +1, 0, b, os_N=N_np[a], od=True)
         add(cached(("nu", a), self.overlap_nu[a], "tc", "dH"), -1, 0, b, os_N=N_nn[a], od=True)
         key = ("blk4", a, normalization)
@@ -789,12 +814,13 @@ class AAT(object):
         else:
             items = [(("up", b), self.overlap_up[b]) for b in range(3)] + [(("un", b), self.overlap_un[b]) for b in range(3)]
             bra, ket = "dR", "t"
-        items = [it for it in items if ("blk", it[0], normalization) not in self._cache]
+        rk = tuple(self._active_rows())
+        items = [it for it in items if ("blk", it[0], normalization, rk) not in self._cache]
         for i0 in range(0, len(items), max_stack):
             chunk = items[i0:i0 + max_stack]
             res = self._blocks([S for _, S in chunk], pick(A1, bra), A2[bra], pick(A1, ket), A2[ket])
             for (nm, _), r in zip(chunk, res):
-                self._cache[("blk", nm, normalization)] = r
+                self._cache[("blk", nm, normalization, rk)] = r
 
     def compute_spatial_aats(self, alpha, beta, normalization="full"):
         """Reference: aats.py:646-1055.  Returns Im(I)/(4 h_R h_B) for one (alpha, beta)."""
@@ -889,9 +915,16 @@ class AAT(object):
             I["0S"], I["S0"], I["SS"], I["SD"], I["DS"] = term(0, 1), term(1, 0), term(1, 1), term(1, 2), term(2, 1)
         return I
 
+    def _so_terms_cached(self, alpha, beta, normalization):
+        """the nine per-term methods of one element share one evaluation (the reference recomputes per method)"""
+        key = ("so_terms", alpha, beta, normalization)
+        if key not in self._cache:
+            self._cache[key] = self._so_terms(alpha, beta, normalization)
+        return self._cache[key]
+
     def _so_scaled(self, name, alpha, beta, normalization):
         k = 1 / (4 * self.nuc_pert_strength * self.mag_pert_strength)
-        return k * np.imag(self._so_terms(alpha, beta, normalization)[name])
+        return k * np.imag(self._so_terms_cached(alpha, beta, normalization)[name])
 
     def compute_SO_I_00(self, alpha, beta, normalization): return self._so_scaled("00", alpha, beta, normalization)
     def compute_SO_I_0D(self, alpha, beta, normalization): return self._so_scaled("0D", alpha, beta, normalization)
@@ -906,7 +939,7 @@ class AAT(object):
     def compute_SO_aats(self, alpha, beta, normalization="full"):
         """Reference: aats.py:520-554."""
         t0 = time.time()
-        I = self._so_terms(alpha, beta, normalization)
+        I = self._so_terms_cached(alpha, beta, normalization)
         k = 1 / (4 * self.nuc_pert_strength * self.mag_pert_strength)
         tot = sum(k * np.imag(x) for x in I.values())
         if config.VERBOSE:

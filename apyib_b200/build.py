@@ -15,12 +15,42 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 OBJDIR = os.path.join(LIBDIR, "obj")
 
 
+STAMP = os.path.join(LIBDIR, "build.sha256")
+
+
+def source_hash():
+    """sha256 over every file of csrc/, the public header and the compiler flags (content, not mtimes: a snapshot
+    copied to another box keeps its contents but not necessarily its timestamps)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "apyib_b200.h")]
+    for f in files:
+        if os.path.isfile(f):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "apyib_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    try:
+        return open(STAMP).read().strip() != source_hash()
+    except OSError:
+        return True
+
+
+def build_locked(force=False, verbose=False):
+    """build() serialised across processes (torchrun ranks importing the package at the same time): one builds,
+    the others wait on the lock and then find the library up to date."""
+    import fcntl
+    os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build(force=force, verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 def build(force=False, verbose=False):
@@ -44,13 +74,16 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed compiling %s" % src)
         if verbose:
             print(res.stdout + res.stderr)
-    tmp = LIB + ".tmp"
+    tmp = LIB + ".tmp.%d" % os.getpid()
     res = subprocess.run([nvcc] + NVCC_FLAGS + ["-shared"] + [obj for _, obj, _ in results] + ["-o", tmp],
                          capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed linking libapyib_b200.so")
     os.replace(tmp, LIB)
+    with open(STAMP + ".tmp.%d" % os.getpid(), "w") as f:
+        f.write(source_hash() + "\n")
+    os.replace(STAMP + ".tmp.%d" % os.getpid(), STAMP)
     return LIB
 
 

@@ -127,13 +127,14 @@ class _Engine:
                                                ptr(self.w), self.n1, self.len, ptr(self.out6), ptr(self.scratch),
                                                self.nb, ptr(self.active), stream_ptr()))
 
-    def _copy(self, dst, src):
-        """dense copy of equally shaped tensors via the copy kernel (per point if strided)"""
-        if dst.is_contiguous() and src.is_contiguous():
+    def _copy(self, dst, src, alpha=1.0):
+        """dst[s] = alpha * src[s] for equally shaped [nb, ...] tensors whose rows are dense: ONE launch for the batch"""
+        if alpha == 1.0 and dst.is_contiguous() and src.is_contiguous():
             check(lib.apyib_copy(self.code, ptr(dst), ptr(src), dst.numel(), stream_ptr()))
         else:
-            for s in range(self.nb):
-                check(lib.apyib_copy(self.code, ptr(dst[s]), ptr(src[s]), dst[s].numel(), stream_ptr()))
+            assert dst[0].is_contiguous() and src[0].is_contiguous()
+            check(lib.apyib_copy_rows(self.code, ptr(dst), dst.stride(0), ptr(src), src.stride(0), dst[0].numel(),
+                                      self.nb, float(alpha), _NULL, stream_ptr()))
 
     def initial_guess(self):
         """t = r0 / D, E = w.t   (ci_wfn.py:66-70, 193-197, 286-293, 435-442)."""
@@ -144,9 +145,7 @@ class _Engine:
         self.t.zero_()
         self._copy(self.r, self.r0)
         if self.symmetrize:                   # CID spatial keeps 0.5*K in r0 (ci_wfn.py:83); guess uses K
-            for s in range(self.nb):
-                check(lib.apyib_axpby(self.code, self.n2, 2.0, 0.0, ptr(self.r0[s, self.n1:]), 0, 0.0, 0.0,
-                                      ptr(self.r[s, self.n1:]), stream_ptr()))
+            self._copy(self.r[:, self.n1:], self.r0[:, self.n1:], 2.0)
         self._update()
         self._copy(self.t_old, self.t)
         self._energy_rms(False)
@@ -158,9 +157,8 @@ class _Engine:
             self._copy(self.r, self.r0)                      # (the r2 part is overwritten by the symmetrisation)
             self._copy(self.r_half, self.r0[:, self.n1:])
             residual(self.r_half)
-            for s in range(self.nb):
-                check(lib.apyib_symmetrize_ijab(self.code, ptr(self.r_half[s]), ptr(self.r[s, self.n1:]), self.O,
-                                                self.V, stream_ptr()))
+            check(lib.apyib_symmetrize_ijab_batch(self.code, ptr(self.r_half), self.r_half.stride(0), ptr(self.r[:, self.n1:]),
+                                                  self.r.stride(0), self.O, self.V, self.nb, ptr(self.active), stream_ptr()))
         else:
             self._copy(self.r, self.r0)
             residual(None)
@@ -184,10 +182,22 @@ class _Engine:
         return [tuple(np.float64(x) for x in row[0::2]) for row in h]
 
     def run(self, residual, print_level=0, E_SCF=0.0, E_nuc=0.0):
-        """The reference's iteration control (ci_wfn.py:76-130 etc.), verbatim semantics, applied to
-        every point of the batch independently."""
+        g = self.run_steps(residual, print_level, E_SCF, E_nuc)
+        while True:
+            try:
+                next(g)
+            except StopIteration as done:
+                return done.value
+
+    def run_steps(self, residual, print_level=0, E_SCF=0.0, E_nuc=0.0):
+        """The reference's iteration control (ci_wfn.py:76-130 etc.), verbatim semantics, applied to every point of
+        the batch independently.  Generator: yields right after the launches of an iteration have been enqueued and
+        BEFORE the blocking read-back of its 6 doubles per point, so that a caller can keep several batches (the
+        float64 and the complex128 points of a molecule, each on its own stream) in flight from one host thread
+        (`_drive`).  The generator's return value is the list of energies."""
         p, nb = self.p, self.nb
         self.initial_guess()
+        yield
         E = [x[0] for x in self.read()]
         graph = None
         iteration = 1
@@ -201,6 +211,7 @@ class _Engine:
                     graph = Graph()
                     graph.capture(lambda: self.iteration(residual))
                 graph.launch()
+            yield
             vals = self.read()
             changed = False
             for s in range(nb):
@@ -230,6 +241,27 @@ class _Engine:
                 self.active.copy_(torch.tensor([1 if a else 0 for a in active], dtype=torch.int32))
             iteration += 1
         return E
+
+
+def _drive(jobs):
+    """jobs: [(generator, stream | None)].  Advances the generators round-robin, each under its own stream, until all
+    have finished; returns their return values.  While the host blocks on the read-back of one batch, the launches
+    of the other batches are already queued on their streams and keep the GPU busy."""
+    results = [None] * len(jobs)
+    live = list(range(len(jobs)))
+    while live:
+        for k in list(live):
+            gen, st = jobs[k]
+            try:
+                if st is None:
+                    next(gen)
+                else:
+                    with torch.cuda.stream(st):
+                        next(gen)
+            except StopIteration as done:
+                results[k] = done.value
+                live.remove(k)
+    return results
 
 
 # -------------------------------------------------------------------------------------------------
@@ -279,19 +311,24 @@ def _solve_CID(parameters, points, print_level):
     F = torch.stack([pt.F for pt in points])
     Foo, Fvv = F[:, :O, :O], F[:, O:, O:]
 
+    ladder = _PackedLadder(Wvvvv, O, V, nb, dt) if config.PACKED_LADDER else None
+
     def residual(r):
         t2 = eng.t2()
         r = r.view(nb, O, O, V, V)
         contract("sijae,sbe->sijab", t2, Fvv, r, 1.0, 1.0)              # ci_wfn.py:84
         contract("simab,smj->sijab", t2, Foo, r, -1.0, 1.0)             # :85
         contract("smnab,smnij->sijab", t2, Woooo, r, 0.5, 1.0)          # :86
-        contract("sijef,sabef->sijab", t2, Wvvvv, r, 0.5, 1.0)          # :87
+        if ladder is not None:                                          # :87 over the pairs i <= j only
+            ladder.apply(t2, r)
+        else:
+            contract("sijef,sabef->sijab", t2, Wvvvv, r, 0.5, 1.0)
         contract("simae,smbje->sijab", t2, Wovvo, r, 1.0, 1.0)          # :88  (t2 - t2.swapaxes(2,3)) . W
         contract("simea,smbje->sijab", t2, Wovvo, r, -1.0, 1.0)
         contract("simae,smbje->sijab", t2, Lovvo, r, 1.0, 1.0)          # :89
         contract("smjae,smbie->sijab", t2, Wovov, r, -1.0, 1.0)         # :90
 
-    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    E = yield from eng.run_steps(residual, print_level, points[0].E_SCF, points[0].E_nuc)
     return eng, E
 
 
@@ -321,7 +358,7 @@ def _solve_CID_SO(parameters, points, print_level):
         contract("simeb,smaje->sijab", t2, Aovvo, r, 1.0, 1.0)            # :217
         contract("smjeb,smaie->sijab", t2, Aovvo, r, 1.0, 1.0)            # :218
 
-    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    E = yield from eng.run_steps(residual, print_level, points[0].E_SCF, points[0].E_nuc)
     return eng, E
 
 
@@ -366,8 +403,32 @@ def _solve_CISD_SO(parameters, points, print_level):
         contract("skajc,sikcb->sijab", Aovvo, t2, r2, 1.0, 1.0)           # :332
         contract("skaic,skjcb->sijab", Aovvo, t2, r2, 1.0, 1.0)           # :333
 
-    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    E = yield from eng.run_steps(residual, print_level, points[0].E_SCF, points[0].E_nuc)
     return eng, E
+
+
+class _PackedLadder:
+    """The (i<->j, a<->b)-symmetric ladder term  L_ijab = sum_cd <ab|cd> t_ijcd  (ci_wfn.py:87, 476) for the half-sum
+    residual form r2 = h + P h: instead of adding L/2 for all o^2 occupied pairs, add L for i < j and L/2 for i == j
+    -- o(o+1)/2 pairs, 46 % fewer flops at o = 12 -- and let the symmetrisation supply the rest
+    ((h + P h)_jiba = L_ijab = L_jiba).  t2 is packed over the pairs (diagonal pre-scaled by 1/2), contracted with
+    the TMA-fed DMMA kernel and scatter-added into h."""
+
+    def __init__(self, W, O, V, nb, dt):
+        self.W, self.O, self.V, self.nb = W, O, V, nb
+        self.npair = O * (O + 1) // 2
+        self.code = 1 if dt == torch.complex128 else 0
+        self.tp = empty((nb, self.npair, V, V), dt)
+        self.hp = empty((nb, self.npair, V, V), dt)
+
+    def apply(self, t2, h):
+        """h[s,i,j,a,b] += w_ij L[s,i,j,a,b] for i <= j (t2, h: [nb, O, O, V, V] views with dense (i,j,a,b) blocks)"""
+        vv = self.V * self.V
+        check(lib.apyib_pack_pairs(self.code, ptr(t2), t2.stride(0), ptr(self.tp), self.tp.stride(0), self.O, vv,
+                                   self.nb, _NULL, stream_ptr()))
+        contract("sabcd,spcd->spab", self.W, self.tp, self.hp, 1.0, 0.0)
+        check(lib.apyib_unpack_pairs_add(self.code, ptr(self.hp), self.hp.stride(0), ptr(h), h.stride(0), self.O, vv,
+                                         self.nb, _NULL, stream_ptr()))
 
 
 class _CISDOperator:
@@ -402,6 +463,7 @@ class _CISDOperator:
         self.Wvvvo, self.Wvvov = blk("abcj", "jabc"), blk("abic", "iabc")
         self.Wovoo, self.Wvooo = blk("kbij", "kijb"), blk("akij", "kija")
         self.Woooo, self.Wvvvv = blk("klij"), blk("abcd")
+        self._ladder = None
 
     def apply(self, t1, t2, r1, r2, half=False, singles=True):
         """r += (linear part of the CISD residual)(t1, t2).  singles=False keeps only the doubles <- doubles
@@ -428,7 +490,12 @@ class _CISDOperator:
         contract("sac,sijcb->sijab", o.Fvv, t2, r2, 1.0, 1.0)               # :471
         contract("ski,skjab->sijab", o.Foo, t2, r2, -1.0, 1.0)              # :473
         contract("sklij,sklab->sijab", o.Woooo, t2, r2, c, 1.0)             # :475
-        contract("sabcd,sijcd->sijab", o.Wvvvv, t2, r2, c, 1.0)             # :476
+        if half and config.PACKED_LADDER:                                   # :476 over the pairs i <= j only
+            if o._ladder is None:
+                o._ladder = _PackedLadder(o.Wvvvv, o.O, o.V, o.nb, t2.dtype)
+            o._ladder.apply(t2, r2)
+        else:
+            contract("sabcd,sijcd->sijab", o.Wvvvv, t2, r2, c, 1.0)         # :476
         contract("skbjc,sikca->sijab", o.Wovvo, t2, r2, -1.0, 1.0)          # :477
         contract("skaic,skjcb->sijab", o.Lovvo, t2, r2, 1.0, 1.0)           # :478
         contract("skbic,skjac->sijab", o.Wovov, t2, r2, -1.0, 1.0)          # :479
@@ -450,12 +517,11 @@ def _solve_CISD(parameters, points, print_level):
     n1, nb = eng.n1, eng.nb
     op = _CISDOperator([pt.F for pt in points], [pt.ERI for pt in points], O, V, bd, eng.dtype)
     eng.r0[:, :n1].copy_(op.Fai)
-    for s in range(nb):                      # the engine keeps K/2 and symmetrises (ci_wfn.py:83 form)
-        check(lib.apyib_axpby(eng.code, eng.n2, 0.5, 0.0, ptr(op.K[s]), 0, 0.0, 0.0, ptr(eng.r0[s, n1:]), stream_ptr()))
+    eng._copy(eng.r0[:, n1:], op.K, 0.5)      # the engine keeps K/2 and symmetrises (ci_wfn.py:83 form)
     eng.w[:, :n1].copy_(op.w1)
     eng.w[:, n1:].copy_(op.w2)
     residual = lambda rh: op.apply(eng.t1(), eng.t2(), eng.t1(eng.r), rh.view(nb, O, O, V, V), half=True)
-    E = eng.run(residual, print_level, points[0].E_SCF, points[0].E_nuc)
+    E = yield from eng.run_steps(residual, print_level, points[0].E_SCF, points[0].E_nuc)
     return eng, E
 
 
@@ -552,12 +618,8 @@ _SOLVERS = {"CID": (_solve_CID, False), "CID_SO": (_solve_CID_SO, False),
             "CISD": (_solve_CISD, True), "CISD_SO": (_solve_CISD_SO, True)}
 
 
-def solve_batch(method, parameters, points, print_level=0):
-    """Solve `method` for a list of _Point objects (identical shapes and dtype) with shared
-    launches.  Returns (results, iterations): results[s] = (E, t2) or (E, t1, t2) exactly as the
-    single-point methods return them."""
-    fn, singles = _SOLVERS[method]
-    eng, E = fn(parameters, points, print_level)
+def _collect(eng, E, singles):
+    """per-point result tuples (E, t2) / (E, t1, t2) of a finished engine, host or device-resident"""
     res = []
     dev_out = config.RETURN_DEVICE
     t1s = eng.t1() if singles else None
@@ -569,10 +631,69 @@ def solve_batch(method, parameters, points, print_level=0):
         if dev_out:
             t2 = t2s[s].clone()
             res.append((E[s], t1s[s].clone(), t2) if singles else (E[s], t2))
-        else:
-            t2 = t2h[s].copy()
-            res.append((E[s], t1h[s].copy(), t2) if singles else (E[s], t2))
-    return res, list(eng.iterations)
+        else:           # disjoint views of the batch's (pinned) host block: no second host copy
+            res.append((E[s], t1h[s], t2h[s]) if singles else (E[s], t2h[s]))
+    return res
+
+
+def solve_batch(method, parameters, points, print_level=0):
+    """Solve `method` for a list of _Point objects (identical shapes and dtype) with shared
+    launches.  Returns (results, iterations): results[s] = (E, t2) or (E, t1, t2) exactly as the
+    single-point methods return them."""
+    fn, singles = _SOLVERS[method]
+    eng, E = _drive([(fn(parameters, points, print_level), None)])[0]
+    return _collect(eng, E, singles), list(eng.iterations)
+
+
+_side_streams = {}
+
+
+def _streams(n):
+    """n side streams of the current device, created once: PyTorch's caching allocator keeps one memory pool per
+    stream, so fresh streams per solve would mean fresh cudaMallocs per solve."""
+    d = torch.cuda.current_device()
+    pool = _side_streams.setdefault(d, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=d))
+    return pool[:n]
+
+
+def _run_jobs(make_jobs, singles):
+    """make_jobs: list of callables, each returning the generator of one batch (its set-up runs at the generator's
+    first step, under the batch's stream).  One batch -> the caller's stream; several -> one side stream each,
+    driven concurrently from this host thread.  Returns [(results, iterations)] per batch."""
+    if len(make_jobs) == 1 or not config.SOLVE_CONCURRENT:
+        out = []
+        for mk in make_jobs:
+            eng, E = _drive([(mk(), None)])[0]
+            out.append((_collect(eng, E, singles), list(eng.iterations)))
+        return out
+    cur = torch.cuda.current_stream()
+    streams = _streams(len(make_jobs))
+    for st in streams:
+        st.wait_stream(cur)                    # inputs may have been produced on the caller's stream
+    done = _drive([(mk(), st) for mk, st in zip(make_jobs, streams)])
+    out = []
+    for (eng, E), st in zip(done, streams):
+        with torch.cuda.stream(st):
+            res = _collect(eng, E, singles)
+        cur.wait_stream(st)
+        for r in res:                          # device-resident results were allocated on a side stream
+            for x in r:
+                if isinstance(x, torch.Tensor) and x.is_cuda:
+                    x.record_stream(cur)
+        out.append((res, list(eng.iterations)))
+    return out
+
+
+def solve_batches(method, parameters, batches, print_level=0):
+    """Several independent batches (e.g. the float64 and the complex128 finite-difference points of one molecule)
+    solved CONCURRENTLY: one CUDA stream per batch, all driven from this host thread (`_drive`) -- every batch is
+    latency bound on its own (a chain of ~40 dependent launches and one 48-byte read-back per iteration), together
+    they fill the device.  Results are identical to solving the batches one after the other (same launches, same
+    order within a batch).  Returns [(results, iterations)] per batch."""
+    fn, singles = _SOLVERS[method]
+    return _run_jobs([(lambda pts=pts: fn(parameters, pts, print_level)) for pts in batches], singles)
 
 
 class ci_wfn(object):
@@ -591,10 +712,10 @@ class ci_wfn(object):
         self.D_ijab = (self.eps_o.reshape(-1, 1, 1, 1) + self.eps_o.reshape(-1, 1, 1)
                        - self.eps_v.reshape(-1, 1) - self.eps_v)                               # ci_wfn.py:43
         if _integrals is None:
-            self._F_dev, self.E_fc = compute_F_MO_dev(self.parameters, self.wfn, self.C_list)  # ci_wfn.py:46
+            self._F_dev, self._E_fc = compute_F_MO_dev(self.parameters, self.wfn, self.C_list)  # ci_wfn.py:46
             self._ERI_dev = compute_ERI_MO_dev(self.parameters, self.wfn, self.C_list)         # ci_wfn.py:47
         else:                               # built for a whole stack of points at once (ci_wfn.many)
-            self._F_dev, self.E_fc, self._ERI_dev = _integrals
+            self._F_dev, self._E_fc, self._ERI_dev = _integrals
         self._F_host = self._ERI_host = None
         self.iterations = 0
 
@@ -605,6 +726,13 @@ class ci_wfn(object):
         C_lists = [get_slices(parameters, w)[0] for w in wfns]
         ints = mo_integrals_many(parameters, wfns, C_lists)
         return [cls(parameters, w, _integrals=i) for w, i in zip(wfns, ints)]
+
+    @property
+    def E_fc(self):
+        """frozen-core energy of utils.compute_F_MO (utils.py:238-243); read back from the device on first use"""
+        if hasattr(self._E_fc, "get"):
+            self._E_fc = self._E_fc.get()
+        return self._E_fc
 
     # numpy views of the MO integrals, as the reference exposes them (analytic_aats.py reads these)
     @property
@@ -655,16 +783,37 @@ class ci_wfn(object):
 
 
 def solve_many(method, parameters, wfns, print_level=0):
-    """Batched counterpart of `[ci_wfn(parameters, w).solve_<method>() for w in wfns]`: the points
-    are grouped by dtype (real nuclear-displacement points / complex field points) and each group
-    is solved with shared launches.  Returns the per-point result tuples in input order."""
-    cis = ci_wfn.many(parameters, wfns)
+    """Batched counterpart of `[ci_wfn(parameters, w).solve_<method>() for w in wfns]`.  The points are grouped by
+    dtype (real nuclear-displacement points / complex field points); the host->device copies of their AO integrals
+    are queued on the copy stream up front (complex points first), and every group runs as its own pipeline -- MO
+    integrals (each point's transform waits for its own upload), integral blocks, iterations -- on its own stream,
+    all groups driven concurrently from this thread: the complex group is already iterating while the real points
+    are still uploading.  Returns the per-point result tuples in input order."""
+    from .utils import ao_prefetch, _is_complex
+    fn, singles = _SOLVERS[method]
     groups = {}
-    for k, c in enumerate(cis):
-        groups.setdefault((c._ERI_dev.dtype, tuple(c._ERI_dev.shape), len(c.eps_o)), []).append(k)
-    out = [None] * len(cis)
-    for idx in groups.values():
-        res, its = solve_batch(method, parameters, [cis[k].point() for k in idx], print_level)
+    for k, w in enumerate(wfns):
+        nf = w.H.basis_set.n_frozen_core()
+        groups.setdefault((0 if _is_complex(w) else 1, int(w.nbf), int(w.ndocc), nf), []).append(k)
+    keys = sorted(groups)                                            # complex groups first
+    ao_prefetch([wfns[k] for key in keys for k in groups[key]])
+    idxs = []
+    for key in keys:                                                 # big shapes: chunks of one dtype, in upload order
+        idx = groups[key]
+        big = 8 * key[1] ** 4 >= config.SOLVE_CHUNK_MIN_BYTES and len(idx) > config.SOLVE_CHUNK
+        nchunk = -(-len(idx) // config.SOLVE_CHUNK) if big else 1
+        size = -(-len(idx) // nchunk)
+        idxs += [idx[i:i + size] for i in range(0, len(idx), size)]
+    cis = [None] * len(wfns)
+
+    def job(idx):
+        for k, c in zip(idx, ci_wfn.many(parameters, [wfns[k] for k in idx])):
+            cis[k] = c
+        return (yield from fn(parameters, [cis[k].point() for k in idx], print_level))
+
+    solved = _run_jobs([(lambda idx=idx: job(idx)) for idx in idxs], singles)
+    out = [None] * len(wfns)
+    for idx, (res, its) in zip(idxs, solved):
         for k, r, it in zip(idx, res, its):
             out[k] = r
             cis[k].iterations = it

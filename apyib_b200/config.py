@@ -41,6 +41,20 @@ def timed(name):
 #             form, O(o^2 v^2 (o+v)) DMMA contractions instead of (C(o,2) C(v,2))^2 determinants
 AAT_ALGORITHM = "lu"
 
+# Spatial CID / CISD (half-sum residual form, r2 = h + P h): evaluate the P-symmetric ladder term <ab|cd> t_ijcd over
+# the o(o+1)/2 occupied pairs i <= j only (ci_wfn._PackedLadder) -- same result up to rounding, 46 % fewer ladder
+# flops at o = 12.
+PACKED_LADDER = _os.environ.get("APYIB_B200_PACKED_LADDER", "1") == "1"
+
+# Batched solves (ci_wfn.solve_many): run the groups of finite-difference points (float64 / complex128 points, and
+# chunks of at most SOLVE_CHUNK points of one dtype when a point's AO integrals exceed SOLVE_CHUNK_MIN_BYTES)
+# concurrently, one CUDA stream per group, driven from one host thread.  False: one group after the other on the
+# caller's stream (what bench.py uses for its instrumented step, so that per-kernel events are not inflated by a
+# concurrent stream).  Chunks let the first points start iterating while the later ones are still uploading.
+SOLVE_CONCURRENT = True
+SOLVE_CHUNK = 32
+SOLVE_CHUNK_MIN_BYTES = 64 << 20
+
 # Route k-contiguous 2-D operand contractions (ladder term, first AO->MO quarter transform) through the
 # TMA-fed kernel (csrc/contract_tma.cu); the gather kernel handles everything else.
 USE_TMA = True

@@ -56,7 +56,7 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
         : "memory");
 }
 
-// 64 x BN CTA tile (BN = 64 or 48), 4 warps of 32 x BN/2, slab = 128 bytes of k (8 complex / 16 real),
+// 64 x BN CTA tile (BN = 48, 64 or 80), 4 warps of 32 x BN/2, slab = 128 bytes of k (8 complex / 16 real),
 // STAGES-deep ring.  BN = 48 exists for the ladder term: N = o^2 = 144 is 3 x 48 but 2.25 x 64, i.e. a
 // quarter of the DMMAs of a 64-wide tiling would multiply padding.
 template <bool CPLX, int STAGES, int BN>
@@ -262,7 +262,17 @@ extern "C" int apyib_contract_tma(int dtype, const void *d_A, const void *d_B, v
     }
     CUtensorMap mapA, mapB;
     const int64_t kd = K * (dtype == APYIB_C128 ? 2 : 1);
-    const int bn = (((N + 47) / 48) * 48 < ((N + 63) / 64) * 64) ? 48 : 64;      // less padding wins
+    // B-tile width: 48, 64 or 80 columns, whichever pads N least (ties: the wider tile).  N = o^2 = 144 is 3 x 48;
+    // the pair-packed ladder has N = o(o+1)/2 = 78 -> one 80-wide tile instead of 2 x 48 (19 % padding).
+    int bn = 64;
+    {
+        int64_t best = ((N + 63) / 64) * 64;
+        const int cand[2] = {80, 48};
+        for (int c : cand) {
+            const int64_t padded = ((N + c - 1) / c) * c;
+            if (padded < best || (padded == best && c > bn)) { best = padded; bn = c; }
+        }
+    }
     if (!make_map(&mapA, d_A, kd, M, lda * es, batch, a_bstride * es, 64) ||
         !make_map(&mapB, d_B, kd, N, ldb * es, batch, b_bstride * es, bn)) {
         set_error("apyib_contract_tma: cuTensorMapEncodeTiled failed or is unavailable");
@@ -288,9 +298,9 @@ extern "C" int apyib_contract_tma(int dtype, const void *d_A, const void *d_B, v
         contract_tma_kernel<CP, STAGES, BNN><<<grid, 128, smem, st>>>(mapA, mapB, a);                               \
     } while (0)
     if (dtype == APYIB_C128) {
-        if (bn == 48) APYIB_TMA_LAUNCH(true, 48); else APYIB_TMA_LAUNCH(true, 64);
+        if (bn == 48) APYIB_TMA_LAUNCH(true, 48); else if (bn == 80) APYIB_TMA_LAUNCH(true, 80); else APYIB_TMA_LAUNCH(true, 64);
     } else {
-        if (bn == 48) APYIB_TMA_LAUNCH(false, 48); else APYIB_TMA_LAUNCH(false, 64);
+        if (bn == 48) APYIB_TMA_LAUNCH(false, 48); else if (bn == 80) APYIB_TMA_LAUNCH(false, 80); else APYIB_TMA_LAUNCH(false, 64);
     }
 #undef APYIB_TMA_LAUNCH
     APYIB_LAUNCH_CHECK();

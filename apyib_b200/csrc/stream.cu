@@ -320,6 +320,120 @@ __global__ void __launch_bounds__(kThreads) symmetrize_kernel(const T *h, T *out
 }
 
 // --------------------------------------------------------------------------------------
+// round-2 additions: batched streaming helpers
+// --------------------------------------------------------------------------------------
+// float64 -> complex128 (imaginary part 0): the real AO integrals of a magnetic-field point are uploaded once as
+// float64 (half the PCIe bytes) and widened on the device for the complex128 contraction kernels.
+__global__ void __launch_bounds__(kThreads) widen_kernel(cplx *__restrict__ dst, const double *__restrict__ src, int64_t len) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += kUnroll * stride) {
+        double v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + u * stride < len) v[u] = src[base + u * stride];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + u * stride < len) dst[base + u * stride] = make_cplx(v[u], 0.0);
+    }
+}
+
+// nb rows of `len` elements, row pitches dst_stride / src_stride (elements): dst[s][:] = alpha * src[s][:]
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+copy_rows_kernel(T *__restrict__ dst, int64_t dst_stride, const T *__restrict__ src, int64_t src_stride, int64_t len, double alpha,
+                 const int32_t *__restrict__ active) {
+    const int s = blockIdx.y;
+    if (active != nullptr && !active[s]) return;
+    T *d = dst + (int64_t)s * dst_stride;
+    const T *x = src + (int64_t)s * src_stride;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < len; base += kUnroll * stride) {
+        T v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + u * stride < len) v[u] = x[base + u * stride];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + u * stride < len) d[base + u * stride] = alpha * v[u];
+    }
+}
+
+// out[s][i,j,a,b] = h[s][i,j,a,b] + h[s][j,i,b,a] for nb points; one CTA per (point, i <= j pair): the (a,b) block
+// and its transpose partner are staged through shared memory, so both global reads and both writes are coalesced.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+symmetrize_batch_kernel(const T *__restrict__ h, int64_t h_stride, T *__restrict__ out, int64_t out_stride, int o, int v,
+                        const int32_t *__restrict__ active) {
+    const int s = blockIdx.y;
+    if (active != nullptr && !active[s]) return;
+    // blockIdx.x enumerates pairs i <= j
+    int p = blockIdx.x, i = 0;
+    while (p >= o - i) { p -= o - i; ++i; }
+    const int j = i + p;
+    const T *hs = h + (int64_t)s * h_stride;
+    T *os = out + (int64_t)s * out_stride;
+    const int64_t vv = (int64_t)v * v;
+    const T *hij = hs + ((int64_t)i * o + j) * vv;
+    const T *hji = hs + ((int64_t)j * o + i) * vv;
+    T *oij = os + ((int64_t)i * o + j) * vv;
+    T *oji = os + ((int64_t)j * o + i) * vv;
+    constexpr int TS = 32;
+    __shared__ T tile_ij[TS][TS + 1];
+    __shared__ T tile_ji[TS][TS + 1];
+    const int tx = threadIdx.x % TS, ty = threadIdx.x / TS;          // 32 x 8
+    for (int a0 = 0; a0 < v; a0 += TS)
+        for (int b0 = 0; b0 < v; b0 += TS) {
+            // tile (a0.., b0..) of h_ij and tile (b0.., a0..) of h_ji
+            for (int r = ty; r < TS; r += kThreads / TS) {
+                const int a = a0 + r, b = b0 + tx;
+                tile_ij[r][tx] = (a < v && b < v) ? hij[(int64_t)a * v + b] : scalar<T>::zero();
+                const int bb = b0 + r, aa = a0 + tx;
+                tile_ji[r][tx] = (bb < v && aa < v) ? hji[(int64_t)bb * v + aa] : scalar<T>::zero();
+            }
+            __syncthreads();
+            for (int r = ty; r < TS; r += kThreads / TS) {
+                const int a = a0 + r, b = b0 + tx;
+                if (a < v && b < v) oij[(int64_t)a * v + b] = tile_ij[r][tx] + tile_ji[tx][r];
+                const int bb = b0 + r, aa = a0 + tx;
+                if (i != j && bb < v && aa < v) oji[(int64_t)bb * v + aa] = tile_ji[r][tx] + tile_ij[tx][r];
+            }
+            __syncthreads();
+        }
+}
+
+// pair packing for P-symmetric contractions (ladder <ab|cd> t_ijcd, ci_wfn.py:476): tp[s][p][:] = w_p * t[s][i_p, j_p][:]
+// over the pairs i <= j (w = 1 for i < j, 1/2 for i == j), and the scatter-add back: h[s][i_p, j_p][:] += hp[s][p][:].
+// With r2 = h + P h (symmetrize) the i > j blocks and the other half of the diagonal blocks come from the partner.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pack_pairs_kernel(const T *__restrict__ t, int64_t t_stride, T *__restrict__ tp, int64_t tp_stride, int o, int64_t vv,
+                  const int32_t *__restrict__ active) {
+    const int s = blockIdx.z;
+    if (active != nullptr && !active[s]) return;
+    int p = blockIdx.y, i = 0;
+    while (p >= o - i) { p -= o - i; ++i; }
+    const int j = i + p;
+    const double w = (i == j) ? 0.5 : 1.0;
+    const T *src = t + (int64_t)s * t_stride + ((int64_t)i * o + j) * vv;
+    T *dst = tp + (int64_t)s * tp_stride + (int64_t)blockIdx.y * vv;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < vv; e += (int64_t)gridDim.x * blockDim.x) dst[e] = w * src[e];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+unpack_pairs_add_kernel(const T *__restrict__ hp, int64_t hp_stride, T *__restrict__ h, int64_t h_stride, int o, int64_t vv,
+                        const int32_t *__restrict__ active) {
+    const int s = blockIdx.z;
+    if (active != nullptr && !active[s]) return;
+    int p = blockIdx.y, i = 0;
+    while (p >= o - i) { p -= o - i; ++i; }
+    const int j = i + p;
+    const T *src = hp + (int64_t)s * hp_stride + (int64_t)blockIdx.y * vv;
+    T *dst = h + (int64_t)s * h_stride + ((int64_t)i * o + j) * vv;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < vv; e += (int64_t)gridDim.x * blockDim.x) dst[e] = dst[e] + src[e];
+}
+
+// --------------------------------------------------------------------------------------
 // dots: out[j] = sum_i op(x_j[i]) * y[i]
 // --------------------------------------------------------------------------------------
 constexpr int kMaxVec = 8;
@@ -873,6 +987,75 @@ extern "C" int apyib_axpby(int dtype, int64_t len, double alpha_re, double alpha
     else
         axpby_kernel<double><<<stream_grid(len), kThreads, 0, st>>>(len, alpha_re, (const double *)d_x, 0, beta_re, hb,
                                                                    (double *)d_y);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_widen(void *d_dst, const void *d_src, int64_t len, void *stream) {
+    if (len == 0) return APYIB_OK;
+    APYIB_REQUIRE(d_dst && d_src, "null pointer");
+    widen_kernel<<<stream_grid(len), kThreads, 0, (cudaStream_t)stream>>>((cplx *)d_dst, (const double *)d_src, len);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_copy_rows(int dtype, void *d_dst, int64_t dst_stride, const void *d_src, int64_t src_stride, int64_t len,
+                               int nb, double alpha, const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    if (len == 0 || nb == 0) return APYIB_OK;
+    APYIB_REQUIRE(d_dst && d_src && nb > 0 && nb <= 65535, "arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(std::max(1, std::min(stream_grid(len), std::max(1, 1184 / nb))), nb);
+    if (dtype == APYIB_C128)
+        copy_rows_kernel<cplx><<<grid, kThreads, 0, st>>>((cplx *)d_dst, dst_stride, (const cplx *)d_src, src_stride, len, alpha, d_active);
+    else
+        copy_rows_kernel<double><<<grid, kThreads, 0, st>>>((double *)d_dst, dst_stride, (const double *)d_src, src_stride, len, alpha, d_active);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_symmetrize_ijab_batch(int dtype, const void *d_half, int64_t half_stride, void *d_out, int64_t out_stride,
+                                           int64_t o, int64_t v, int nb, const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    APYIB_REQUIRE(d_half && d_out && d_half != d_out, "pointers (must be out of place)");
+    if (o == 0 || v == 0 || nb == 0) return APYIB_OK;
+    APYIB_REQUIRE(nb > 0 && nb <= 65535 && o < 46340, "batch / size");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)(o * (o + 1) / 2), nb);
+    if (dtype == APYIB_C128)
+        symmetrize_batch_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_half, half_stride, (cplx *)d_out, out_stride, (int)o, (int)v, d_active);
+    else
+        symmetrize_batch_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_half, half_stride, (double *)d_out, out_stride, (int)o, (int)v, d_active);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_pack_pairs(int dtype, const void *d_t, int64_t t_stride, void *d_tp, int64_t tp_stride, int64_t o, int64_t vv,
+                                int nb, const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    if (o == 0 || vv == 0 || nb == 0) return APYIB_OK;
+    APYIB_REQUIRE(d_t && d_tp && nb > 0 && nb <= 65535 && o * (o + 1) / 2 <= 65535, "arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)std::min<int64_t>((vv + kThreads - 1) / kThreads, 8), (unsigned)(o * (o + 1) / 2), nb);
+    if (dtype == APYIB_C128)
+        pack_pairs_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_t, t_stride, (cplx *)d_tp, tp_stride, (int)o, vv, d_active);
+    else
+        pack_pairs_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_t, t_stride, (double *)d_tp, tp_stride, (int)o, vv, d_active);
+    APYIB_LAUNCH_CHECK();
+    return APYIB_OK;
+}
+
+extern "C" int apyib_unpack_pairs_add(int dtype, const void *d_hp, int64_t hp_stride, void *d_h, int64_t h_stride, int64_t o,
+                                      int64_t vv, int nb, const int32_t *d_active, void *stream) {
+    APYIB_REQUIRE(dtype == APYIB_F64 || dtype == APYIB_C128, "dtype");
+    if (o == 0 || vv == 0 || nb == 0) return APYIB_OK;
+    APYIB_REQUIRE(d_hp && d_h && nb > 0 && nb <= 65535 && o * (o + 1) / 2 <= 65535, "arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)std::min<int64_t>((vv + kThreads - 1) / kThreads, 8), (unsigned)(o * (o + 1) / 2), nb);
+    if (dtype == APYIB_C128)
+        unpack_pairs_add_kernel<cplx><<<grid, kThreads, 0, st>>>((const cplx *)d_hp, hp_stride, (cplx *)d_h, h_stride, (int)o, vv, d_active);
+    else
+        unpack_pairs_add_kernel<double><<<grid, kThreads, 0, st>>>((const double *)d_hp, hp_stride, (double *)d_h, h_stride, (int)o, vv, d_active);
     APYIB_LAUNCH_CHECK();
     return APYIB_OK;
 }

@@ -44,7 +44,9 @@ def ptr(t):
 
 
 def to_device(x, dtype=None):
-    """numpy (or torch) -> contiguous CUDA tensor, float64 or complex128."""
+    """numpy (or torch) -> contiguous CUDA tensor, float64 or complex128, on the current stream.  A host array that
+    lives in pinned memory (see pin_host_inputs) is copied asynchronously; the caller keeps it alive and unchanged
+    until the stream has passed the copy (the finite-difference inputs are never mutated on the path)."""
     if isinstance(x, torch.Tensor):
         t = x
     else:
@@ -56,12 +58,74 @@ def to_device(x, dtype=None):
         t = t.to(dtype)
     if not t.is_cuda:
         COUNTERS["h2d_bytes"] += t.numel() * t.element_size()
+        return t.to(device(), non_blocking=t.numel() >= _PIN_MIN // 8 and t.is_pinned()).contiguous()
     return t.to(device(), non_blocking=False).contiguous()
 
 
+# ---- pinned host inputs ---------------------------------------------------------------------------------------
+_PIN_MIN = 1 << 20            # arrays below 1 MiB are not worth a registration
+_PINNED = {}                  # address -> (nbytes, array kept alive)
+
+
+def pin_array(a):
+    """Page-lock a C-contiguous numpy array IN PLACE (cudaHostRegister), so that its host->device copies run at full
+    PCIe rate and asynchronously.  Returns the number of bytes newly registered (0: already pinned / too small /
+    not registrable)."""
+    if not isinstance(a, np.ndarray) or not a.flags.c_contiguous or a.nbytes < _PIN_MIN:
+        return 0
+    addr = a.ctypes.data
+    if addr in _PINNED:
+        return 0
+    require_cuda()
+    rc = torch.cuda.cudart().cudaHostRegister(addr, a.nbytes, 0)
+    if int(rc) != 0:
+        return 0
+    _PINNED[addr] = (a.nbytes, a)
+    return a.nbytes
+
+
+def unpin_all():
+    for addr in list(_PINNED):
+        torch.cuda.cudart().cudaHostUnregister(addr)
+        del _PINNED[addr]
+
+
+def pin_host_inputs(wfns):
+    """Register the large host inputs (AO ERIs, T, V, C) of a list of hf_wfn-like objects.  Returns (arrays,
+    bytes) newly pinned.  Optional: unpinned inputs work, their copies are synchronous and slower."""
+    n = nbytes = 0
+    for w in wfns:
+        for a in (getattr(w.H, "ERI", None), getattr(w.H, "T", None), getattr(w.H, "V", None), getattr(w, "C", None)):
+            b = pin_array(a) if a is not None else 0
+            n += 1 if b else 0
+            nbytes += b
+    return n, nbytes
+
+
+_copy_streams = {}
+
+
+def copy_stream():
+    """Dedicated stream for host->device input copies (overlaps the kernels of the compute stream)."""
+    d = torch.cuda.current_device()
+    if d not in _copy_streams:
+        _copy_streams[d] = torch.cuda.Stream(device=d)
+    return _copy_streams[d]
+
+
 def to_host(t):
-    COUNTERS["d2h_bytes"] += t.numel() * t.element_size()
-    return t.detach().cpu().numpy()
+    """CUDA tensor -> fresh numpy array owned by the caller.  Large results land in page-locked host memory (torch's
+    caching pinned allocator), so the copy runs at full PCIe rate and a later re-upload of the same array (the
+    amplitudes go back to the device for the AAT assembly) is asynchronous as well."""
+    nbytes = t.numel() * t.element_size()
+    COUNTERS["d2h_bytes"] += nbytes
+    t = t.detach()
+    if t.is_cuda and nbytes >= _PIN_MIN:
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out.numpy()
+    return t.cpu().numpy()
 
 
 def empty(shape, dtype):

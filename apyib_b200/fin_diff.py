@@ -70,22 +70,56 @@ class finite_difference(object):
         return [wfn.E_SCF, E, wfn.H.E_nuc], T_list, wfn.C, wfn.H.basis_set
 
     # -- fin_diff.py:267-372 ------------------------------------------------------------------
-    def compute_AAT(self, nuc_pert_strength, mag_pert_strength, points=None):
+    # AO integrals, MO integrals, integral blocks and DIIS history of a point live on the device while its batch is
+    # being solved (~3 nbf^4 words); the AAT points are solved in chunks that stay below this budget.
+    AAT_BATCH_BYTES = 120 << 30
+
+    def compute_AAT(self, nuc_pert_strength, mag_pert_strength, points=None, unperturbed_wfn=None):
         """Returns the reference's 12-tuple of lists.  `points` (optional) restricts the work to a
-        subset (sharding); entries not computed are left as None.  All host SCFs run first, then the
-        correlated solves of all points go to the GPU together (batched launches)."""
+        subset (sharding); entries not computed are left as None.  The points are processed in chunks bounded by
+        AAT_BATCH_BYTES: host SCFs of a chunk, then its correlated solves on the GPU together (batched launches),
+        then the chunk's AO integrals are released on both sides -- only (C, basis, T) survive per point, as in
+        the reference's serial loop (fin_diff.py:285-370).  `unperturbed_wfn` (optional, sharded driver): an
+        already converged SCF of the unperturbed point whose correlated solve joins the first chunk; the 12-tuple
+        is then followed by its (E_corr, T_list)."""
         n3 = 3 * self.natom
         res = {("R", +1): ([None] * n3, [None] * n3, [None] * n3), ("R", -1): ([None] * n3, [None] * n3, [None] * n3),
                ("B", +1): ([None] * 3, [None] * 3, [None] * 3), ("B", -1): ([None] * 3, [None] * 3, [None] * 3)}
         pts = list(aat_points(self.natom) if points is None else points)
-        wfns = [self.scf_aat_point(pt, nuc_pert_strength, mag_pert_strength) for pt in pts]
-        solved = correlated_many(self.parameters, wfns) if pts else []
-        for pt, wfn, (E, T_list) in zip(pts, wfns, solved):
-            Cs, Bs, Ts = res[(pt[0], pt[2])]
-            Cs[pt[1]], Bs[pt[1]], Ts[pt[1]] = wfn.C, wfn.H.basis_set, T_list
+        extra = None
+        chunk_p, chunk_w, nbytes = [], [], 0
+
+        def flush():
+            nonlocal extra, nbytes
+            wf = ([unperturbed_wfn] if (unperturbed_wfn is not None and extra is None) else []) + chunk_w
+            if wf:
+                solved = correlated_many(self.parameters, wf)
+                if unperturbed_wfn is not None and extra is None:
+                    extra, solved = solved[0], solved[1:]
+                for pt, wfn, (E, T_list) in zip(chunk_p, chunk_w, solved):
+                    Cs, Bs, Ts = res[(pt[0], pt[2])]
+                    Cs[pt[1]], Bs[pt[1]], Ts[pt[1]] = wfn.C, wfn.H.basis_set, T_list
+                    release_ao(wfn)
+                    try:
+                        wfn.H.ERI = None                       # nbf^4 words of host memory per point
+                    except AttributeError:
+                        pass
+            chunk_p.clear()
+            chunk_w.clear()
+            nbytes = 0
+
+        for pt in pts:
+            w = self.scf_aat_point(pt, nuc_pert_strength, mag_pert_strength)
+            chunk_p.append(pt)
+            chunk_w.append(w)
+            nbytes += 3 * (16 if np.iscomplexobj(w.C) else 8) * w.nbf ** 4
+            if nbytes >= self.AAT_BATCH_BYTES:
+                flush()
+        flush()
         (npC, npB, npT), (nnC, nnB, nnT) = res[("R", +1)], res[("R", -1)]
         (mpC, mpB, mpT), (mnC, mnB, mnT) = res[("B", +1)], res[("B", -1)]
-        return npC, nnC, npB, nnB, npT, nnT, mpC, mnC, mpB, mnB, mpT, mnT
+        out = (npC, nnC, npB, nnB, npT, nnT, mpC, mnC, mpB, mnB, mpT, mnT)
+        return out + (extra,) if unperturbed_wfn is not None else out
 
     # -- energy-only double differences ---------------------------------------------------------
     # AO integrals + ERI_MO of a point live on the device while its batch is being solved; bound the batch.

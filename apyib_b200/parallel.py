@@ -21,7 +21,6 @@ import numpy as np
 
 from . import config
 from .aats import AAT
-from .energy import energy
 from .fin_diff import finite_difference, aat_points, point_cost
 from .hostchem import Hamiltonian, hf_wfn
 
@@ -111,7 +110,8 @@ def exchange_points(dist, blob, world):
 def owned_elements(n3, rank, world):
     """(alpha, beta) elements of the (3N,3) tensor evaluated by `rank`: whole rows alpha, round
     robin.  All determinant families that depend on alpha (pu/nu[alpha], pp/pn/np/nn[alpha][:]) are
-    then private to one rank; only the 7 alpha-independent overlaps (uu, up/un) are recomputed."""
+    then private to one rank (AAT(..., rows=) builds overlaps, norms and scaled amplitudes for the owned rows
+    only); the 7 alpha-independent overlaps (uu, up/un) are evaluated per rank, against the owned bra rows."""
     return [(a, b) for a in range(n3) if a % world == rank for b in range(3)]
 
 
@@ -128,53 +128,64 @@ def gather_tensor(dist, I, world):
 
 
 def compute_parallel_aats(parameters, nuc_pert_strength, mag_pert_strength, normalization='full', num_processes=4):
+    from .energy import scf_point
     dist, rank, world = _dist()
-    E_list, T_list, C, basis = energy(parameters)
-    E_tot = E_list[0] + E_list[1] + E_list[2]
-    if config.VERBOSE and rank == 0:
-        print("Total Energy: ", E_tot)
-    H = Hamiltonian(parameters)
-    wfn = hf_wfn(H)
-    natom = H.molecule.natom()
+    # every rank needs the unperturbed orbitals (phase reference of all points): host SCF on every rank; its
+    # correlated solve is ONE more point of the partition, solved by one rank and exchanged with the others
+    wfn = scf_point(parameters)
+    C, basis = wfn.C, wfn.H.basis_set
+    natom = wfn.H.molecule.natom()
 
     fd = finite_difference(parameters, basis, C)
-    pts = aat_points(natom)
+    pts = [("U", 0, 0)] + aat_points(natom)
     owner = partition(pts, [point_cost(p[0]) for p in pts], world)
     mine = [p for p, o in zip(pts, owner) if o == rank]
-    lists = fd.compute_AAT(nuc_pert_strength, mag_pert_strength, points=mine)
+    own_u = ("U", 0, 0) in mine
+    lists = fd.compute_AAT(nuc_pert_strength, mag_pert_strength, points=[p for p in mine if p[0] != "U"],
+                           unperturbed_wfn=wfn if own_u else None)
+    blob = {}
+    if own_u:
+        E_corr, T_list = lists[-1]
+        lists = lists[:-1]
+        blob[("U", 0, 0)] = (E_corr, T_list)
+    slot = lambda p: ((0 if p[0] == "R" else 6) + (0 if p[2] > 0 else 1), p[1])
     if world > 1:
         # exchange (C, T) of every point; basis handles are rebuilt locally (geometry only)
-        blob = {}
         for p in mine:
-            i0 = 0 if p[2] > 0 else 1
-            grp = 0 if p[0] == "R" else 6
-            blob[p] = (lists[grp + i0][p[1]], lists[grp + 4 + i0][p[1]])
+            if p[0] != "U":
+                g, i = slot(p)
+                blob[p] = (lists[g][i], lists[g + 4][i])
         lists = [list(x) for x in lists]
-        for p, (Cp, Tp) in exchange_points(dist, blob, world).items():
-            i0 = 0 if p[2] > 0 else 1
-            grp = 0 if p[0] == "R" else 6
-            lists[grp + i0][p[1]] = Cp
-            lists[grp + 4 + i0][p[1]] = Tp
-        for p in pts:                      # basis handles for points solved elsewhere
-            i0 = 0 if p[2] > 0 else 1
-            grp = 0 if p[0] == "R" else 6
-            if lists[grp + 2 + i0][p[1]] is None:
+        rows = sorted(set(a for a, _ in owned_elements(3 * natom, rank, world)))
+        for p, val in exchange_points(dist, blob, world).items():
+            if p[0] == "U":
+                blob[p] = val
+                continue
+            g, i = slot(p)
+            lists[g][i], lists[g + 4][i] = val
+        for p in pts[1:]:                  # basis handles for points solved elsewhere (owned rows and field points only)
+            g, i = slot(p)
+            if lists[g + 2][i] is None and (p[0] == "B" or i in rows):
                 if p[0] == "R":
                     fd.parameters["geom"] = fd._displaced([(p[1], p[2] * nuc_pert_strength)])
-                    lists[grp + 2 + i0][p[1]] = Hamiltonian(fd.parameters).basis_set
+                    lists[g + 2][i] = Hamiltonian(fd.parameters).basis_set
                     fd._reset()
                 else:
-                    lists[grp + 2 + i0][p[1]] = basis
+                    lists[g + 2][i] = basis
+    else:
+        rows = None
+    E_corr, T_list = blob[("U", 0, 0)]
+    if config.VERBOSE and rank == 0:
+        print("Total Energy: ", wfn.E_SCF + E_corr + wfn.H.E_nuc)
     (nuc_pos_C, nuc_neg_C, nuc_pos_basis, nuc_neg_basis, nuc_pos_T, nuc_neg_T,
      mag_pos_C, mag_neg_C, mag_pos_basis, mag_neg_basis, mag_pos_T, mag_neg_T) = lists
 
     AATs = AAT(parameters, wfn, C, basis, T_list, nuc_pos_C, nuc_neg_C, nuc_pos_basis, nuc_neg_basis, nuc_pos_T,
                nuc_neg_T, mag_pos_C, mag_neg_C, mag_pos_basis, mag_neg_basis, mag_pos_T, mag_neg_T,
-               nuc_pert_strength, mag_pert_strength)
+               nuc_pert_strength, mag_pert_strength, rows=rows)
     spatial = parameters['method'] in ('RHF', 'MP2', 'CID', 'CISD')
     fn = AATs.compute_spatial_aats if spatial else AATs.compute_SO_aats
     I = np.zeros((3 * natom, 3))
-    AATs.prefetch_rows([a for a, _ in owned_elements(3 * natom, rank, world)])
     for a, b in owned_elements(3 * natom, rank, world):
         I[a, b] = fn(a, b, normalization)
     I = gather_tensor(dist, I, world)

@@ -13,7 +13,7 @@ import torch
 
 from ._lib import lib, check
 from .contraction import contract, contract_new
-from .device import (to_device, to_host, empty, zeros, dtype_code, ptr, stream_ptr, reduce_scratch, i32, i64)
+from .device import (to_device, to_host, empty, zeros, dtype_code, ptr, stream_ptr, reduce_scratch, i32, i64, copy_stream)
 
 SPATIAL_METHODS = ("RHF", "MP2", "CID", "CISD")
 SO_METHODS = ("MP2_SO", "CID_SO", "CISD_SO")
@@ -40,8 +40,7 @@ def get_slices(parameters, wfn):
 # ---------------------------------------------------------------------------------------------
 # upload-once cache of the per-geometry AO integrals (north star: "uploaded once")
 # ---------------------------------------------------------------------------------------------
-def ao_on_device(wfn, want_complex):
-    H = wfn.H
+def _ao_cache(H):
     cache = getattr(H, "_apyib_b200_dev", None)
     if cache is None:
         cache = {}
@@ -49,14 +48,54 @@ def ao_on_device(wfn, want_complex):
             H._apyib_b200_dev = cache
         except AttributeError:
             pass
+    return cache
+
+
+def ao_prefetch(wfns):
+    """Start the host->device copies of the AO integrals (h = T + V and the nbf^4 ERIs) of `wfns`, in this order, on
+    the copy stream -- the consumers (ao_on_device) make the compute stream wait on a per-point event, so the copies
+    of later points overlap the kernels of earlier ones.  Arrays are uploaded in their host dtype (the AO ERIs of a
+    magnetic-field point are real: half the bytes of a complex128 copy)."""
+    cs = copy_stream()
+    for w in wfns:
+        cache = _ao_cache(w.H)
+        if "raw" in cache or "r" in cache or "c" in cache:
+            continue
+        with torch.cuda.stream(cs):
+            h = to_device(np.asarray(w.H.T) + np.asarray(w.H.V))
+            G = cache.get("eri_r")                      # uploaded by the device-assisted SCF already (hostchem)
+            if G is None:
+                G = to_device(np.asarray(w.H.ERI))
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        cache["raw"] = (h, G, ev)
+
+
+def _widen(x):
+    out = torch.empty(x.shape, dtype=torch.complex128, device=x.device)
+    check(lib.apyib_widen(ptr(out), ptr(x), x.numel(), stream_ptr()))
+    return out
+
+
+def ao_on_device(wfn, want_complex):
+    cache = _ao_cache(wfn.H)
     key = "c" if want_complex else "r"
     if key not in cache:
-        dt = torch.complex128 if want_complex else torch.float64
-        h = np.asarray(H.T) + np.asarray(H.V)
-        if not want_complex and (np.iscomplexobj(h) or np.iscomplexobj(H.ERI)):
-            raise TypeError("complex integrals need the complex path")
-        G = None if want_complex else cache.get("eri_r")      # uploaded by the device-assisted SCF already (hostchem)
-        cache[key] = (to_device(h, dt), G if G is not None else to_device(np.asarray(H.ERI), dt))
+        if "raw" not in cache:
+            ao_prefetch([wfn])
+        h, G, ev = cache["raw"]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for x in (h, G):
+            x.record_stream(cur)
+        if want_complex:
+            cache[key] = tuple(x if x.dtype == torch.complex128 else _widen(x) for x in (h, G))
+        else:
+            if h.dtype != torch.float64 or G.dtype != torch.float64:
+                raise TypeError("complex integrals need the complex path")
+            cache[key] = (h, G)
+        if cache[key][1] is not G:
+            del cache["raw"]                            # the float64 upload of a complex point is not needed again
     return cache[key]
 
 
@@ -76,7 +115,22 @@ def _is_complex(wfn):
 # ---------------------------------------------------------------------------------------------
 # a2  compute_F_MO                                                      (apyib/utils.py:217-254)
 # ---------------------------------------------------------------------------------------------
-def compute_F_MO_dev(parameters, wfn, C_list):
+class LazyScalar:
+    """A scalar result that is still on the device (the frozen-core energy of compute_F_MO): reading it back forces a
+    host-device synchronisation, so the batched drivers defer it until somebody asks (ci_wfn.E_fc)."""
+
+    def __init__(self, dev, cplx, index=None):
+        self.dev, self.cplx, self.index = dev, cplx, index
+
+    def get(self):
+        h = to_host(self.dev)
+        if self.index is not None:            # one entry of a per-point complex128 vector
+            x = h[self.index]
+            return complex(x) if self.cplx else float(np.real(x))
+        return complex(h[0], h[1]) if self.cplx else float(h[0])
+
+
+def compute_F_MO_dev(parameters, wfn, C_list, lazy=False):
     f, o, v, t = C_list
     cplx = _is_complex(wfn)
     dt = torch.complex128 if cplx else torch.float64
@@ -98,8 +152,9 @@ def compute_F_MO_dev(parameters, wfn, C_list):
         e = zeros((2,), torch.float64)
         check(lib.apyib_dots(dtype_code(hs), ptr(D_fc.transpose(0, 1).contiguous()), 0, 1, ptr(hs),
                              hs.numel(), 0, ptr(e), ptr(reduce_scratch()), stream_ptr()))
-        eh = to_host(e)
-        E_fc = complex(eh[0], eh[1]) if cplx else float(eh[0])
+        E_fc = LazyScalar(e, cplx)
+        if not lazy:
+            E_fc = E_fc.get()
         h = h_fc
     _, F_AO = fock_like(h, Cd[:, o])
     Ct = Cd[:, t]
@@ -151,7 +206,7 @@ def mo_integrals_many(parameters, wfns, C_lists):
         itemsize = 16 if cplx else 8
         if len(idx) == 1 or len(idx) * nbf ** 4 * itemsize > MO_BATCH_BYTES:
             for k in idx:
-                F, E_fc = compute_F_MO_dev(parameters, wfns[k], C_lists[k])
+                F, E_fc = compute_F_MO_dev(parameters, wfns[k], C_lists[k], lazy=True)
                 out[k] = (F, E_fc, compute_ERI_MO_dev(parameters, wfns[k], C_lists[k]))
             continue
         dt = torch.complex128 if cplx else torch.float64
@@ -176,8 +231,7 @@ def mo_integrals_many(parameters, wfns, C_lists):
             hs = h + h_fc                                                  # (plumbing: one elementwise add per group)
             e = zeros((len(idx),), dt)
             contract("snm,smn->s", D_fc, hs, e, 1.0, 0.0)
-            eh = to_host(e)
-            E_fc = [complex(x) if cplx else float(np.real(x)) for x in eh]
+            E_fc = [LazyScalar(e, cplx, j) for j in range(len(idx))]
             h = h_fc
         _, F_AO = fock_like(h, Cd[:, :, o])
         Ct = Cd[:, :, t]
@@ -310,3 +364,32 @@ def compute_phase(ndocc, nbf, unperturbed_basis, unperturbed_wfn, ket_basis, ket
     N = np.sqrt(d * np.conjugate(d))
     phase = d / N
     return np.asarray(ket_wfn) * (phase ** -1)[None, :]
+
+
+# ---------------------------------------------------------------------------------------------
+# a10  solve_general_DIIS                                               (apyib/utils.py:104-140)
+# ---------------------------------------------------------------------------------------------
+def solve_general_DIIS(parameters, res_vec, t_vec, e_iter, t_iter, iteration, min_DIIS=1, max_DIIS=7):
+    """The reference's DIIS step with its own calling convention (numpy arrays in and out: error / amplitude history
+    as columns, returns (t_vec, e_iter, t_iter)).  The CI solvers of this package keep their history in device ring
+    buffers and never call this; it exists for external callers of apyib.utils and runs the same kernels: Gram
+    matrix B = e^H e by the contraction kernel, the bordered (m+1) x (m+1) solve by `apyib_diis_solve`, the
+    extrapolation t = sum_j c_j t_j by the contraction kernel."""
+    e_iter, t_iter = np.asarray(e_iter), np.asarray(t_iter)
+    while e_iter.shape[1] > max_DIIS:                                     # utils.py:109-112
+        e_iter, t_iter = e_iter[:, 1:], t_iter[:, 1:]
+    if iteration != 1:                                                    # utils.py:117-119
+        e_iter = np.hstack((e_iter, np.atleast_2d(np.asarray(res_vec)).T))
+        t_iter = np.hstack((t_iter, np.atleast_2d(np.asarray(t_vec)).T))
+    m = e_iter.shape[1]
+    if m > 8:
+        raise ValueError("solve_general_DIIS: at most 8 history vectors (max_DIIS <= 7)")
+    cplx = np.iscomplexobj(e_iter) or np.iscomplexobj(t_iter)
+    E = to_device(np.ascontiguousarray(e_iter.T).astype(np.complex128), torch.complex128)      # [m, len]
+    T = to_device(np.ascontiguousarray(t_iter.T).astype(np.complex128), torch.complex128)
+    B = contract_new("mo,no->mn", E, E, conj_a=True)                      # utils.py:121
+    c = zeros((16,), torch.float64)
+    check(lib.apyib_diis_solve(1, ptr(B), m, m, C.c_void_p(0), ptr(c), 1, C.c_void_p(0), stream_ptr()))   # :122-135
+    cc = torch.view_as_complex(c.view(8, 2))[:m].contiguous()
+    t_new = to_host(contract_new("m,mo->o", cc, T))                       # utils.py:138
+    return (t_new if cplx else np.ascontiguousarray(t_new.real)), e_iter, t_iter

@@ -194,6 +194,25 @@ int apyib_axpby(int dtype, int64_t len, double alpha_re, double alpha_im, const 
                 double beta_re, double beta_im, void *d_y, void *stream);
 /* t_old = t.copy() (ci_wfn.py:80, 207, 304-305, 453-454)                                      */
 int apyib_copy(int dtype, void *d_dst, const void *d_src, int64_t len, void *stream);
+/* Batched row copy with scale: dst[s][0:len] = alpha * src[s][0:len], s < nb, row pitches in elements
+ * (the per-point `r = K.copy()` / `0.5 * <ab|ij>` set-ups of ci_wfn.py:83, 466 for a stack of points).     */
+int apyib_copy_rows(int dtype, void *d_dst, int64_t dst_stride, const void *d_src, int64_t src_stride,
+                    int64_t len, int nb, double alpha, const int32_t *d_active, void *stream);
+/* float64 -> complex128: the AO integrals of a magnetic-field point are real (hamiltonian.py:29-35; only V picks
+ * up the imaginary field term, :57-70); numpy upcasts them implicitly inside utils.py:274, here it is explicit. */
+int apyib_widen(void *d_dst_c128, const void *d_src_f64, int64_t len, void *stream);
+/* r_T2 = r_T2 + r_T2.swapaxes(0,1).swapaxes(2,3) (ci_wfn.py:92) for nb points in one launch (out of place).  */
+int apyib_symmetrize_ijab_batch(int dtype, const void *d_half, int64_t half_stride, void *d_out,
+                                int64_t out_stride, int64_t o, int64_t v, int nb, const int32_t *d_active,
+                                void *stream);
+/* Pair packing for the (i<->j, a<->b)-symmetric ladder term <ab|cd> t_ijcd (ci_wfn.py:87, 476):
+ * tp[s][p][:] = w_p t[s][i_p, j_p][:] over the o(o+1)/2 pairs i <= j (w = 1/2 on the diagonal), and the
+ * scatter-add h[s][i_p, j_p][:] += hp[s][p][:]; together with the symmetrisation above the contraction then
+ * runs over o(o+1)/2 instead of o^2 occupied pairs.  vv = elements per (i, j) block.                        */
+int apyib_pack_pairs(int dtype, const void *d_t, int64_t t_stride, void *d_tp, int64_t tp_stride, int64_t o,
+                     int64_t vv, int nb, const int32_t *d_active, void *stream);
+int apyib_unpack_pairs_add(int dtype, const void *d_hp, int64_t hp_stride, void *d_h, int64_t h_stride,
+                           int64_t o, int64_t vv, int nb, const int32_t *d_active, void *stream);
 
 /* ---- determinants of substituted occupied-overlap matrices ----------------------
  * out[r*ncol + c] = det( S[rows[r, :], cols[c, :]] ),  n x n, LU with partial

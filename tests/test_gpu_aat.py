@@ -275,3 +275,52 @@ def test_lemma_tables_match_lu_tables(nbf, no, nf):
                     want = to_host(_det_outer(S[s], no, T.L[rk], T.L[ck]))
                     scale = max(1e-300, np.abs(want).max())
                     assert np.abs(got[s] - want).max() < 1e-12 * max(scale, h ** (rk + ck)), (rk, ck, h)
+
+
+# ---- term-resolved literals of the reference's tests (test_011/012/013: I_00, I_0D, I_D0, I_DD per element) ----
+def _term_cases():
+    seen, out = set(), []
+    for c in LIT["cases"]:
+        if "I_00_ref" not in c["arrays"]:
+            continue
+        key = (c["parameters"]["method"], c["normalization"], c["h_R"], c["h_B"])
+        if key not in seen:
+            seen.add(key)
+            out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("c", _term_cases(), ids=lambda c: "%s-%s" % (c["parameters"]["method"], c["normalization"]))
+def test_h2_2_term_resolved_literals(c):
+    """The reference's tests build the AAT object themselves and loop over the per-term methods
+    (test_012_AAT_SO.py / test_013_AAT_parallel.py: compute_SO_I_00 / _0D / _D0 / _DD for every (alpha, beta));
+    the same calls through the drop-in classes must reproduce the hard-coded term-resolved tensors.  The spatial route
+    evaluates I_00 and I_DD only for MP2 (aats.py:744-750)."""
+    from apyib_b200.aats import AAT
+    from apyib_b200.energy import energy
+    from apyib_b200.fin_diff import finite_difference
+    from apyib_b200.hostchem import Hamiltonian, hf_wfn
+    p = _params(c)
+    norm, h_R, h_B = c["normalization"], c["h_R"], c["h_B"]
+    E_list, T_list, C, basis = energy(p)
+    wfn = hf_wfn(Hamiltonian(p))
+    lists = finite_difference(p, basis, C).compute_AAT(h_R, h_B)
+    A = AAT(p, wfn, C, basis, T_list, *lists, h_R, h_B)
+    natom = 4
+    want = {k: np.array(c["arrays"]["I_%s_ref" % k]) for k in ("00", "0D", "D0", "DD")}
+    so = p["method"].endswith("_SO")
+    got = {k: np.zeros((3 * natom, 3)) for k in want}
+    kfac = 1 / (4 * h_R * h_B)
+    for a in range(3 * natom):
+        for b in range(3):
+            if so:
+                for k in want:
+                    got[k][a, b] = getattr(A, "compute_SO_I_" + k)(a, b, norm)
+            else:
+                t = A._spatial_terms(a, b, norm)
+                for k in want:
+                    got[k][a, b] = kfac * np.imag(t[k])
+    for k in (want if so else ("00", "DD")):
+        assert np.abs(got[k] - want[k]).max() < 1e-7, (k, np.abs(got[k] - want[k]).max())      # the reference's own tolerance
+    tot = sum(got.values())
+    assert np.abs(tot - np.array(c["arrays"]["aat_ref"])).max() < 1e-7

@@ -232,3 +232,21 @@ def test_scf_with_device_jk_equals_host_scf(field):
     assert abs(res[0][0] - res[1][0]) < 1e-11 and np.abs(res[0][2] - res[1][2]).max() < 1e-10
     assert np.abs(res[0][1] - res[1][1]).max() < 1e-8         # |C|: eigenvector phases are arbitrary
     assert np.iscomplexobj(res[1][0]) == np.iscomplexobj(res[0][0])
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_solve_general_diis_drop_in(cplx):
+    """utils.solve_general_DIIS with the reference's calling convention (utils.py:104-140), incl. the > 7-vector
+    truncation and the iteration == 1 seeding, against the oracle"""
+    from apyib_b200.utils import solve_general_DIIS
+    rng = np.random.default_rng(77)
+    n = 500
+    rnd = lambda *s: rng.standard_normal(s) + (1j * rng.standard_normal(s) if cplx else 0)
+    e_g, t_g = rnd(n, 1), rnd(n, 1)
+    e_o, t_o = e_g.copy(), t_g.copy()
+    for it in range(1, 12):
+        r, t = (e_g[:, 0], t_g[:, 0]) if it == 1 else (rnd(n), rnd(n))
+        tn_g, e_g, t_g = solve_general_DIIS({}, r, t, e_g, t_g, it)
+        tn_o, e_o, t_o = orc.solve_general_DIIS(r, t, e_o, t_o, it)
+        assert e_g.shape == e_o.shape and e_g.shape[1] <= 8 and np.array_equal(e_g, e_o) and np.array_equal(t_g, t_o)
+        assert tn_g.dtype == tn_o.dtype and np.abs(tn_g - tn_o).max() < 1e-9 * max(1.0, np.abs(tn_o).max())

@@ -230,3 +230,33 @@ def test_sorted_lists_have_the_group_structure_of_the_prefix_shared_lu(no, nf, n
         bad = srt.copy()
         bad[0, 0], bad[0, 1] = bad[0, 1], bad[0, 0]
         assert prefix_groups(bad, no, 2) is None or no - 2 < 2
+
+
+def test_drop_in_signatures():
+    """Boundary: every class / method / function of the reference's hot-path surface exists in the
+    product under the same name with the same positional parameters and defaults (extra trailing keyword
+    parameters with defaults are allowed).  The snapshot is extracted from the unmodified reference with `ast`
+    (tests/golden/make_signatures.py)."""
+    import inspect
+    import json
+    import importlib
+    snap = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_signatures.json")))
+    assert len(snap) >= 40
+    for name, ref in snap.items():
+        parts = name.split(".")
+        obj = importlib.import_module("apyib_b200." + parts[0])
+        for part in parts[1:]:
+            assert hasattr(obj, part), "missing " + name
+            obj = getattr(obj, part)
+        sig = inspect.signature(obj)
+        params = [q for q in sig.parameters.values()]
+        names = [q.name for q in params]
+        nref = len(ref["args"])
+        if name == "utils.compute_mo_overlap" or name == "utils.compute_phase":
+            nref_cmp = nref                      # (+ optional ao_overlap=: Psi4's mixed-basis overlap is a host input)
+        assert names[:nref] == ref["args"], (name, names, ref["args"])
+        ndef = len(ref["defaults"])
+        got_def = [q.default for q in params[nref - ndef:nref]] if ndef else []
+        assert got_def == ref["defaults"], (name, got_def, ref["defaults"])
+        for q in params[nref:]:
+            assert q.default is not inspect.Parameter.empty or q.kind in (q.VAR_POSITIONAL, q.VAR_KEYWORD), (name, q.name)
