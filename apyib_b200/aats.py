@@ -592,9 +592,10 @@ class AAT(object):
         wy = cn("qklcd,sld->sqkc", Y2, B)                                # sum_ld y2[k,l,c,d] S_ld
         ux = cn("xijab,sjb->sxia", X2, A)                                # sum_jb x2[i,j,a,b] jb_S
         uxp = cn("xijab,sia->sxjb", X2, A)                               # sum_ia x2[i,j,a,b] ia_S
-        T1 = cn("siakc,qklcd->sqiald", G, Y2)
-        Z = cn("sqiald,sjbld->sqiajb", T1, G)
-        dd["c6"] = cn("xijab,sqiajb->sxq", X2, Z)
+        if not (factorized and P):
+            T1 = cn("siakc,qklcd->sqiald", G, Y2)
+            Z = cn("sqiald,sjbld->sqiajb", T1, G)
+            dd["c6"] = cn("xijab,sqiajb->sxq", X2, Z)                    # sum x2 y2 ia_S_kc jb_S_ld   (aats.py:737)
         if P:
             D20 = outer(2, 0).reshape(nS, P)                             # iajb_S  (restricted)
             D02 = outer(0, 2).reshape(nS, P)                             # S_kcld  (restricted)
@@ -609,6 +610,7 @@ class AAT(object):
                 # doubles x doubles, doubles x singles and singles x doubles tables in closed form
                 f = self._dd_factorized(prep, nS, ns, no, nf, X2, Y2)
                 dd["c1f"] = f["dd"]
+                dd["c6f"] = f["c6"]
                 half = lambda a, b, rest: _axpby(0.5, cn("sx,sq->sxq", a, b), 1.0, rest)
                 # sum_r Xh[r] D21[r,c] y[c] / det(S_oo) = alpha (Q.y)/2 + M.y
                 dd["c3f"] = half(f["alpha"], cn("skc,sqkc->sq", f["Q"], wy), cn("sxkc,sqkc->sxq", f["M"], wy))
@@ -656,6 +658,8 @@ class AAT(object):
         for k in ("c3", "c4", "ds1", "sd1"):          # closed forms are per det(S_oo), like c1f
             if k + "f" in h:
                 h[k] = dSh_all.reshape(nS, 1, 1) * h[k + "f"]
+        if "c6f" in h:                                # product of two singly-singly substituted determinants
+            h["c6"] = (dSh_all ** 2).reshape(nS, 1, 1) * h["c6f"]
         res = []
         for s in range(nS):
             dSh = complex(dSh_all[s])
@@ -690,7 +694,7 @@ class AAT(object):
         i.e. O(o^2 v^2 (o+v)) DMMA contractions instead of (C(o,2) C(v,2))^2 determinants.
         Returns the intermediates and "dd" [nS, nx, ny]: the unrestricted sum (= 16 x the restricted
         i<j,a<b,k<l,c<d sum) over det T."""
-        from .utils import gather4
+        from .utils import gather4, gather4_stack
         nv = ns - no
         o = no - nf
         cn = contract_new
@@ -709,6 +713,14 @@ class AAT(object):
                 gather4(t, 0, t.shape, [0, 1, 2, 3], [0, 0, 0, 0], 2.0, [1, 0, 2, 3], [0, 0, 0, 0], -2.0, out=out[q])
             return out
 
+        def antisym_stack(Z6):      # the same completion for a [s, x, k, l, c, d] stack: two launches
+            flat = Z6.reshape((-1,) + tuple(Z6.shape[2:]))
+            n = flat.shape[0]
+            sh = tuple(flat.shape[1:])
+            t = gather4_stack([flat[r] for r in range(n)], 0, sh, [0, 1, 2, 3], [0, 0, 0, 0], 1.0, [0, 1, 3, 2], [0, 0, 0, 0], -1.0)
+            t = gather4_stack([t[r] for r in range(n)], 0, sh, [0, 1, 2, 3], [0, 0, 0, 0], 2.0, [1, 0, 2, 3], [0, 0, 0, 0], -2.0)
+            return t.reshape(Z6.shape)
+
         Xf, Yf = antisym(X2), antisym(Y2)
         U = cn("xijab,sai->sxjb", Xf, P)
         alpha = cn("sxjb,sbj->sx", U, P)
@@ -716,18 +728,34 @@ class AAT(object):
         beta = cn("sqkc,skc->sq", W, Q)
         M = cn("sxkb,sbc->sxkc", cn("skj,sxjb->sxkb", Ai, U), R)
         mixed = cn("sxkc,sqkc->sxq", M, W)
-        Z = cn("ski,xijab->sxkjab", Ai, Xf)
-        Z = cn("slj,sxkjab->sxklab", Ai, Z)
-        Z = cn("sac,sxklab->sxklcb", R, Z)
-        Z = cn("sbd,sxklcb->sxklcd", R, Z)
-        gamma = cn("sxklcd,qklcd->sxq", Z, Yf)
+        # Z = A A R R x2 is linear in the amplitudes and commutes with the antisymmetric completion
+        # (Z[Xf] = antisym(Z[x2])), so the four o^2 v^2 (o + v) transforms are done ONCE, on the plain amplitudes,
+        # and serve both the doubles x doubles table (with Xf, Yf) and the singly x singly product term below
+        Zx = cn("ski,xijab->sxkjab", Ai, X2)
+        Zx = cn("slj,sxkjab->sxklab", Ai, Zx)
+        Zx = cn("sac,sxklab->sxklcb", R, Zx)
+        Zx = cn("sbd,sxklcb->sxklcd", R, Zx)
+        gamma = cn("sxklcd,qklcd->sxq", antisym_stack(Zx), Yf)
         ab = cn("sx,sq->sxq", alpha, beta)
         _axpby(4.0, mixed, 1.0, ab)
         _axpby(1.0, gamma, 1.0, ab)
         _axpby(4.0, ab, 0.0, mixed)          # mixed <- 4 (alpha beta + 4 mixed + gamma)
+        # sum x2[ijab] y2[klcd] ia_S_kc jb_S_ld / det(S_oo)^2 (the 8 x2.y2.M_iakc.M_jbld term of aats.py:737) with
+        # ia_S_kc = det(S_oo) (P_ai Q_kc + R_ac A_ki):  (U1.P)(W1.Q) + (A U1 R).W1 + (A U2 R).W2 + Z[x2].y2,
+        # U1_jb = sum_ia x2 P_ai, U2_ia = sum_jb x2 P_bj, W1_ld = sum_kc y2 Q_kc, W2_kc = sum_ld y2 Q_ld
+        U1 = cn("xijab,sai->sxjb", X2, P)
+        U2 = cn("xijab,sbj->sxia", X2, P)
+        W1 = cn("qklcd,skc->sqld", Y2, Q)
+        W2 = cn("qklcd,sld->sqkc", Y2, Q)
+        c6 = cn("sx,sq->sxq", cn("sxjb,sbj->sx", U1, P), cn("sqld,sld->sq", W1, Q))
+        M1 = cn("sxlb,sbd->sxld", cn("slj,sxjb->sxlb", Ai, U1), R)
+        M2 = cn("sxka,sac->sxkc", cn("ski,sxia->sxka", Ai, U2), R)
+        _axpby(1.0, cn("sxld,sqld->sxq", M1, W1), 1.0, c6)
+        _axpby(1.0, cn("sxkc,sqkc->sxq", M2, W2), 1.0, c6)
+        _axpby(1.0, cn("sxklcd,qklcd->sxq", Zx, Y2), 1.0, c6)
         # alpha, beta, M, W also give the doubles x singles / singles x doubles tables (see _blocks):
         #   sum_ijab Xf det3(ijab; kc) = -2 alpha Q_kc - 4 M_kc,   sum_klcd Yf det3(ia; klcd) = 2 beta P_ai + 4 N_ia
-        return dict(dd=mixed, alpha=alpha, beta=beta, M=M, W=W, Ai=Ai, P=P, Q=Q, R=R)
+        return dict(dd=mixed, c6=c6, alpha=alpha, beta=beta, M=M, W=W, Ai=Ai, P=P, Q=Q, R=R)
 
     def _spatial_terms(self, alpha, beta, normalization):
         m = self.parameters["method"]

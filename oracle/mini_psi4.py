@@ -15,6 +15,11 @@ import numpy as np
 import hostinputs as hc
 
 _options = {"basis": "STO-3G", "freeze_core": False}
+_MASS = {"H": 1.00782503223, "HE": 4.00260325413}
+# CODATA 2014 (qcelemental's default context, which psi4.qcel.constants exposes) -- vcd.py:37-42
+_CODATA2014 = {"speed of light in vacuum": 299792458.0, "electron mass": 9.10938356e-31,
+               "Avogadro constant": 6.022140857e+23, "atomic unit of charge": 1.6021766208e-19,
+               "electric constant": 8.854187817e-12, "Planck constant": 6.62607004e-34}
 
 
 class _Mat:
@@ -50,6 +55,15 @@ class _Molecule:
 
     def nuclear_repulsion_energy(self, field=(0.0, 0.0, 0.0)):
         return self._m.nuclear_repulsion_energy(field)
+
+    def mass(self, i):                                   # most abundant isotope, as psi4 / qcelemental report it
+        return _MASS[self._m.symbols[i].upper()]
+
+    def to_arrays(self):                                 # (geom [bohr], mass, elem, Z, uniq) -- vcd.py:107
+        Z = np.array([self._m.true_atomic_number(i) for i in range(self._m.natom())], dtype=float)
+        mass = np.array([self.mass(i) for i in range(self._m.natom())])
+        elem = np.array(self._m.symbols)
+        return self._m.geometry(), mass, elem, Z, elem
 
     def fix_orientation(self, *_):
         pass
@@ -133,4 +147,7 @@ def as_module():
     psi4.geometry = lambda s: _Molecule(hc.Molecule.from_string(s))
     psi4.set_output_file = lambda *a, **k: None
     psi4.set_memory = lambda *a, **k: None
+    qcel = types.ModuleType("psi4.qcel")
+    qcel.constants = types.SimpleNamespace(get=lambda name: _CODATA2014[name])
+    psi4.qcel = qcel
     return psi4

@@ -48,7 +48,7 @@ def load(with_mini_psi4=False):
     ns = types.SimpleNamespace()
     names = ["utils", "mp2_wfn", "ci_wfn", "aats"]
     if with_mini_psi4:
-        names += ["hamiltonian", "hf_wfn", "energy", "fin_diff", "parallel"]
+        names += ["hamiltonian", "hf_wfn", "energy", "fin_diff", "parallel", "vcd"]
     for m in names:
         setattr(ns, m, importlib.import_module("apyib." + m))
     return ns

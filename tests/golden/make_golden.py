@@ -244,7 +244,33 @@ def fd_drivers(lit):
     json.dump(out, open(os.path.join(HERE, "reference_fd_drivers.json"), "w"), indent=1)
 
 
+def vcd_handoff(lit):
+    """BASELINE configs[2] end to end on the reference's (H2)_2 molecule (STO-3G, MP2 and CISD): the UNMODIFIED
+    reference's compute_Hessian + compute_APT + compute_parallel_aats feed its own vcd.compute_vcd_from_input
+    (vcd.py:32-136) -> frequencies, IR intensities, VCD rotational strengths.  Numbers only."""
+    ns = ref_harness.load(with_mini_psi4=True)
+    fd = json.load(open(os.path.join(HERE, "reference_fd_drivers.json")))
+    out = {"molecule": "(H2)_2", "basis": "STO-3G", "cases": []}
+    for method, h_aat in (("MP2", 1e-4), ("CISD", 1e-6)):
+        c = [c for c in fd["cases"] if c["method"] == method][0]
+        mk = lambda: {"geom": lit["geom"], "basis": "STO-3G", "method": method, "freeze_core": False, "DIIS": True,
+                      "e_convergence": 1e-13, "d_convergence": 1e-13, "max_iterations": 120,
+                      "F_el": [0.0, 0.0, 0.0], "F_mag": [0.0, 0.0, 0.0]}
+        hess, apt = np.array(c["Hessian"]), np.array(c["APT"])
+        aat = np.asarray(quiet(ns.parallel.compute_parallel_aats, mk(), h_aat, h_aat, "full", 2))
+        with np.errstate(invalid="ignore"):
+            w, D, R = quiet(ns.vcd.vcd(mk()).compute_vcd_from_input, hess, apt, aat)
+        out["cases"].append({"method": method, "h_R": c["h_R"], "h_F": c["h_F"], "h_aat": h_aat, "AAT": aat.tolist(),
+                             "frequencies_cm1": [None if not np.isfinite(x) else float(x) for x in w],
+                             "ir_intensities_kmmol": np.asarray(D).tolist(),
+                             "rotational_strengths": np.asarray(R).tolist()})
+    json.dump(out, open(os.path.join(HERE, "reference_vcd.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if "--only-vcd" in sys.argv:
+        vcd_handoff(json.load(open(os.path.join(HERE, "reference_literals.json"))))
+        sys.exit(0)
     if "--only-fd-drivers" in sys.argv:
         fd_drivers(json.load(open(os.path.join(HERE, "reference_literals.json"))))
         sys.exit(0)
@@ -259,4 +285,5 @@ if __name__ == "__main__":
     linear_response(ns)
     linear_response_cid(ns)
     fd_drivers(lit)
+    vcd_handoff(lit)
     print("wrote", sorted(os.listdir(HERE)))

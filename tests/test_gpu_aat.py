@@ -324,3 +324,33 @@ def test_h2_2_term_resolved_literals(c):
         assert np.abs(got[k] - want[k]).max() < 1e-7, (k, np.abs(got[k] - want[k]).max())      # the reference's own tolerance
     tot = sum(got.values())
     assert np.abs(tot - np.array(c["arrays"]["aat_ref"])).max() < 1e-7
+
+
+@pytest.mark.parametrize("method", ["MP2", "CISD"])
+def test_vcd_handoff_end_to_end(method):
+    """BASELINE configs[2] end to end on the reference's (H2)_2 molecule: Hessian, APT and AAT tensor from the
+    device drivers feed compute_vcd_from_input unchanged and reproduce the spectrum the UNMODIFIED reference chain
+    (compute_Hessian + compute_APT + compute_parallel_aats + vcd.py) produced in the build container; tolerances are
+    those of the reference's own VCD test (test_023_VCD.py: 0.1 cm^-1 / 0.1 units), tightened."""
+    from apyib_b200.energy import energy
+    from apyib_b200.fin_diff import finite_difference
+    from apyib_b200.parallel import compute_parallel_aats
+    from apyib_b200.vcd import vcd
+    ref = json.load(open(os.path.join(HERE, "golden", "reference_vcd.json")))
+    c = [c for c in ref["cases"] if c["method"] == method][0]
+    mk = lambda: {"geom": LIT["geom"], "basis": "STO-3G", "method": method, "freeze_core": False, "DIIS": True,
+                  "e_convergence": 1e-13, "d_convergence": 1e-13, "max_iterations": 120,
+                  "F_el": [0.0, 0.0, 0.0], "F_mag": [0.0, 0.0, 0.0]}
+    p = mk()
+    E_list, T_list, C, basis = energy(p)
+    fd = finite_difference(p, basis, C)
+    hess = fd.compute_Hessian(c["h_R"])
+    apt = fd.compute_APT(c["h_R"], c["h_F"])
+    aat = compute_parallel_aats(mk(), c["h_aat"], c["h_aat"], "full")
+    assert hess.shape == (12, 12) and apt.shape == (12, 3) and aat.shape == (12, 3)
+    assert np.abs(aat - np.array(c["AAT"])).max() < 1e-7
+    w, D, R = vcd(mk()).compute_vcd_from_input(hess, apt, aat, print_level=0)
+    wr = np.array([np.nan if x is None else x for x in c["frequencies_cm1"]])
+    assert np.nanmax(np.abs(w - wr)) < 0.1
+    assert np.abs(D - np.array(c["ir_intensities_kmmol"])).max() < 1e-3
+    assert np.abs(R - np.array(c["rotational_strengths"])).max() < 1e-2

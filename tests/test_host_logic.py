@@ -260,3 +260,25 @@ def test_drop_in_signatures():
         assert got_def == ref["defaults"], (name, got_def, ref["defaults"])
         for q in params[nref:]:
             assert q.default is not inspect.Parameter.empty or q.kind in (q.VAR_POSITIONAL, q.VAR_KEYWORD), (name, q.name)
+
+
+def test_vcd_drop_in_matches_unmodified_reference():
+    """apyib_b200.vcd.vcd.compute_vcd_from_input (host post-processing, BASELINE configs[2] hand-off) on the
+    reference's own (H2)_2 Hessian / APT / AAT reproduces the frequencies, IR intensities and VCD rotational
+    strengths the UNMODIFIED reference's vcd.py:32-136 computed from them (tests/golden/reference_vcd.json)."""
+    import json
+    from apyib_b200.vcd import vcd
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    lit = json.load(open(os.path.join(G, "reference_literals.json")))
+    fd = json.load(open(os.path.join(G, "reference_fd_drivers.json")))
+    ref = json.load(open(os.path.join(G, "reference_vcd.json")))
+    assert len(ref["cases"]) == 2
+    for c in ref["cases"]:
+        f = [x for x in fd["cases"] if x["method"] == c["method"]][0]
+        w, D, R = vcd({"geom": lit["geom"]}).compute_vcd_from_input(np.array(f["Hessian"]), np.array(f["APT"]),
+                                                                    np.array(c["AAT"]), print_level=0)
+        wr = np.array([np.nan if x is None else x for x in c["frequencies_cm1"]])
+        assert w.shape == (6,) and np.array_equal(np.isnan(w), np.isnan(wr))
+        assert np.nanmax(np.abs(w - wr)) < 1e-8
+        assert np.abs(D - np.array(c["ir_intensities_kmmol"])).max() < 1e-10
+        assert np.abs(R - np.array(c["rotational_strengths"])).max() < 1e-10
