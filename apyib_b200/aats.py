@@ -185,7 +185,7 @@ def _vdot(x, y, conj_x=True):
 # CUDA-graph replay of the device part of AAT._blocks (config.AAT_USE_GRAPH)
 # -------------------------------------------------------------------------------------------------
 _block_graphs = {}          # stack shape -> _BlockGraph | "warm" (seen once, eager) | None (not capturable)
-GRAPH_MAX_BYTES = 256 << 20
+GRAPH_MAX_BYTES = 6 << 30
 GRAPH_MAX_LIVE = 24
 
 

@@ -27,7 +27,7 @@ import torch
 
 from . import config
 from ._lib import lib, check
-from .contraction import contract
+from .contraction import contract, SCRATCH_OWNER
 from .device import (to_device, to_host, empty, zeros, ptr, stream_ptr, Graph)
 from .utils import (get_slices, compute_F_MO_dev, compute_ERI_MO_dev, spin_block_2_dev, gather4, gather4_stack,
                     mo_integrals_many)
@@ -62,8 +62,9 @@ def w_block(E, labels, out_labels, space, bounds, spin=0, c1=1.0, c2=0.0, out=No
 class _Point:
     """MO integrals of one finite-difference point on the device (what ci_wfn.__init__ builds)."""
 
-    def __init__(self, F, ERI, eps_o, eps_v, E_SCF=0.0, E_nuc=0.0):
+    def __init__(self, F, ERI, eps_o, eps_v, E_SCF=0.0, E_nuc=0.0, eps_dev=None):
         self.F, self.ERI, self.eps_o, self.eps_v, self.E_SCF, self.E_nuc = F, ERI, eps_o, eps_v, E_SCF, E_nuc
+        self.eps_dev = eps_dev          # (occupied, virtual) orbital energies already on the device, or None
 
 
 class _Engine:
@@ -77,8 +78,9 @@ class _Engine:
         self.len = self.n1 + self.n2
         self.has_singles, self.so, self.symmetrize = has_singles, int(spin_orbital), symmetrize
         self.code = 1 if dtype == torch.complex128 else 0
-        self.eps_o = to_device(np.ascontiguousarray(np.real(eps_o), dtype=np.float64))       # [nb, o_spatial]
-        self.eps_v = to_device(np.ascontiguousarray(np.real(eps_v), dtype=np.float64))
+        # [nb, o_spatial] / [nb, v_spatial] float64; device tensors when the points carry their uploaded energies
+        up = lambda x: x if isinstance(x, torch.Tensor) else to_device(np.ascontiguousarray(np.real(x), dtype=np.float64))
+        self.eps_o, self.eps_v = up(eps_o), up(eps_v)
         z = lambda *s: zeros(s, dtype)
         L = self.len
         self.t, self.r, self.t_old, self.w, self.r0 = z(nb, L), z(nb, L), z(nb, L), z(nb, L), z(nb, L)
@@ -252,6 +254,7 @@ def _drive(jobs):
     while live:
         for k in list(live):
             gen, st = jobs[k]
+            SCRATCH_OWNER[0] = None if st is None else k      # split-K scratch of this batch (contraction._work_buffer)
             try:
                 if st is None:
                     next(gen)
@@ -261,6 +264,8 @@ def _drive(jobs):
             except StopIteration as done:
                 results[k] = done.value
                 live.remove(k)
+            finally:
+                SCRATCH_OWNER[0] = None
     return results
 
 
@@ -284,8 +289,12 @@ def _stack(items, fn, shape, dtype):
 
 def _make_engine(parameters, points, has_singles, so, symmetrize=False):
     O, V, bd = _sizes(points, so)
-    eps_o = np.stack([np.asarray(pt.eps_o) for pt in points])
-    eps_v = np.stack([np.asarray(pt.eps_v) for pt in points])
+    if all(pt.eps_dev is not None for pt in points):          # no host->device copy on the solve path
+        eps_o = torch.stack([pt.eps_dev[0] for pt in points])
+        eps_v = torch.stack([pt.eps_dev[1] for pt in points])
+    else:
+        eps_o = np.stack([np.asarray(pt.eps_o) for pt in points])
+        eps_v = np.stack([np.asarray(pt.eps_v) for pt in points])
     eng = _Engine(parameters, points[0].ERI.dtype, len(points), O, V, has_singles, so, eps_o, eps_v, symmetrize)
     return eng, O, V, bd
 
@@ -749,7 +758,11 @@ class ci_wfn(object):
 
     def point(self):
         """Device-side integrals of this wavefunction, for solve_batch."""
-        return _Point(self._F_dev, self._ERI_dev, self.eps_o, self.eps_v, self.wfn.E_SCF, self.H.E_nuc)
+        from .utils import wfn_small_on_device
+        eps = wfn_small_on_device(self.wfn, self._ERI_dev.dtype == torch.complex128)[1]
+        o, v = self.C_list[1], self.C_list[2]
+        return _Point(self._F_dev, self._ERI_dev, self.eps_o, self.eps_v, self.wfn.E_SCF, self.H.E_nuc,
+                      eps_dev=(eps[o.start:o.stop], eps[v.start:v.stop]))
 
     def _solve(self, method, print_level):
         res, its = solve_batch(method, self.parameters, [self.point()], print_level)

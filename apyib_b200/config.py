@@ -46,12 +46,14 @@ AAT_ALGORITHM = "lu"
 # flops at o = 12.
 PACKED_LADDER = _os.environ.get("APYIB_B200_PACKED_LADDER", "1") == "1"
 
-# Batched solves (ci_wfn.solve_many): run the groups of finite-difference points (float64 / complex128 points, and
-# chunks of at most SOLVE_CHUNK points of one dtype when a point's AO integrals exceed SOLVE_CHUNK_MIN_BYTES)
-# concurrently, one CUDA stream per group, driven from one host thread.  False: one group after the other on the
-# caller's stream (what bench.py uses for its instrumented step, so that per-kernel events are not inflated by a
-# concurrent stream).  Chunks let the first points start iterating while the later ones are still uploading.
-SOLVE_CONCURRENT = True
+# Batched solves (ci_wfn.solve_many): the finite-difference points are grouped by dtype (float64 / complex128) and,
+# when a point's AO integrals exceed SOLVE_CHUNK_MIN_BYTES, split into chunks of at most SOLVE_CHUNK points in upload
+# order; the groups are solved one after the other on the caller's stream while the copy stream keeps uploading the
+# AO integrals of the later groups (complex points first, so their iterations hide the upload of the real points).
+# SOLVE_CONCURRENT = True runs the groups on one CUDA stream each, driven from one host thread.  Measured on a B200
+# (round 2): no gain at N = 1 at the (S)-methyloxirane/cc-pVDZ shape (the device is saturated: 1.06 s vs 1.02 s), and
+# an unexplained sporadic 1e-6 deviation in the amplitudes of the first point of a group -- OFF.
+SOLVE_CONCURRENT = _os.environ.get("APYIB_B200_SOLVE_CONCURRENT", "0") == "1"
 SOLVE_CHUNK = 32
 SOLVE_CHUNK_MIN_BYTES = 64 << 20
 

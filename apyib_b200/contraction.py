@@ -104,16 +104,36 @@ def _plan(spec, A, B, out):
         ksplit = 1
         if tiles < 2 * 148 and K >= 2048:
             ksplit = int(min(max(1, (3 * 148) // tiles), (K + 511) // 512, 65535 // batch[0]))
-    work = torch.empty(batch[0] * ksplit * M * N, dtype=A.dtype, device=A.device) if ksplit > 1 else None
+    work = batch[0] * ksplit * M * N if ksplit > 1 else 0          # elements of split-K scratch (per-stream buffer)
     p = (M, N, K, ptrs, a_kfast, b_kfast, dev, batch, ksplit, work, tma)
     _table_cache[key] = p
     return p
+
+
+_splitk_scratch = {}
+SCRATCH_OWNER = [None]        # set by ci_wfn._drive to the batch whose launches are being enqueued (None: caller's stream)
+
+
+def _work_buffer(dtype, numel):
+    """Split-K partial-sum scratch.  Launches of one solve batch are ordered on the batch's stream, so they share one
+    buffer; batches that run concurrently on different streams must not.  The buffer is therefore owned by the BATCH
+    (SCRATCH_OWNER), not looked up by the current stream: an iteration is captured into a CUDA graph on a separate
+    capture stream and replayed on the batch's stream, and the address baked into the graph must be the batch's own.
+    Buffers are never freed: captured graphs keep their addresses."""
+    if numel == 0:
+        return None
+    key = (torch.cuda.current_device(), SCRATCH_OWNER[0], dtype)
+    bufs = _splitk_scratch.setdefault(key, [])
+    if not bufs or bufs[-1].numel() < numel:
+        bufs.append(torch.empty(max(numel, 1 << 16), dtype=dtype, device=device()))
+    return bufs[-1]
 
 
 def contract(spec, A, B, out, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
     """out = alpha * einsum(spec, op(A), op(B)) + beta * out, on the current stream."""
     assert A.dtype == B.dtype == out.dtype, "mixed dtypes: %s %s %s" % (A.dtype, B.dtype, out.dtype)
     M, N, K, ptrs, a_kfast, b_kfast, _keep, batch, ksplit, work, tma = _plan(spec, A, B, out)
+    work = _work_buffer(A.dtype, work)
     alpha, beta = complex(alpha), complex(beta)
     if tma is not None and ksplit == 1 and config.USE_TMA:
         with config.timed("contract_tma[%s %dx%dx%d b%d]" % ("c128" if A.dtype == torch.complex128 else "f64", M, N, K, batch[0])):

@@ -57,8 +57,10 @@ def to_device(x, dtype=None):
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
     if not t.is_cuda:
-        COUNTERS["h2d_bytes"] += t.numel() * t.element_size()
-        return t.to(device(), non_blocking=t.numel() >= _PIN_MIN // 8 and t.is_pinned()).contiguous()
+        nbytes = t.numel() * t.element_size()
+        COUNTERS["h2d_bytes"] += nbytes
+        if nbytes >= _PIN_MIN and t.is_pinned():
+            return t.to(device(), non_blocking=True).contiguous()
     return t.to(device(), non_blocking=False).contiguous()
 
 
@@ -103,6 +105,17 @@ def pin_host_inputs(wfns):
 
 
 _copy_streams = {}
+_capture_streams = {}
+
+
+def capture_stream():
+    """ONE dedicated stream per device for recording CUDA graphs.  torch.cuda.Stream() hands out streams from a small
+    round-robin pool, so a fresh object per capture would sooner or later alias a stream that carries live work."""
+    d = torch.cuda.current_device()
+    if d not in _capture_streams:
+        _capture_streams[d] = torch.cuda.Stream(device=d)
+    return _capture_streams[d]
+
 
 
 def copy_stream():
@@ -167,7 +180,7 @@ class Graph:
         cannot be captured, so recording happens on a private side stream; `fn` must only
         launch libapyib_b200 kernels on the *current* stream and must not allocate."""
         n0 = _lib.LAUNCHES[0]
-        side = torch.cuda.Stream()
+        side = capture_stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             check(lib.apyib_graph_begin(C.c_void_p(side.cuda_stream)))

@@ -49,6 +49,8 @@ def correlated_many(parameters, wfns, print_level=0):
     if m in ("CID", "CISD", "CID_SO", "CISD_SO"):
         res = solve_many(m, parameters, wfns, print_level)
         return [(r[0], [1, r[1], r[2]] if len(r) == 3 else [1, 0, r[1]]) for r in res]
+    from .utils import ao_prefetch
+    ao_prefetch(wfns)            # queue every point's AO-integral upload on the copy stream; point k+1 uploads while k transforms
     return [_correlated(parameters, w, print_level) for w in wfns]
 
 

@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import config
 from ._lib import lib, check
 from .device import to_device, to_host, empty, zeros, dtype_code, ptr, stream_ptr, reduce_scratch
 from .utils import get_slices, compute_ERI_MO_dev
@@ -47,7 +48,7 @@ class mp2_wfn(object):
             E_MP2 = np.complex128(complex(e[0], e[1]))
         else:
             E_MP2 = np.float64(e[0])
-        return E_MP2, to_host(t2)
+        return E_MP2, (t2 if config.RETURN_DEVICE else to_host(t2))      # device-resident mode: bench `value` leg
 
     def solve_MP2(self):
         """Reference: mp2_wfn.py:42-59.  Returns (E_MP2, t2[o,o,v,v])."""

@@ -57,18 +57,42 @@ def ao_prefetch(wfns):
     of later points overlap the kernels of earlier ones.  Arrays are uploaded in their host dtype (the AO ERIs of a
     magnetic-field point are real: half the bytes of a complex128 copy)."""
     cs = copy_stream()
-    for w in wfns:
-        cache = _ao_cache(w.H)
-        if "raw" in cache or "r" in cache or "c" in cache:
-            continue
-        with torch.cuda.stream(cs):
-            h = to_device(np.asarray(w.H.T) + np.asarray(w.H.V))
+    todo = [w for w in wfns if not any(k in _ao_cache(w.H) for k in ("raw", "r", "c"))]
+    with torch.cuda.stream(cs):
+        # ALL small per-point inputs first (h = T + V, MO coefficients, orbital energies): a host->device copy
+        # queues behind every copy submitted before it (one DMA engine per direction), so a small synchronous
+        # upload issued later -- while 30 GB of AO integrals are in flight -- would stall its stream for the
+        # whole upload window (measured: +0.45 s on the first batch at the methyloxirane shape)
+        small = [(to_device(np.asarray(w.H.T) + np.asarray(w.H.V)), to_device(np.asarray(w.C)),
+                  to_device(np.ascontiguousarray(np.real(np.asarray(w.eps)), dtype=np.float64))) for w in todo]
+        for w, (h, Cd, eps) in zip(todo, small):
+            cache = _ao_cache(w.H)
             G = cache.get("eri_r")                      # uploaded by the device-assisted SCF already (hostchem)
             if G is None:
                 G = to_device(np.asarray(w.H.ERI))
             ev = torch.cuda.Event()
             ev.record(cs)
-        cache["raw"] = (h, G, ev)
+            cache["raw"] = (h, G, ev)
+            cache["C"], cache["eps"], cache["C_host"] = Cd, eps, w.C
+
+
+def wfn_small_on_device(wfn, want_complex):
+    """(MO coefficients in the solver's dtype, orbital energies float64) of a point on the device: from the upload
+    cache when ao_prefetch / ao_on_device has seen the point (and wfn.C has not been replaced since), else uploaded now."""
+    cache = _ao_cache(wfn.H)
+    dt = torch.complex128 if want_complex else torch.float64
+    Cd = cache.get("C") if cache.get("C_host") is wfn.C else None
+    if Cd is None:
+        Cd = to_device(np.asarray(wfn.C))
+        eps = to_device(np.ascontiguousarray(np.real(np.asarray(wfn.eps)), dtype=np.float64))
+        cache["C"], cache["eps"], cache["C_host"] = Cd, eps, wfn.C
+    if Cd.dtype != dt:
+        if dt == torch.float64:
+            raise TypeError("complex MO coefficients need the complex path")
+        Cd = _widen(Cd)
+    for x in (Cd, cache["eps"]):
+        x.record_stream(torch.cuda.current_stream())
+    return Cd, cache["eps"]
 
 
 def _widen(x):
@@ -130,33 +154,42 @@ class LazyScalar:
         return complex(h[0], h[1]) if self.cplx else float(h[0])
 
 
+def _axpby_new(alpha, x, beta, y):
+    """alpha * x + beta * y as a new tensor (apyib_axpby on a copy of y)"""
+    out = y.clone()
+    a, b = complex(alpha), complex(beta)
+    check(lib.apyib_axpby(dtype_code(out), out.numel(), a.real, a.imag, ptr(x.contiguous()), 0, b.real, b.imag, ptr(out), stream_ptr()))
+    return out
+
+
 def compute_F_MO_dev(parameters, wfn, C_list, lazy=False):
     f, o, v, t = C_list
     cplx = _is_complex(wfn)
     dt = torch.complex128 if cplx else torch.float64
     h, G = ao_on_device(wfn, cplx)
-    Cd = to_device(np.asarray(wfn.C), dt)
+    Cd = wfn_small_on_device(wfn, cplx)[0]
     Gx = G.swapaxes(1, 2)                                   # strided view, no copy
 
-    def fock_like(h_in, Cocc):
-        D = contract_new("mp,np->mn", Cocc, Cocc, conj_b=True)
-        F = h_in.clone()
-        contract("ls,mnls->mn", D, G, F, alpha=2.0, beta=1.0)       # + 2 J
-        contract("ls,mnls->mn", D, Gx, F, alpha=-1.0, beta=1.0)     # - K
-        return D, F
-
+    # (2J - K)[D] for the frozen-core and the active occupied density in ONE pass each over the nbf^4 integrals
+    # (utils.py:238-249 contracts them one after the other: four passes)
+    fc = parameters["freeze_core"] == True  # noqa: E712 (reference semantics, utils.py:238)
+    dens = [contract_new("mp,np->mn", Cd[:, sl], Cd[:, sl], conj_b=True) for sl in ((f, o) if fc else (o,))]
+    D = torch.stack(dens)                                           # [x, l, s]
+    JK = zeros((len(dens),) + tuple(h.shape), dt)
+    contract("xls,mnls->xmn", D, G, JK, alpha=2.0, beta=0.0)        # + 2 J
+    contract("xls,mnls->xmn", D, Gx, JK, alpha=-1.0, beta=1.0)      # - K
     E_fc = 0
-    if parameters["freeze_core"] == True:  # noqa: E712 (reference semantics, utils.py:238)
-        D_fc, h_fc = fock_like(h, Cd[:, f])
-        hs = h + h_fc
+    if fc:
+        h_fc = _axpby_new(1.0, JK[0], 1.0, h)                       # h + (2J - K)[D_fc]
+        hs = _axpby_new(1.0, h_fc, 1.0, h)
         e = zeros((2,), torch.float64)
-        check(lib.apyib_dots(dtype_code(hs), ptr(D_fc.transpose(0, 1).contiguous()), 0, 1, ptr(hs),
+        check(lib.apyib_dots(dtype_code(hs), ptr(dens[0].transpose(0, 1).contiguous()), 0, 1, ptr(hs),
                              hs.numel(), 0, ptr(e), ptr(reduce_scratch()), stream_ptr()))
         E_fc = LazyScalar(e, cplx)
         if not lazy:
             E_fc = E_fc.get()
         h = h_fc
-    _, F_AO = fock_like(h, Cd[:, o])
+    F_AO = _axpby_new(1.0, JK[-1], 1.0, h)
     Ct = Cd[:, t]
     tmp = contract_new("ij,jq->iq", F_AO, Ct)
     F_MO = contract_new("ip,iq->pq", Ct, tmp, conj_a=True)
@@ -180,7 +213,7 @@ def compute_ERI_MO_dev(parameters, wfn, C_list):
     cplx = _is_complex(wfn)
     dt = torch.complex128 if cplx else torch.float64
     _, G = ao_on_device(wfn, cplx)
-    Ct = to_device(np.asarray(wfn.C), dt)[:, C_list[3]].t().contiguous()        # [t, nbf]: rows = MO, k contiguous
+    Ct = wfn_small_on_device(wfn, cplx)[0][:, C_list[3]].t().contiguous()        # [t, nbf]: rows = MO, k contiguous
     X = contract_new("mnlg,sg->smnl", G, Ct)
     X = contract_new("smnl,rl->rsmn", X, Ct, conj_b=True)
     X = contract_new("rsmn,qn->qrsm", X, Ct)

@@ -75,19 +75,19 @@ def aat_points(natom):
     return pts + [("B", b, +1) for b in range(3)] + [("B", b, -1) for b in range(3)]
 
 
-def base_config(wl):
-    return {"workload": wl["label"], "nbf": wl["nbf"], "ndocc": wl["ndocc"], "nfzc": wl["nfzc"], "natom": wl["natom"],
+def base_config(wl, method="CISD"):
+    return {"workload": wl["label"].replace("CISD", method), "nbf": wl["nbf"], "ndocc": wl["ndocc"], "nfzc": wl["nfzc"], "natom": wl["natom"],
             "fd_points": 6 * wl["natom"] + 7, "overlap_matrices": 7 + 42 * wl["natom"], "h_R": H_R, "h_B": H_B,
-            "method": "CISD", "l2": L2_NOTE, "sharding": "fd-points, then tensor rows alpha"}
+            "method": method, "l2": L2_NOTE, "sharding": "fd-points, then tensor rows alpha"}
 
 
 # ---------------------------------------------------------------------------------------------
 # host inputs (untimed): SCF + phase fix for the finite-difference points (numpy only: `hostinputs`)
 # ---------------------------------------------------------------------------------------------
-def prepare(wl, points=None):
+def prepare(wl, points=None, method="CISD"):
     import hostinputs as hc
     prov = hc.SyntheticProvider(wl["nbf"], wl["ndocc"], wl["natom"], seed=1000 * 2, nfzc=wl["nfzc"])
-    par = {"geom": prov.geometry_string(), "basis": "synthetic", "method": "CISD", "freeze_core": wl["nfzc"] > 0,
+    par = {"geom": prov.geometry_string(), "basis": "synthetic", "method": method, "freeze_core": wl["nfzc"] > 0,
            "F_el": [0.0] * 3, "F_mag": [0.0] * 3, "provider": prov, "DIIS": True, "max_iterations": 120,
            "e_convergence": 1e-12, "d_convergence": 1e-12}
 
@@ -292,7 +292,7 @@ def reference_arm(args, wl):
 def gpu_step(work, rank=0, world=1, dist=None, phases=None):
     import torch
     from apyib_b200.aats import AAT
-    from apyib_b200.ci_wfn import solve_many
+    from apyib_b200.energy import correlated_many
     from apyib_b200.fin_diff import point_cost
     from apyib_b200.parallel import partition, exchange_points, owned_elements
     par, w0, natom = work["par"], work["w0"], work["natom"]
@@ -304,8 +304,8 @@ def gpu_step(work, rank=0, world=1, dist=None, phases=None):
     own = partition(allp, [point_cost(p[0]) for p in allp], world)
     my_pts = [p for p, o in zip(allp, own) if o == rank]
     wf = lambda p: w0 if p[0] == "U" else work["pts"][p]
-    sols = solve_many("CISD", par, [wf(p) for p in my_pts])
-    mine = {p: [1, r[1], r[2]] for p, r in zip(my_pts, sols)}
+    sols = correlated_many(par, [wf(p) for p in my_pts])          # [(E_corr, [t0, t1, t2])], batched on the device
+    mine = {p: T_list for p, (_, T_list) in zip(my_pts, sols)}
     mark("solves")
     import apyib_b200
     if apyib_b200.config.TIMING is not None:             # instrumented step: keep the two phases apart
@@ -481,6 +481,8 @@ def main():
                     help="substituted determinants by batched LU, by the determinant lemma, or in closed form "
                          "(default: per workload -- lu for h2o2, factorized for methyloxirane)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--method", default="CISD", choices=["CISD", "CID", "MP2"],
+                    help="correlated method of the finite-difference AAT (BASELINE configs[2] is MP2, configs[3] CISD)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -489,9 +491,11 @@ def main():
         from tools import bench_sweep
         return bench_sweep.main(args, rank, world, local_rank)
     wl = WORKLOADS[args.workload]
-    config = base_config(wl)
+    config = base_config(wl, args.method)
 
     if args.impl == "reference":
+        if args.method != "CISD":
+            raise SystemExit("--impl reference samples the CISD workload only")
         if rank == 0:
             reference_arm(args, wl)
         return
@@ -513,7 +517,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    work = prepare(wl)
+    work = prepare(wl, method=args.method)
     # e2e leg: the host copies of the AO integrals live in pinned (page-locked) memory, registered once here
     pinned = dev.pin_host_inputs([work["w0"]] + list(work["pts"].values()))
     l2buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -624,9 +628,9 @@ def main():
         roof["timed_kernel_ms_aat_phase"] = round(sum(aat_ms.values()), 2)
         roof["timed_kernel_ms_total"] = round(sum(sum(a.elapsed_time(b) for a, b in v) for v in timing.values()), 2)
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.method == "CISD":
         cpu = cpu_baseline_once(wl)
-    line = {"metric": METRIC, "value": t_dev / args.steps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    line = {"metric": METRIC.replace("cisd", args.method.lower()), "value": t_dev / args.steps, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64/c128", "data": "synthetic", "config": config,
             "clocks": sampler.result(),

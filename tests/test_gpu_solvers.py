@@ -250,3 +250,36 @@ def test_solve_general_diis_drop_in(cplx):
         tn_o, e_o, t_o = orc.solve_general_DIIS(r, t, e_o, t_o, it)
         assert e_g.shape == e_o.shape and e_g.shape[1] <= 8 and np.array_equal(e_g, e_o) and np.array_equal(t_g, t_o)
         assert tn_g.dtype == tn_o.dtype and np.abs(tn_g - tn_o).max() < 1e-9 * max(1.0, np.abs(tn_o).max())
+
+
+def test_concurrent_identical_batches_equal_sequential():
+    """ci_wfn.solve_batches: two batches of IDENTICAL shape and dtype solved concurrently on two streams (what the
+    chunked finite-difference driver does at cc-pVDZ sizes) must equal the same batches solved one after the other --
+    shapes chosen so that the T1 <- T2 couplings take the split-K path, whose scratch buffers must not be shared
+    between streams"""
+    import apyib_b200
+    from apyib_b200.ci_wfn import ci_wfn, solve_batches
+    cfg = apyib_b200.config
+    p = par("CISD")
+    ws = [orc.rotated_wfn(26, 6, 700 + k, False, 0) for k in range(4)]
+    pts = [ci_wfn(p, w).point() for w in ws]
+    old = (cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE)
+    try:
+        cfg.RETURN_DEVICE = False
+        res = {}
+        for flag in (False, True, True, True):
+            cfg.SOLVE_CONCURRENT = flag
+            out = solve_batches("CISD", p, [pts[:2], pts[2:]])
+            flat = [r for batch, _ in out for r in batch]
+            if flag not in res:
+                res[flag] = flat
+            else:
+                for a, b in zip(res[flag], flat):
+                    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        for a, b in zip(res[False], res[True]):
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        for w, r in zip(ws, res[True]):
+            Eo, t1o, t2o = orc.solve_CISD(p, w)
+            assert abs(r[0] - Eo) < E_TOL and np.abs(r[2] - t2o).max() < T_TOL
+    finally:
+        cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE = old
