@@ -187,6 +187,7 @@ def _vdot(x, y, conj_x=True):
 _block_graphs = {}          # stack shape -> _BlockGraph | "warm" (seen once, eager) | None (not capturable)
 GRAPH_MAX_BYTES = 6 << 30
 GRAPH_MAX_LIVE = 24
+BLK4_GROUP = 5              # nuclear coordinates per (beta x pp/pn/np/nn) overlap stack: 12 overlaps each
 
 
 class _BlockGraph:
@@ -271,8 +272,21 @@ class AAT(object):
         # pairs at once: the AO overlaps are host inputs, the C^H S C products two batched launches per dtype
         jobs = []
 
+        ao_cache = {}
+
+        def ao_overlap(bb, kb):
+            """mixed-geometry AO overlap, evaluated once per distinct (bra geometry, ket geometry): all field points
+            share the unperturbed geometry, so only 6N + 1 of the 42N + 7 calls are different"""
+            try:
+                key = (id(bb.provider), id(kb.provider), bb.molecule.geometry().tobytes(), kb.molecule.geometry().tobytes())
+            except AttributeError:
+                key = (id(bb), id(kb))
+            if key not in ao_cache:
+                ao_cache[key] = provider_ao_overlap(bb, kb)
+            return ao_cache[key]
+
         def ovl(bb, Cb, kb, Ck):
-            jobs.append((Cb, provider_ao_overlap(bb, kb), Ck))
+            jobs.append((Cb, ao_overlap(bb, kb), Ck))
             return len(jobs) - 1
 
         U, Ub = self.unperturbed_wfn, unperturbed_basis
@@ -808,10 +822,17 @@ class AAT(object):
         add(cached(("pu", a), self.overlap_pu[a], "tc", "dH"), +1, 0, b, os_N=N_np[a], od=True)
         add(cached(("nu", a), self.overlap_nu[a], "tc", "dH"), -1, 0, b, os_N=N_nn[a], od=True)
         key = ("blk4", a, normalization)
-        if key not in self._cache:       # the 12 (beta x pp/pn/np/nn) overlaps of this alpha in one stack
-            stack = [m[a][bb] for bb in range(3) for m in (self.overlap_pp, self.overlap_pn, self.overlap_np,
-                                                              self.overlap_nn)]
-            self._cache[key] = self._blocks(stack, pick(A1, "tc"), A2["tc"], pick(A1, "t"), A2["t"])
+        if key not in self._cache:
+            # the 12 (beta x pp/pn/np/nn) overlaps of this alpha -- together with those of the next active rows
+            # that are still missing, BLK4_GROUP rows per stack: the launches of a stack are latency bound (a
+            # few dozen sub-millisecond kernels), so five rows cost little more than one
+            todo = [r for r in self._active_rows() if r != a and ("blk4", r, normalization) not in self._cache]
+            grp = [a] + todo[:max(0, BLK4_GROUP - 1)]
+            stack = [m[r][bb] for r in grp for bb in range(3) for m in (self.overlap_pp, self.overlap_pn,
+                                                                          self.overlap_np, self.overlap_nn)]
+            res = self._blocks(stack, pick(A1, "tc"), A2["tc"], pick(A1, "t"), A2["t"])
+            for j, r in enumerate(grp):
+                self._cache[("blk4", r, normalization)] = res[12 * j:12 * j + 12]
         r4 = self._cache[key][4 * b:4 * b + 4]
         # I_00 (aats.py:672-677) from det(S_oo) of the same four overlaps, which their stack has already evaluated
         I["00"] = (r4[0]["dS"] ** 2 * N_np[a] * N_mp[b] - r4[1]["dS"] ** 2 * N_np[a] * N_mn[b]

@@ -40,6 +40,30 @@ def get_slices(parameters, wfn):
 # ---------------------------------------------------------------------------------------------
 # upload-once cache of the per-geometry AO integrals (north star: "uploaded once")
 # ---------------------------------------------------------------------------------------------
+_HOST2DEV = {}           # id(host array) -> (weakref to the array, device copy)
+
+
+def register_device_copy(host_array, dev_tensor):
+    """Remember that `dev_tensor` is the device copy of the numpy array `host_array` (identity, not value): the MO
+    coefficients uploaded for the solves are needed again for the MO overlaps of the AAT stage."""
+    import weakref
+    if isinstance(host_array, np.ndarray):
+        if len(_HOST2DEV) > 4096:
+            for k in [k for k, (r, _) in _HOST2DEV.items() if r() is None]:
+                del _HOST2DEV[k]
+        try:
+            _HOST2DEV[id(host_array)] = (weakref.ref(host_array), dev_tensor)
+        except TypeError:
+            pass
+
+
+def lookup_device_copy(host_array):
+    ent = _HOST2DEV.get(id(host_array))
+    if ent is not None and ent[0]() is host_array and ent[1].device.index == torch.cuda.current_device():
+        return ent[1]
+    return None
+
+
 def _ao_cache(H):
     cache = getattr(H, "_apyib_b200_dev", None)
     if cache is None:
@@ -74,6 +98,7 @@ def ao_prefetch(wfns):
             ev.record(cs)
             cache["raw"] = (h, G, ev)
             cache["C"], cache["eps"], cache["C_host"] = Cd, eps, w.C
+            register_device_copy(w.C, Cd)
 
 
 def wfn_small_on_device(wfn, want_complex):
@@ -86,6 +111,7 @@ def wfn_small_on_device(wfn, want_complex):
         Cd = to_device(np.asarray(wfn.C))
         eps = to_device(np.ascontiguousarray(np.real(np.asarray(wfn.eps)), dtype=np.float64))
         cache["C"], cache["eps"], cache["C_host"] = Cd, eps, wfn.C
+        register_device_copy(wfn.C, Cd)
     if Cd.dtype != dt:
         if dt == torch.float64:
             raise TypeError("complex MO coefficients need the complex path")
@@ -362,24 +388,50 @@ def mo_overlap_dev(C_bra, S_ao, C_ket):
 def mo_overlaps_dev(triples, host=False):
     """[C_bra^H S_AO C_ket for (C_bra, S_AO, C_ket) in triples] with TWO batched contraction launches per
     dtype group (real / complex) instead of two per matrix: the finite-difference AAT needs 1 + 6 + 6N + 36N
-    overlaps of identical shape (aats.py:53-115).  Returns device tensors, float64 where all three inputs
-    are real (like numpy would), complex128 otherwise; host=True returns numpy arrays instead (one copy per group)."""
+    overlaps of identical shape (aats.py:53-115) built from only 6N + 7 distinct coefficient matrices and 6N + 1
+    distinct AO overlaps.  Every DISTINCT operand (by identity) goes to the device once -- coefficient matrices
+    that were uploaded for the solves (ao_prefetch) or came through the NCCL exchange are not uploaded at all --
+    and the per-overlap operand stacks are gathered on the device.  Returns device tensors, float64 where all
+    three inputs are real (like numpy would), complex128 otherwise; host=True returns numpy arrays instead (one
+    copy per group)."""
     out = [None] * len(triples)
+    uniq, ops = {}, []                                   # id(operand) -> position, [(device tensor, is complex)]
+
+    def slot(x):
+        k = uniq.get(id(x))
+        if k is None:
+            if isinstance(x, torch.Tensor):
+                d = x if x.is_cuda else to_device(x)
+            else:
+                d = lookup_device_copy(x)
+                if d is None:
+                    d = to_device(np.asarray(x))
+            k = uniq[id(x)] = len(ops)
+            ops.append(d)
+        return k
+
+    idx = [tuple(slot(x) for x in t) for t in triples]
     groups = {}
-    # MO coefficients that came through the NCCL exchange are device tensors; they are nbf^2 and join the host stack
-    triples = [tuple(x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x) for x in t) for t in triples]
-    for k, t in enumerate(triples):
-        cplx = any(np.iscomplexobj(x) for x in t)
-        groups.setdefault((cplx, np.shape(t[0]), np.shape(t[1]), np.shape(t[2])), []).append(k)
-    for (cplx, _, _, _), idx in groups.items():
-        dt, npdt = (torch.complex128, np.complex128) if cplx else (torch.float64, np.float64)
-        stack = lambda j: to_device(np.stack([np.asarray(triples[k][j]) for k in idx]).astype(npdt, copy=False), dt)
-        Cb, S, Ck = stack(0), stack(1), stack(2)
+    for k, t in enumerate(idx):
+        cplx = any(ops[j].dtype == torch.complex128 for j in t)
+        groups.setdefault((cplx,) + tuple(tuple(ops[j].shape) for j in t), []).append(k)
+    for key, members in groups.items():
+        dt = torch.complex128 if key[0] else torch.float64
+        used = sorted(set(j for k in members for j in idx[k]))
+        pos = {j: p for p, j in enumerate(used)}
+        shapes = set(tuple(ops[j].shape) for j in used)
+        if len(shapes) == 1:                             # square case: one stack of all distinct operands
+            U = torch.stack([ops[j] if ops[j].dtype == dt else _widen(ops[j]) for j in used])
+            sel = lambda c: U.index_select(0, torch.tensor([pos[idx[k][c]] for k in members], device=U.device))
+            Cb, S, Ck = sel(0), sel(1), sel(2)
+        else:
+            cast = lambda j: ops[j] if ops[j].dtype == dt else _widen(ops[j])
+            Cb, S, Ck = (torch.stack([cast(idx[k][c]) for k in members]) for c in range(3))
         tmp = contract_new("smn,snq->smq", S, Ck)
         res = contract_new("smp,smq->spq", Cb, tmp, conj_a=True)
         if host:
             res = to_host(res)                       # ONE device->host copy per dtype group
-        for j, k in enumerate(idx):
+        for j, k in enumerate(members):
             out[k] = res[j]
     return out
 
