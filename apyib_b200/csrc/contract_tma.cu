@@ -170,33 +170,51 @@ contract_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (tid == 0 && kt + STAGES < nslab) issue(kt + STAGES);
     }
 
+    // epilogue (see contract.cu): all old values of a fragment row are loaded before the row is written
     const bool has_beta = (p.beta_re != 0.0) || (p.beta_im != 0.0);
     using T = typename std::conditional<CPLX, cplx, double>::type;
     T *C = reinterpret_cast<T *>(p.C) + (size_t)z * p.c_bs;
+    int64_t on[TN][2];
+    bool nok[TN][2];
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int64_t n = n0 + wn0 + j * 8 + fk * 2 + q;
+            nok[j][q] = n < p.N;
+            on[j][q] = nok[j][q] ? p.c_n[n] : 0;
+        }
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         const int64_t m = m0 + wm0 + i * 8 + fr;
         if (m >= p.M) continue;
-        const int64_t om = p.c_m[m];
+        T *row = C + p.c_m[m];
+        T oldv[TN][2];
+        if (has_beta) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    if (nok[j][q]) oldv[j][q] = row[on[j][q]];
+        }
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int64_t n = n0 + wn0 + j * 8 + fk * 2 + q;
-                if (n >= p.N) continue;
-                T *dst = C + om + p.c_n[n];
+                if (!nok[j][q]) continue;
+                T *dst = row + on[j][q];
                 if constexpr (CPLX) {
                     double xr = cr[i][j][q], xi = ci[i][j][q];
                     double vr = p.alpha_re * xr - p.alpha_im * xi, vi = p.alpha_re * xi + p.alpha_im * xr;
                     if (has_beta) {
-                        cplx o = *dst;
+                        const cplx o = oldv[j][q];
                         vr += p.beta_re * o.x - p.beta_im * o.y;
                         vi += p.beta_re * o.y + p.beta_im * o.x;
                     }
                     *dst = make_cplx(vr, vi);
                 } else {
                     double v = p.alpha_re * cr[i][j][q];
-                    if (has_beta) v += p.beta_re * (*dst);
+                    if (has_beta) v += p.beta_re * oldv[j][q];
                     *dst = v;
                 }
             }

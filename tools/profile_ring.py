@@ -23,13 +23,17 @@ terms = [("skbjc,sikca->sijab", "ovvo", "t2"), ("skaic,skjcb->sijab", "ovvo", "t
          ("skija,skb->sijab", "vooo", "t1"), ("sac,sijcb->sijab", "Fvv", "t2"), ("sbc,sijac->sijab", "Fvv", "t2"),
          ("ski,skjab->sijab", "Foo", "t2"), ("skj,sikab->sijab", "Foo", "t2"),
          ("sajbc,sijbc->sia", "vovv", "t2"), ("skjib,skjab->sia", "ooov", "t2"), ("sjb,sijab->sia", "Fov", "t2")]
+if "vvvv" in W:        # pair-packed ladder (ci_wfn._PackedLadder): N = o(o+1)/2 occupied pairs
+    npair = o * (o + 1) // 2
+    W["tp"], W["hp"] = rnd(nb, npair, v, v), torch.zeros(nb, npair, v, v, dtype=dt, device=dev)
+    terms.append(("sabcd,spcd->spab", "vvvv", "tp"))
 only = os.environ.get("ONLY")
 flop_unit = 8.0 if dt == torch.complex128 else 2.0
 for spec, wk, tk in terms:
     if wk not in W or (only and only not in spec):
         continue
-    A, B = W[wk], (t2 if tk == "t2" else t1)
-    out = r1 if spec.endswith("sia") else r2
+    A, B = W[wk], (t2 if tk == "t2" else (W["tp"] if tk == "tp" else t1))
+    out = r1 if spec.endswith("sia") else (W["hp"] if tk == "tp" else r2)
     for _ in range(2):
         contract(spec, A, B, out, 1.0, 1.0)
     torch.cuda.synchronize()
@@ -42,7 +46,7 @@ for spec, wk, tk in terms:
     ms = e0.elapsed_time(e1) / reps
     ins = spec.split("->")[0].split(",")
     idx = set(ins[0]) | set(ins[1])
-    size = dict(s=nb, i=o, j=o, k=o, l=o, a=v, b=v, c=v, d=v)
+    size = dict(s=nb, i=o, j=o, k=o, l=o, a=v, b=v, c=v, d=v, p=o * (o + 1) // 2)
     fl = flop_unit * np.prod([float(size[c]) for c in idx])
     byts = (A.numel() + B.numel() + 2 * out.numel()) * A.element_size()
     print("%-22s %8.3f ms  %6.2f TFLOP/s  %7.1f GB/s (operands once)" % (spec, ms, fl / ms / 1e9, byts / ms / 1e6))
