@@ -409,7 +409,8 @@ def roofline_from_timing(timing, wl, step_s, fp64_peak, peak_src):
         itemsize = 16 if m.group(2) == "c128" else 8
         extra["algorithmic_bytes"] = itemsize * nb_ * (M_ * K_ + K_ * N_ + 2 * M_ * N_)
         kern = ("contract_tma_kernel (FP64 DMMA, TMA-fed) " if m.group(1) else "contract_kernel (FP64 DMMA, LDGSTS gather) ") + name
-        tkey = ("contract_tma_kernel " if m.group(1) else "contract_kernel ") + name.split("[")[1].rstrip("]")
+        tkey = ("contract_tma_kernel " if m.group(1) else "contract_kernel ") + "%s %dx%dx%d" % (m.group(2), M_, N_, K_)
+        extra["_nb"] = nb_
         note = ("FP64 tensor (DMMA) roofline; flops = the dense count of the einsum as EXECUTED (2 MNK real / 8 MNK "
                 "complex per point; M x N x K and the point batch b are in the kernel name)")
     elif name.startswith("det_pairs"):
@@ -455,10 +456,14 @@ def roofline_from_timing(timing, wl, step_s, fp64_peak, peak_src):
         tab = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tab.get(tkey)
         if ent:
-            roof["traffic"] = ent.get("dram_bytes_per_launch")
+            if "dram_bytes_per_point" in ent:        # contraction captures: one launch of nb_captured points
+                roof["traffic"] = ent["dram_bytes_per_point"] * roof.get("_nb", 1)
+            else:
+                roof["traffic"] = ent.get("dram_bytes_per_launch")
             roof["traffic_source"] = ent.get("source")
     except Exception:
         pass
+    roof.pop("_nb", None)
     # the next few signatures, for context (same step)
     top = sorted(tot_ms.items(), key=lambda kv: -kv[1])[:12]
     roof["top_signatures_ms"] = {k: round(v, 2) for k, v in top}

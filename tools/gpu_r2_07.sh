@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 for n in 8 4; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 2 > gpurun_out/b_meth_n$n.log 2>&1
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 4 --warmup 3 > gpurun_out/b_meth_n$n.log 2>&1
 echo "n$n rc=$?"
 tail -1 gpurun_out/b_meth_n$n.log | python -c "
 import json,sys
