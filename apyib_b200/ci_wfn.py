@@ -655,6 +655,7 @@ def solve_batch(method, parameters, points, print_level=0):
 
 
 _side_streams = {}
+_DEBUG_KEEP = None          # tools/diag_race3.py: list that receives the ci_wfn objects of every solve_many call
 
 
 def _streams(n):
@@ -818,6 +819,8 @@ def solve_many(method, parameters, wfns, print_level=0):
         size = -(-len(idx) // nchunk)
         idxs += [idx[i:i + size] for i in range(0, len(idx), size)]
     cis = [None] * len(wfns)
+    if _DEBUG_KEEP is not None:
+        _DEBUG_KEEP.append(cis)
 
     def job(idx):
         for k, c in zip(idx, ci_wfn.many(parameters, [wfns[k] for k in idx])):
