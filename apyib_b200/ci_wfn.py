@@ -668,16 +668,35 @@ def _streams(n):
     return pool[:n]
 
 
-def _run_jobs(make_jobs, singles):
+def _concurrent(sizes):
+    """config.SOLVE_CONCURRENT -> run these groups (sizes = elements per group: points x o^2 v^2) concurrently?"""
+    mode = config.SOLVE_CONCURRENT
+    if mode in (True, "1", 1):
+        return True
+    if mode in (False, "0", 0, None):
+        return False
+    return len(sizes) > 1 and max(sizes) <= config.SOLVE_CONCURRENT_MAX_ELEMS
+
+
+def _run_jobs(make_jobs, singles, concurrent=False):
     """make_jobs: list of callables, each returning the generator of one batch (its set-up runs at the generator's
-    first step, under the batch's stream).  One batch -> the caller's stream; several -> one side stream each,
-    driven concurrently from this host thread.  Returns [(results, iterations)] per batch."""
-    if len(make_jobs) == 1 or not config.SOLVE_CONCURRENT:
+    first step, under the batch's stream).  Sequential: one batch after the other on the caller's stream.
+    Concurrent: one side stream per batch, driven from this host thread, with the TMA-fed contraction kernel
+    switched off for the duration (config.SOLVE_CONCURRENT).  Returns [(results, iterations)] per batch."""
+    if len(make_jobs) == 1 or not concurrent:
         out = []
         for mk in make_jobs:
             eng, E = _drive([(mk(), None)])[0]
             out.append((_collect(eng, E, singles), list(eng.iterations)))
         return out
+    use_tma, config.USE_TMA = config.USE_TMA, False
+    try:
+        return _run_jobs_concurrently(make_jobs, singles)
+    finally:
+        config.USE_TMA = use_tma
+
+
+def _run_jobs_concurrently(make_jobs, singles):
     cur = torch.cuda.current_stream()
     streams = _streams(len(make_jobs))
     for st in streams:
@@ -703,7 +722,8 @@ def solve_batches(method, parameters, batches, print_level=0):
     they fill the device.  Results are identical to solving the batches one after the other (same launches, same
     order within a batch).  Returns [(results, iterations)] per batch."""
     fn, singles = _SOLVERS[method]
-    return _run_jobs([(lambda pts=pts: fn(parameters, pts, print_level)) for pts in batches], singles)
+    return _run_jobs([(lambda pts=pts: fn(parameters, pts, print_level)) for pts in batches], singles,
+                     concurrent=config.SOLVE_CONCURRENT in (True, "1", 1))
 
 
 class ci_wfn(object):
@@ -827,7 +847,15 @@ def solve_many(method, parameters, wfns, print_level=0):
             cis[k] = c
         return (yield from fn(parameters, [cis[k].point() for k in idx], print_level))
 
-    solved = _run_jobs([(lambda idx=idx: job(idx)) for idx in idxs], singles)
+    def elems(idx):                                                  # points x o^2 v^2 of a group
+        w = wfns[idx[0]]
+        o = int(w.ndocc) - w.H.basis_set.n_frozen_core()
+        v = int(w.nbf) - int(w.ndocc)
+        f = 4 if method.endswith("_SO") else 1
+        return len(idx) * f * f * o * o * v * v
+
+    solved = _run_jobs([(lambda idx=idx: job(idx)) for idx in idxs], singles,
+                       concurrent=_concurrent([elems(idx) for idx in idxs]))
     out = [None] * len(wfns)
     for idx, (res, its) in zip(idxs, solved):
         for k, r, it in zip(idx, res, its):

@@ -50,12 +50,16 @@ PACKED_LADDER = _os.environ.get("APYIB_B200_PACKED_LADDER", "1") == "1"
 # when a point's AO integrals exceed SOLVE_CHUNK_MIN_BYTES, split into chunks of at most SOLVE_CHUNK points in upload
 # order; the groups are solved one after the other on the caller's stream while the copy stream keeps uploading the
 # AO integrals of the later groups (complex points first, so their iterations hide the upload of the real points).
-# SOLVE_CONCURRENT = True runs the groups on one CUDA stream each, driven from one host thread.  OFF: measured on a
-# B200 (round 2, tools/diag_race*.py) it gives nothing at N = 1 at the (S)-methyloxirane/cc-pVDZ shape (the device
-# is saturated: 1.06 s vs 1.02 s), and TMA-fed contraction kernels (contract_tma.cu) that run concurrently on
-# DIFFERENT streams corrupt each other's loads (MO integrals off by 1e-2; exact with USE_TMA = False or with
-# CUDA_LAUNCH_BLOCKING=1) -- the tensor maps are __grid_constant__ kernel parameters; isolated, not fixed.
-SOLVE_CONCURRENT = _os.environ.get("APYIB_B200_SOLVE_CONCURRENT", "0") == "1"
+# SOLVE_CONCURRENT: run the groups on one CUDA stream each, driven from one host thread ("1"), never ("0"), or
+# "auto" (default): only when every group is SMALL (points x o^2 v^2 <= SOLVE_CONCURRENT_MAX_ELEMS), i.e. when a
+# group's ~40 dependent launches per iteration cannot fill the device on their own -- the H2O2/6-31G-sized
+# molecules, and the 8-GPU runs of larger ones where a rank holds ~8 real points and one complex point.  Large
+# groups saturate the device anyway (measured at N = 1, (S)-methyloxirane/cc-pVDZ shape: 1.06 s vs 1.02 s).
+# The concurrent section runs WITHOUT the TMA-fed contraction kernel: TMA kernels running concurrently on different
+# streams corrupt each other's loads (MO integrals off by 1e-2; bit-exact with USE_TMA = False or with
+# CUDA_LAUNCH_BLOCKING=1; tools/diag_race3.py) -- the tensor maps are __grid_constant__ parameters; isolated, not fixed.
+SOLVE_CONCURRENT = _os.environ.get("APYIB_B200_SOLVE_CONCURRENT", "auto")
+SOLVE_CONCURRENT_MAX_ELEMS = 8_000_000
 SOLVE_CHUNK = 32
 SOLVE_CHUNK_MIN_BYTES = 64 << 20
 
