@@ -272,15 +272,22 @@ class AAT(object):
         # pairs at once: the AO overlaps are host inputs, the C^H S C products two batched launches per dtype
         jobs = []
 
-        ao_cache = {}
+        ao_cache, geo_cache = {}, {}
+
+        def geo_key(basis):
+            k = geo_cache.get(id(basis))
+            if k is None:
+                try:
+                    k = (id(basis.provider), basis.molecule.geometry().tobytes())
+                except AttributeError:
+                    k = id(basis)
+                geo_cache[id(basis)] = k
+            return k
 
         def ao_overlap(bb, kb):
             """mixed-geometry AO overlap, evaluated once per distinct (bra geometry, ket geometry): all field points
             share the unperturbed geometry, so only 6N + 1 of the 42N + 7 calls are different"""
-            try:
-                key = (id(bb.provider), id(kb.provider), bb.molecule.geometry().tobytes(), kb.molecule.geometry().tobytes())
-            except AttributeError:
-                key = (id(bb), id(kb))
+            key = (geo_key(bb), geo_key(kb))
             if key not in ao_cache:
                 ao_cache[key] = provider_ao_overlap(bb, kb)
             return ao_cache[key]
@@ -406,6 +413,15 @@ class AAT(object):
     # ---------------------------------------------------------------------------------------
     # spatial route
     # ---------------------------------------------------------------------------------------
+    def _amp(self, x):
+        """complex128 device copy of an amplitude array, uploaded / converted once per AAT object (the norms and
+        the scaled amplitude combinations both read every amplitude set)"""
+        memo = self.__dict__.setdefault("_amp_memo", {})
+        ent = memo.get(id(x))
+        if ent is None or ent[0] is not x:
+            ent = memo[id(x)] = (x, _dev(x))
+        return ent[1]
+
     def _active_rows(self):
         """nuclear coordinates whose norms / scaled amplitudes are built: the hinted rows (constructor `rows=`,
         prefetch_rows) or all of them"""
@@ -429,13 +445,13 @@ class AAT(object):
             # (x = t0 + 2<t1|t1> + 2<t2|t2> - <t2|t2^T>, aats.py:652-669)
             Ts = ([self.unperturbed_T] + [self.nuc_pos_T[a] for a in rows] + [self.nuc_neg_T[a] for a in rows]
                   + list(self.mag_pos_T) + list(self.mag_neg_T))
-            t2 = torch.stack([_dev(T[2]) for T in Ts])
+            t2 = torch.stack([self._amp(T[2]) for T in Ts])
             npt = len(Ts)
             acc = zeros((3, npt), _C128)
             contract("sijab,sijab->s", t2, t2, acc[0], 1.0, 0.0, conj_a=True)
             contract("sijab,sijba->s", t2, t2, acc[1], 1.0, 0.0, conj_a=True)
             if cisd:
-                t1 = torch.stack([_dev(T[1]) for T in Ts])
+                t1 = torch.stack([self._amp(T[1]) for T in Ts])
                 contract("sia,sia->s", t1, t1, acc[2], 1.0, 0.0, conj_a=True)
             h = to_host(acc)
             Nall = [1 / np.sqrt(Ts[s][0] + (2 * complex(h[0, s]) - complex(h[1, s])) + (2 * complex(h[2, s]) if cisd else 0))
@@ -461,22 +477,23 @@ class AAT(object):
         def build(idx):
             if idx == 1 and not cisd:
                 return None
-            T0 = _dev(self.unperturbed_T[idx])
+            T0 = self._amp(self.unperturbed_T[idx])
             t = _axpby(N, T0, 0.0, torch.empty_like(T0))
             tc = _axpby(np.conj(N), T0, 0.0, torch.empty_like(T0), conj_x=True)
             dH, dR = [], []
             for b in range(3):
-                x = _axpby(N_mp[b], _dev(self.mag_pos_T[b][idx]), 0.0, torch.empty_like(T0))
-                dH.append(_axpby(-N_mn[b], _dev(self.mag_neg_T[b][idx]), 1.0, x))
+                x = _axpby(N_mp[b], self._amp(self.mag_pos_T[b][idx]), 0.0, torch.empty_like(T0))
+                dH.append(_axpby(-N_mn[b], self._amp(self.mag_neg_T[b][idx]), 1.0, x))
             for a in rows:
-                x = _axpby(np.conj(N_np[a]), _dev(self.nuc_pos_T[a][idx]), 0.0,
+                x = _axpby(np.conj(N_np[a]), self._amp(self.nuc_pos_T[a][idx]), 0.0,
                            torch.empty_like(T0), conj_x=True)
-                dR.append(_axpby(-np.conj(N_nn[a]), _dev(self.nuc_neg_T[a][idx]), 1.0, x,
+                dR.append(_axpby(-np.conj(N_nn[a]), self._amp(self.nuc_neg_T[a][idx]), 1.0, x,
                                  conj_x=True))
             return dict(t=t[None], tc=tc[None], dH=torch.stack(dH), dR=torch.stack(dR))
 
         res = {1: build(1), 2: build(2), "pos": {a: k for k, a in enumerate(rows)}}
         self._cache[key] = res
+        self.__dict__.pop("_amp_memo", None)           # the raw device copies are not needed any more
         return res
 
     def _block(self, S_host, X1, X2, Y1, Y2):
@@ -744,12 +761,24 @@ class AAT(object):
         mixed = cn("sxkc,sqkc->sxq", M, W)
         # Z = A A R R x2 is linear in the amplitudes and commutes with the antisymmetric completion
         # (Z[Xf] = antisym(Z[x2])), so the four o^2 v^2 (o + v) transforms are done ONCE, on the plain amplitudes,
-        # and serve both the doubles x doubles table (with Xf, Yf) and the singly x singly product term below
-        Zx = cn("ski,xijab->sxkjab", Ai, X2)
-        Zx = cn("slj,sxkjab->sxklab", Ai, Zx)
-        Zx = cn("sac,sxklab->sxklcb", R, Zx)
-        Zx = cn("sbd,sxklcb->sxklcd", R, Zx)
-        gamma = cn("sxklcd,qklcd->sxq", antisym_stack(Zx), Yf)
+        # and serve both the doubles x doubles table (with Xf, Yf) and the singly x singly product term below.
+        # The quadrilinear form sum x_ijab y_klcd A_ki A_lj R_ac R_bd can be transformed from either side: the side
+        # with FEWER amplitude sets is transformed (up/un: 30 bra sets against 1 ket set per overlap).
+        nx, ny = X2.shape[0], Y2.shape[0]
+        if ny < nx:
+            Zy = cn("sbd,qklcd->sqklcb", R, Y2)
+            Zy = cn("sac,sqklcb->sqklab", R, Zy)
+            Zy = cn("slj,sqklab->sqkjab", Ai, Zy)
+            Zy = cn("ski,sqkjab->sqijab", Ai, Zy)
+            gamma = cn("xijab,sqijab->sxq", Xf, antisym_stack(Zy))
+            zxy = cn("xijab,sqijab->sxq", X2, Zy)
+        else:
+            Zx = cn("ski,xijab->sxkjab", Ai, X2)
+            Zx = cn("slj,sxkjab->sxklab", Ai, Zx)
+            Zx = cn("sac,sxklab->sxklcb", R, Zx)
+            Zx = cn("sbd,sxklcb->sxklcd", R, Zx)
+            gamma = cn("sxklcd,qklcd->sxq", antisym_stack(Zx), Yf)
+            zxy = cn("sxklcd,qklcd->sxq", Zx, Y2)
         ab = cn("sx,sq->sxq", alpha, beta)
         _axpby(4.0, mixed, 1.0, ab)
         _axpby(1.0, gamma, 1.0, ab)
@@ -766,7 +795,7 @@ class AAT(object):
         M2 = cn("sxka,sac->sxkc", cn("ski,sxia->sxka", Ai, U2), R)
         _axpby(1.0, cn("sxld,sqld->sxq", M1, W1), 1.0, c6)
         _axpby(1.0, cn("sxkc,sqkc->sxq", M2, W2), 1.0, c6)
-        _axpby(1.0, cn("sxklcd,qklcd->sxq", Zx, Y2), 1.0, c6)
+        _axpby(1.0, zxy, 1.0, c6)
         # alpha, beta, M, W also give the doubles x singles / singles x doubles tables (see _blocks):
         #   sum_ijab Xf det3(ijab; kc) = -2 alpha Q_kc - 4 M_kc,   sum_klcd Yf det3(ia; klcd) = 2 beta P_ai + 4 N_ia
         return dict(dd=mixed, c6=c6, alpha=alpha, beta=beta, M=M, W=W, Ai=Ai, P=P, Q=Q, R=R)

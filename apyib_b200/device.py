@@ -126,14 +126,14 @@ def copy_stream():
     return _copy_streams[d]
 
 
-def to_host(t):
+def to_host(t, pinned=True):
     """CUDA tensor -> fresh numpy array owned by the caller.  Large results land in page-locked host memory (torch's
     caching pinned allocator), so the copy runs at full PCIe rate and a later re-upload of the same array (the
     amplitudes go back to the device for the AAT assembly) is asynchronous as well."""
     nbytes = t.numel() * t.element_size()
     COUNTERS["d2h_bytes"] += nbytes
     t = t.detach()
-    if t.is_cuda and nbytes >= _PIN_MIN:
+    if pinned and t.is_cuda and nbytes >= _PIN_MIN:
         out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         out.copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -430,7 +430,9 @@ def mo_overlaps_dev(triples, host=False):
         tmp = contract_new("smn,snq->smq", S, Ck)
         res = contract_new("smp,smq->spq", Cb, tmp, conj_a=True)
         if host:
-            res = to_host(res)                       # ONE device->host copy per dtype group
+            # ONE device->host copy per dtype group, into ordinary memory: the overlaps live as long as the AAT
+            # object, and a fresh page-locked block per object costs more (cudaHostAlloc) than the copy saves
+            res = to_host(res, pinned=False)
         for j, k in enumerate(members):
             out[k] = res[j]
     return out
