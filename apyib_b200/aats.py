@@ -725,7 +725,7 @@ class AAT(object):
         i.e. O(o^2 v^2 (o+v)) DMMA contractions instead of (C(o,2) C(v,2))^2 determinants.
         Returns the intermediates and "dd" [nS, nx, ny]: the unrestricted sum (= 16 x the restricted
         i<j,a<b,k<l,c<d sum) over det T."""
-        from .utils import gather4, gather4_stack
+        from .utils import gather4
         nv = ns - no
         o = no - nf
         cn = contract_new
@@ -743,14 +743,6 @@ class AAT(object):
                 t = gather4(X[q], 0, X[q].shape, [0, 1, 2, 3], [0, 0, 0, 0], 1.0, [0, 1, 3, 2], [0, 0, 0, 0], -1.0)
                 gather4(t, 0, t.shape, [0, 1, 2, 3], [0, 0, 0, 0], 2.0, [1, 0, 2, 3], [0, 0, 0, 0], -2.0, out=out[q])
             return out
-
-        def antisym_stack(Z6):      # the same completion for a [s, x, k, l, c, d] stack: two launches
-            flat = Z6.reshape((-1,) + tuple(Z6.shape[2:]))
-            n = flat.shape[0]
-            sh = tuple(flat.shape[1:])
-            t = gather4_stack([flat[r] for r in range(n)], 0, sh, [0, 1, 2, 3], [0, 0, 0, 0], 1.0, [0, 1, 3, 2], [0, 0, 0, 0], -1.0)
-            t = gather4_stack([t[r] for r in range(n)], 0, sh, [0, 1, 2, 3], [0, 0, 0, 0], 2.0, [1, 0, 2, 3], [0, 0, 0, 0], -2.0)
-            return t.reshape(Z6.shape)
 
         Xf, Yf = antisym(X2), antisym(Y2)
         U = cn("xijab,sai->sxjb", Xf, P)
@@ -770,14 +762,16 @@ class AAT(object):
             Zy = cn("sac,sqklcb->sqklab", R, Zy)
             Zy = cn("slj,sqklab->sqkjab", Ai, Zy)
             Zy = cn("ski,sqkjab->sqijab", Ai, Zy)
-            gamma = cn("xijab,sqijab->sxq", Xf, antisym_stack(Zy))
+            gamma = cn("xijab,sqijab->sxq", Xf, Zy, alpha=8.0)        # sum antisym(Zy).Xf = 8 sum Zy.Xf (see below)
             zxy = cn("xijab,sqijab->sxq", X2, Zy)
         else:
             Zx = cn("ski,xijab->sxkjab", Ai, X2)
             Zx = cn("slj,sxkjab->sxklab", Ai, Zx)
             Zx = cn("sac,sxklab->sxklcb", R, Zx)
             Zx = cn("sbd,sxklcb->sxklcd", R, Zx)
-            gamma = cn("sxklcd,qklcd->sxq", antisym_stack(Zx), Yf)
+            # the antisymmetriser a = 2(1 - P_ab)(1 - P_ij) is self-adjoint and a.a = 8 a, so
+            # sum antisym(Zx).Yf = sum Zx.antisym(Yf) = 8 sum Zx.Yf: the completed Z is never formed
+            gamma = cn("sxklcd,qklcd->sxq", Zx, Yf, alpha=8.0)
             zxy = cn("sxklcd,qklcd->sxq", Zx, Y2)
         ab = cn("sx,sq->sxq", alpha, beta)
         _axpby(4.0, mixed, 1.0, ab)
