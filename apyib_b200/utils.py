@@ -292,7 +292,7 @@ def mo_integrals_many(parameters, wfns, C_lists):
         E_fc = [0] * len(idx)
         if parameters["freeze_core"] == True:  # noqa: E712 (reference semantics, utils.py:238)
             D_fc, h_fc = fock_like(h, Cd[:, :, f])
-            hs = h + h_fc                                                  # (plumbing: one elementwise add per group)
+            hs = _axpby_new(1.0, h_fc, 1.0, h)                             # h + h_fc (apyib_axpby)
             e = zeros((len(idx),), dt)
             contract("snm,smn->s", D_fc, hs, e, 1.0, 0.0)
             E_fc = [LazyScalar(e, cplx, j) for j in range(len(idx))]
