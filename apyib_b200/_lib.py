@@ -111,7 +111,7 @@ _KERNELS_PER_CALL = {
     "apyib_contract": 1, "apyib_contract_tma": 1, "apyib_gather4": 1, "apyib_gather4_batch": 1, "apyib_gather2": 1, "apyib_mp2_t2_energy": 2, "apyib_ci_update": 1,
     "apyib_symmetrize_ijab": 1, "apyib_dots": 1, "apyib_diis_push": 1, "apyib_diis_solve": 1,
     "apyib_lincomb_energy_rms": 1, "apyib_iter_advance": 1, "apyib_copy": 1, "apyib_copy_rows": 1, "apyib_widen": 1, "apyib_symmetrize_ijab_batch": 1, "apyib_pack_pairs": 1, "apyib_unpack_pairs_add": 1, "apyib_axpby": 1,
-    "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_det_outer_sorted": 1, "apyib_det_matvec_sorted": 2, "apyib_det_matvec_pairs": 2, "apyib_det_outer_stack": 1, "apyib_det_matvec_stack": 2, "apyib_det_matvec_pairs_stack": 2, "apyib_pack_doubles": 1,
+    "apyib_det_outer": 1, "apyib_det_matvec": 2, "apyib_det_outer_sorted": 1, "apyib_det_matvec_sorted": 2, "apyib_det_matvec_pairs": 3, "apyib_det_outer_stack": 1, "apyib_det_matvec_stack": 2, "apyib_det_matvec_pairs_stack": 3, "apyib_pack_doubles": 1,
     "apyib_lemma_prepare": 1, "apyib_lemma_outer": 1, "apyib_lemma_matvec": 2,
 }
 LAUNCHES = [0]

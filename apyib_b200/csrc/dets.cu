@@ -371,9 +371,29 @@ static int64_t pairs_nchunk(int64_t nrow, int64_t ngroup, int n, int k, int ns, 
     return chunks_for((nrow + 31) / 32, ngroup, w, 4096);
 }
 
+// per overlap: nchunk x ny x nrow partial sums + ny x ncol sorted, sign-folded amplitude entries (a stack of nS
+// overlaps needs nS times this; the partial sums of all overlaps come first, then the amplitude copies)
 extern "C" int64_t apyib_det_matvec_pairs_work_len(int64_t nrow, int64_t ngroup, int ny, int n, int k, int ns, int nc) {
     const int64_t c = pairs_nchunk(nrow, ngroup, n, k, ns, nc);
-    return (c > 0 ? c : 1) * ny * nrow;
+    const int64_t group_len = (k == 1) ? (int64_t)nc : (int64_t)nc * (nc - 1) / 2;
+    return (c > 0 ? c : 1) * ny * nrow + (int64_t)ny * ngroup * group_len;
+}
+
+// Ys[s][q][c] = sign[c] * Y[s][q][index[c]]: the amplitude vector in the order (and with the signs) of the sorted
+// column lists, so that the pair loop of the prefix-shared LU kernel reads ONE warp-uniform, contiguous entry per
+// determinant instead of sign + index + a gathered Y entry.
+__global__ void __launch_bounds__(256) permute_y_kernel(const cplx *__restrict__ Y, int64_t y_stride, const double *__restrict__ sign,
+                                                        const int32_t *__restrict__ index, int64_t ncol, int ny,
+                                                        cplx *__restrict__ Ys) {
+    Y += (size_t)blockIdx.y * y_stride;
+    Ys += (size_t)blockIdx.y * ny * ncol;
+    const int64_t total = (int64_t)ny * ncol;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = e / ncol, c = e - q * ncol;
+        const cplx v = Y[q * ncol + index[c]];
+        const double sg = sign[c];
+        Ys[e] = make_cplx(sg * v.x, sg * v.y);
+    }
 }
 
 extern "C" int apyib_det_set_pairs_variant(int which) {
@@ -405,9 +425,19 @@ static int det_matvec_pairs_impl(const void *d_S, int nS, int ns, int n, int k, 
     const int64_t gchunk = (ngroup + nchunk - 1) / nchunk;
     const int64_t len = (int64_t)ny * nrow;
     cudaStream_t st = (cudaStream_t)stream;
+    // amplitude vectors in sorted-list order with the list signs folded in (one copy per overlap, or one for all)
+    cplx *Ys = (cplx *)d_work + (int64_t)nS * nchunk * len;
+    const int nYs = y_stride == 0 ? 1 : nS;
+    {
+        int64_t pb = ((int64_t)ny * ncol + 255) / 256;
+        if (pb > 148 * 4) pb = 148 * 4;
+        permute_y_kernel<<<dim3((unsigned)pb, (unsigned)nYs), 256, 0, st>>>((const cplx *)d_Y, y_stride, d_col_sign, d_col_index,
+                                                                           ncol, ny, Ys);
+        APYIB_LAUNCH_CHECK();
+    }
     int rc = launch_det_pairs(n, k, st, (const cplx *)d_S, ns, d_rows, nrow, d_cols_sorted, ngroup, group_len, d_cand, nc,
-                              gchunk, nchunk, d_col_sign, d_col_index, (const cplx *)d_Y, ny, ncol, (cplx *)d_work, nS,
-                              y_stride, nchunk * len);
+                              gchunk, nchunk, nullptr, nullptr, Ys, ny, ncol, (cplx *)d_work, nS,
+                              y_stride == 0 ? 0 : (int64_t)ny * ncol, nchunk * len);
     if (rc != APYIB_OK) return rc;
     int64_t b = (len + 7) / 8;
     if (b > 148 * 8) b = 148 * 8;

@@ -268,27 +268,21 @@ det_pairs_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__
                         cplx d;
                         d.x = fma(-a1.x, b0.x, fma(a1.y, b0.y, fma(a0.x, b1.x, -a0.y * b1.y)));
                         d.y = fma(-a1.x, b0.y, fma(-a1.y, b0.x, fma(a0.x, b1.y, a0.y * b1.x)));
+                        // Y arrives in sorted-list order with the list signs folded in (permute_y_kernel): one
+                        // warp-uniform, contiguous entry per determinant
                         const int64_t c = cbase + t;
-                        const double sg = __ldg(&csign[c]);
-                        const int64_t cc = (int64_t)__ldg(&cindex[c]);
-                        d.x *= sg;
-                        d.y *= sg;
 #pragma unroll
                         for (int q = 0; q < NYMAX; ++q)
-                            if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + cc]);
+                            if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
                     }
                 }
             } else {
                 for (int x = 0; x < nc; ++x) {
-                    cplx d = pd * Lsm[x * T];
+                    const cplx d = pd * Lsm[x * T];
                     const int64_t c = cbase + x;
-                    const double sg = __ldg(&csign[c]);
-                    const int64_t cc = (int64_t)__ldg(&cindex[c]);
-                    d.x *= sg;
-                    d.y *= sg;
 #pragma unroll
                     for (int q = 0; q < NYMAX; ++q)
-                        if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + cc]);
+                        if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
                 }
             }
         }

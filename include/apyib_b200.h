@@ -261,7 +261,9 @@ int apyib_det_matvec_sorted(const void *d_S, int ns, int n, const int32_t *d_row
  * apyib_det_matvec_sorted (Z[q,r] = sum_c det(r,c) Y[q,c], Y indexed by the ORIGINAL enumeration), ~12x
  * fewer flops at n = 9, nc = 13.  Replaces the same np.linalg.det calls (aats.py:587-618).  Returns
  * APYIB_ERR_UNSUPPORTED when (n, k) is not instantiated (2 <= n <= 12) or the footprint does not fit.
- * d_work: apyib_det_matvec_pairs_work_len(...) complex128 elements.                                      */
+ * d_work: apyib_det_matvec_pairs_work_len(...) complex128 elements per overlap (partial sums of the group chunks +
+ * a copy of Y in sorted-list order with the list signs folded in, made by a small gather launch, so that the
+ * determinant loop reads one contiguous warp-uniform amplitude per determinant).                            */
 int64_t apyib_det_matvec_pairs_work_len(int64_t nrow, int64_t ngroup, int ny, int n, int k, int ns, int nc);
 int apyib_det_matvec_pairs(const void *d_S, int ns, int n, int k, const int32_t *d_rows, int64_t nrow,
                            const int32_t *d_cols_sorted, const double *d_col_sign, const int32_t *d_col_index,

@@ -175,3 +175,31 @@ def test_sampled_determinant_block_target_shape():
         out = empty((1, 300, 300), torch.complex128)
         check(lib.apyib_lemma_outer(ptr(prep), 1, T_NBF, no, 2, ptr(dr), 300, 2, ptr(dc), 300, ptr(out), stream_ptr()))
         assert np.abs(to_host(out)[0] - want).max() <= 10 * tol * scale
+
+
+@pytest.mark.parametrize("algo", ["lu", "lemma"])
+def test_aat_element_h2o2_shape_vs_streamed_oracle(algo):
+    """configs[1] at FULL size against an oracle (not only self-consistency): one (alpha, beta) element, all nine I_xy
+    terms, with the batched-LU kernels (prefix-shared LU on the 2808 x 2808 doubles x doubles table, what bench.py
+    --workload h2o2 runs) and the lemma kernel, vs the streamed oracle on sparse amplitudes"""
+    import apyib_b200
+    from apyib_b200 import aats
+    from apyib_b200.aats import AAT
+    from oracle import sparse_aat as sp
+    cfg = apyib_b200.config
+    A = sp.sparse_aat_inputs("CISD", NBF, NDOCC, 0, 1, 2230, h=1e-4, nnz2=40, nnz1=30)
+    want = sp.spatial_aat_terms_streamed(A, 2, 1, "full")
+    old = cfg.AAT_ALGORITHM
+    try:
+        cfg.AAT_ALGORITHM = algo
+        aats._block_graphs.clear()
+        G = AAT.from_parts(A.method, A.nbf, A.ndocc, A.nfzc, A.nuc_pert_strength, A.mag_pert_strength,
+                           **{k: getattr(A, k) for k in PARTS if hasattr(A, k)})
+        G.prefetch_rows([2])
+        got = G._spatial_terms(2, 1, "full")
+        k = 1 / (4 * A.nuc_pert_strength * A.mag_pert_strength)
+        for name, ref in want.items():
+            assert abs(k * np.imag(got[name] - ref)) < 1e-8 * max(1.0, abs(k * np.imag(ref))), (algo, name, got[name], ref)
+    finally:
+        cfg.AAT_ALGORITHM = old
+        aats._block_graphs.clear()
