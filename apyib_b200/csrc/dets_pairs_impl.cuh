@@ -260,20 +260,33 @@ det_pairs_kernel(const cplx *__restrict__ S, int ns, const int32_t *__restrict__
             const cplx pd = make_cplx(sgp * detx, sgp * dety);
             const int64_t cbase = g * npair;
             if (K == 2) {
-                int64_t t = 0;
-                for (int x = 0; x + 1 < nc; ++x) {
-                    const cplx a0 = pd * Lsm[(2 * x) * T], a1 = pd * Lsm[(2 * x + 1) * T];
-                    for (int y = x + 1; y < nc; ++y, ++t) {
-                        const cplx b0 = Lsm[(2 * y) * T], b1 = Lsm[(2 * y + 1) * T];
-                        cplx d;
-                        d.x = fma(-a1.x, b0.x, fma(a1.y, b0.y, fma(a0.x, b1.x, -a0.y * b1.y)));
-                        d.y = fma(-a1.x, b0.y, fma(-a1.y, b0.x, fma(a0.x, b1.y, a0.y * b1.x)));
-                        // Y arrives in sorted-list order with the list signs folded in (permute_y_kernel): one
-                        // warp-uniform, contiguous entry per determinant
-                        const int64_t c = cbase + t;
+                // determinants of the group: d(x, y) = prefix * (w_x[0] w_y[1] - w_x[1] w_y[0]) for x < y, list index
+                // t(x, y) = x nc - x (x + 1) / 2 + (y - x - 1) (lexicographic).  Two x per pass over y: every w_y read
+                // from shared memory feeds two determinants (the loop is bound by LDS issue otherwise).
+                auto det2 = [](const cplx &a0, const cplx &a1, const cplx &b0, const cplx &b1) {
+                    cplx d;
+                    d.x = fma(-a1.x, b0.x, fma(a1.y, b0.y, fma(a0.x, b1.x, -a0.y * b1.y)));
+                    d.y = fma(-a1.x, b0.y, fma(-a1.y, b0.x, fma(a0.x, b1.y, a0.y * b1.x)));
+                    return d;
+                };
+                auto accum = [&](const cplx &d, int64_t c) {
 #pragma unroll
-                        for (int q = 0; q < NYMAX; ++q)
-                            if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
+                    for (int q = 0; q < NYMAX; ++q)
+                        if (NYT || q < ny) z[q] = z[q] + d * ldg(&Y[(int64_t)q * ncol + c]);
+                };
+                for (int x = 0; x + 1 < nc; x += 2) {
+                    const int64_t t0 = cbase + (int64_t)x * nc - (int64_t)x * (x + 1) / 2;           // t(x, x + 1)
+                    const cplx a0 = pd * Lsm[(2 * x) * T], a1 = pd * Lsm[(2 * x + 1) * T];
+                    const cplx e0r = Lsm[(2 * x + 2) * T], e1r = Lsm[(2 * x + 3) * T];               // w of x + 1
+                    accum(det2(a0, a1, e0r, e1r), t0);                                              // pair (x, x + 1)
+                    if (x + 2 < nc) {
+                        const cplx e0 = pd * e0r, e1 = pd * e1r;
+                        const int64_t t1 = cbase + (int64_t)(x + 1) * nc - (int64_t)(x + 1) * (x + 2) / 2;   // t(x + 1, x + 2)
+                        for (int y = x + 2; y < nc; ++y) {
+                            const cplx b0 = Lsm[(2 * y) * T], b1 = Lsm[(2 * y + 1) * T];
+                            accum(det2(a0, a1, b0, b1), t0 + (y - x - 1));
+                            accum(det2(e0, e1, b0, b1), t1 + (y - x - 2));
+                        }
                     }
                 }
             } else {

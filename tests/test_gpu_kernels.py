@@ -432,7 +432,7 @@ def test_det_stack_entry_points_match_single_overlap_calls(n, nv, nf):
 @pytest.mark.parametrize("n,nv", [(4, 5), (9, 6), (9, 13), (12, 4)])
 def test_det_pairs_single_vector_variant_matches_generic(n, nv):
     """apyib_det_set_pairs_variant(1): the single-vector specialisation of the prefix-shared LU kernel must give
-    bit-identical results to the generic kernel (same arithmetic, fewer predicated issue slots)."""
+    the results of the generic kernel (same arithmetic, fewer predicated issue slots) to the last bits."""
     import apyib_b200
     from apyib_b200._lib import lib, check
     from apyib_b200.aats import _Tables, _det_matvec
@@ -450,7 +450,8 @@ def test_det_pairs_single_vector_variant_matches_generic(n, nv):
         for variant in (0, 1):
             check(lib.apyib_det_set_pairs_variant(variant))
             res.append(to_host(_det_matvec(S, n, rows, cols, Y, T.LS[2], T.PFX[2], 2)))
-        assert np.array_equal(res[0], res[1])
+        # same arithmetic; the two instantiations may contract their FMAs differently (last-bit differences)
+        assert np.abs(res[0] - res[1]).max() <= 1e-13 * np.abs(res[0]).max()
     finally:
         check(lib.apyib_det_set_pairs_variant(1 if apyib_b200.config.PAIRS_SINGLE_VECTOR else 0))
         apyib_b200.config.LU_PREFIX = old
