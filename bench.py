@@ -581,7 +581,8 @@ def main():
     sampler = ClockSampler(local_rank)
     # warm-up (also fills the device-resident AO-integral caches and the offset-table cache)
     timed_steps(args.warmup, True)
-    sampler.start()
+    if rank == 0:                      # one nvidia-smi poller per job: N of them contend for the driver lock
+        sampler.start()
     cfg.TIMING = None
     _lib.LAUNCHES[0] = 0
     t_dev, I_dev = timed_steps(args.steps, True)
@@ -609,7 +610,8 @@ def main():
     h2d, d2h = dev.COUNTERS["h2d_bytes"] // args.steps, dev.COUNTERS["d2h_bytes"] // args.steps
     phases_e2e = phase_summary()
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     if dist is not None:
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
