@@ -163,6 +163,11 @@ class CpuSampler:
         import multiprocessing as mp
         self.orc, self.wl, self.iters, self.det_budget = orc, wl, iters, det_budget
         self.cores = os.cpu_count() or 1
+        try:            # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses all host cores, as it says
+            from threadpoolctl import threadpool_limits
+            self._blas_limit = threadpool_limits(limits=self.cores)
+        except Exception:
+            self._blas_limit = None
         self.work = prepare(wl, points=[("B", 0, +1)])
         self.par = self.work["par"]
         self.w_real, self.w_cplx = self.work["w0"], self.work["pts"][("B", 0, +1)]
