@@ -156,7 +156,8 @@ class _Engine:
         """One trip of the reference's while-loop body for all active points, on the current stream."""
         self._copy(self.t_old, self.t)
         if self.symmetrize:
-            self._copy(self.r, self.r0)                      # (the r2 part is overwritten by the symmetrisation)
+            if self.n1:                                      # r1 <- its constant part; r2 is written by the symmetrisation
+                self._copy(self.r[:, :self.n1], self.r0[:, :self.n1])
             self._copy(self.r_half, self.r0[:, self.n1:])
             residual(self.r_half)
             check(lib.apyib_symmetrize_ijab_batch(self.code, ptr(self.r_half), self.r_half.stride(0), ptr(self.r[:, self.n1:]),
