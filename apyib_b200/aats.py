@@ -187,7 +187,8 @@ def _vdot(x, y, conj_x=True):
 _block_graphs = {}          # stack shape -> _BlockGraph | "warm" (seen once, eager) | None (not capturable)
 GRAPH_MAX_BYTES = 6 << 30
 GRAPH_MAX_LIVE = 24
-BLK4_GROUP = 5              # nuclear coordinates per (beta x pp/pn/np/nn) overlap stack: 12 overlaps each
+import os as _os
+BLK4_GROUP = int(_os.environ.get("APYIB_B200_BLK4_GROUP", "5"))   # nuclear coordinates per (beta x pp/pn/np/nn) overlap stack: 12 overlaps each
 
 
 class _BlockGraph:
