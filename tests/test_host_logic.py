@@ -282,3 +282,24 @@ def test_vcd_drop_in_matches_unmodified_reference():
         assert np.nanmax(np.abs(w - wr)) < 1e-8
         assert np.abs(D - np.array(c["ir_intensities_kmmol"])).max() < 1e-10
         assert np.abs(R - np.array(c["rotational_strengths"])).max() < 1e-10
+
+
+def test_reference_arm_and_oracle_do_not_import_the_product():
+    """bench.py --impl reference times the oracle port on host inputs from the neutral `hostinputs` package: neither
+    that arm nor the oracle may import apyib_b200 (the product library must not be loaded in the reference arm)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); import hostinputs; from oracle import apyib_oracle, fd_pipeline, sparse_aat, mini_psi4; "
+            "print(any(m.split('.')[0] == 'apyib_b200' for m in sys.modules))" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout.strip()
+    assert out == "False"
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "small",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, check=True)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["product_imported"] is False and line["extrapolated"] is True
+    assert line["steps"] == 1 and line["unit"] == "s/molecule" and line["higher_is_better"] is False
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert 0 < line["ms_per_step"] < 60e3 and line["value"] > 0
