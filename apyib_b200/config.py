@@ -57,7 +57,8 @@ PACKED_LADDER = _os.environ.get("APYIB_B200_PACKED_LADDER", "1") == "1"
 # groups saturate the device anyway (measured at N = 1, (S)-methyloxirane/cc-pVDZ shape: 1.06 s vs 1.02 s).
 # The concurrent section runs WITHOUT the TMA-fed contraction kernel: TMA kernels running concurrently on different
 # streams corrupt each other's loads (MO integrals off by 1e-2; bit-exact with USE_TMA = False or with
-# CUDA_LAUNCH_BLOCKING=1; tools/diag_race3.py) -- the tensor maps are __grid_constant__ parameters; isolated, not fixed.
+# CUDA_LAUNCH_BLOCKING=1; tools/diag_race3.py).  Passing the tensor maps through global memory (fence.proxy.tensormap)
+# instead of as __grid_constant__ parameters was tried and does not change it; isolated, not fixed.
 SOLVE_CONCURRENT = _os.environ.get("APYIB_B200_SOLVE_CONCURRENT", "auto")
 SOLVE_CONCURRENT_MAX_ELEMS = 8_000_000
 SOLVE_CHUNK = 32

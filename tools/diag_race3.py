@@ -20,7 +20,8 @@ def run(conc):
     res = cw.solve_many("CISD", par, wfns)
     torch.cuda.synchronize()
     cis = cw._DEBUG_KEEP[0]
-    ints = [(c._F_dev.clone(), c._ERI_dev.clone(), c.iterations) for c in cis]
+    ints = [(c._F_dev.clone(), c._ERI_dev.clone() if k < 8 else c._ERI_dev[:1, :1].clone(), c.iterations) for k, c in enumerate(cis)]
+    cw._DEBUG_KEEP.clear()
     return res, ints
 
 cfg.USE_TMA = os.environ.get('TMA', '1') == '1'
