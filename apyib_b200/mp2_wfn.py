@@ -57,3 +57,41 @@ class mp2_wfn(object):
     def solve_MP2_SO(self):
         """Reference: mp2_wfn.py:64-87.  Returns (E_MP2, t2[O,O,V,V]) in the spin-orbital basis."""
         return self._solve(True)
+
+    def perturbed_t2(self, t2, dF_MO, dERI, kind):
+        """Closed-form perturbed MP2 amplitudes of the analytic AAT route:
+            kind "H" (magnetic field,        analytic_aats.py:347-352)
+            kind "R" (nuclear displacement,  analytic_aats.py:446-451)
+        dt2 = [ d<ab|ij> (+/-) (dF . t2 terms) ] / D_ijab with `dERI` the perturbed PHYSICISTS' integrals d<pq|rs> and
+        `dF_MO` the perturbed Fock matrix over the active MO space, exactly the reference's local variables
+        `dERI_dH` / `dERI_dR`, `df_dH` / `df_dR` (host inputs from CPHF + Psi4 derivative integrals).  The four
+        contractions run on the DMMA contraction kernel, the division on the Jacobi-update kernel.  Returns dt2."""
+        from .ci_wfn import _Engine
+        from .contraction import contract
+        from .utils import gather4
+        O, V = len(self.eps_o), len(self.eps_v)
+        cplx = any(np.iscomplexobj(x) for x in (t2, dF_MO, dERI))
+        dt = torch.complex128 if cplx else torch.float64
+        T2, dF, dW = (to_device(np.asarray(x), dt) if not isinstance(x, torch.Tensor) else to_device(x, dt) for x in (t2, dF_MO, dERI))
+        eng = _Engine({"DIIS": False}, dt, 1, O, V, False, False, self.eps_o[None, :], self.eps_v[None, :])
+        r = eng.t2(eng.r)[0]
+        Foo, Fvv = dF[:O, :O], dF[O:, O:]
+        if kind == "H":
+            gather4(dW, 0, (O, O, V, V), [2, 3, 0, 1], [O, O, 0, 0], out=r)        # dERI.swapaxes(0,2).swapaxes(1,3)[o,o,v,v]
+            contract("ac,ijcb->ijab", Fvv, T2, r, 1.0, 1.0)
+            contract("bc,ijac->ijab", Fvv, T2, r, 1.0, 1.0)
+            contract("ki,kjab->ijab", Foo, T2, r, -1.0, 1.0)
+            contract("kj,ikab->ijab", Foo, T2, r, -1.0, 1.0)
+        elif kind == "R":
+            gather4(dW, 0, (O, O, V, V), [0, 1, 2, 3], [0, 0, O, O], out=r)        # dERI[o,o,v,v]
+            contract("kjab,ik->ijab", T2, Foo, r, -1.0, 1.0)
+            contract("ikab,kj->ijab", T2, Foo, r, -1.0, 1.0)
+            contract("ijcb,ac->ijab", T2, Fvv, r, 1.0, 1.0)
+            contract("ijac,cb->ijab", T2, Fvv, r, 1.0, 1.0)
+        else:
+            raise ValueError("kind must be 'H' or 'R'")
+        eng.out6.zero_()
+        eng.t.zero_()
+        eng._update()                                    # E = 0, t = 0:  t <- r / D_ijab
+        out = eng.t2()[0]
+        return out.clone() if config.RETURN_DEVICE else to_host(out)

@@ -485,3 +485,27 @@ def solve_general_DIIS(parameters, res_vec, t_vec, e_iter, t_iter, iteration, mi
     cc = torch.view_as_complex(c.view(8, 2))[:m].contiguous()
     t_new = to_host(contract_new("m,mo->o", cc, T))                       # utils.py:138
     return (t_new if cplx else np.ascontiguousarray(t_new.real)), e_iter, t_iter
+
+
+# ---------------------------------------------------------------------------------------------
+# a21  perturbed MO integrals of the analytic route              (apyib/analytic_aats.py:730-733, 977-981)
+# ---------------------------------------------------------------------------------------------
+def build_dERI(U, ERI_full, nfzc, kind, core=None):
+    """dERI_dH (kind "H", analytic_aats.py:730-733) / dERI_dR (kind "R", :977-981): four nbf^5 contractions of the CPHF
+    coefficients U (nbf, nbf) with the PHYSICISTS' MO integrals over all nbf orbitals (`ERI` of the reference at that
+    point, analytic_aats.py:27-33), t = [nfzc, nbf); the bra terms carry a minus sign for the magnetic field.  `core`
+    (kind "R") is the derivative-integral term `ERI_core[a]`, a host input.  Returns a numpy array (n_t^4)."""
+    cplx = any(np.iscomplexobj(x) for x in (U, ERI_full) + (() if core is None else (core,)))
+    dt = torch.complex128 if cplx else torch.float64
+    Ud, W = to_device(np.asarray(U), dt), to_device(np.asarray(ERI_full), dt)
+    nbf = Ud.shape[0]
+    t = slice(int(nfzc), nbf)
+    nt = nbf - int(nfzc)
+    Ut = Ud[:, t]
+    sgn = -1.0 if kind == "H" else 1.0
+    out = zeros((nt, nt, nt, nt), dt) if core is None else to_device(np.asarray(core), dt).clone()
+    contract("tr,pqts->pqrs", Ut, W[t, t, :, t], out, 1.0, 1.0)
+    contract("ts,pqrt->pqrs", Ut, W[t, t, t, :], out, 1.0, 1.0)
+    contract("tp,tqrs->pqrs", Ut, W[:, t, t, t], out, sgn, 1.0)
+    contract("tq,ptrs->pqrs", Ut, W[t, :, t, t], out, sgn, 1.0)
+    return to_host(out)

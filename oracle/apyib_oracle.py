@@ -897,3 +897,40 @@ def solve_perturbed_CID(parameters, wfn, t2, E_CID, dF_MO, dERI_MO, dE_guess=0.0
             break
         it += 1
     return (dE, dt2, min(it, parameters["max_iterations"])) if return_iters else (dE, dt2)
+
+
+# ----------------------------------------------------------------------------
+# a21  closed-form MP2 perturbed amplitudes and the perturbed-integral builds of the analytic route
+#      analytic_aats.py:347-352, 446-451 (dt2) and :730-733, 977-981 (dERI).  PARITY UNPINNED against outputs of the
+#      reference (its surrounding routine needs Psi4 derivative integrals); a line-by-line transcription.
+# ----------------------------------------------------------------------------
+def perturbed_MP2_t2(t2, dF, dW, D_ijab, O, V, kind):
+    """dW: perturbed PHYSICISTS' integrals d<pq|rs> over the active MO space, dF the perturbed Fock matrix.
+    kind "H": analytic_aats.py:347-352 (magnetic field); kind "R": :446-451 (nuclear displacement)."""
+    o, v = slice(0, O), slice(O, O + V)
+    if kind == "H":
+        dt2 = dW.swapaxes(0, 2).swapaxes(1, 3)[o, o, v, v].copy()
+        dt2 = dt2 + np.einsum("ac,ijcb->ijab", dF[v, v], t2)
+        dt2 = dt2 + np.einsum("bc,ijac->ijab", dF[v, v], t2)
+        dt2 = dt2 - np.einsum("ki,kjab->ijab", dF[o, o], t2)
+        dt2 = dt2 - np.einsum("kj,ikab->ijab", dF[o, o], t2)
+    else:
+        dt2 = dW[o, o, v, v].copy()
+        dt2 = dt2 - np.einsum("kjab,ik->ijab", t2, dF[o, o])
+        dt2 = dt2 - np.einsum("ikab,kj->ijab", t2, dF[o, o])
+        dt2 = dt2 + np.einsum("ijcb,ac->ijab", t2, dF[v, v])
+        dt2 = dt2 + np.einsum("ijac,cb->ijab", t2, dF[v, v])
+    return dt2 / D_ijab
+
+
+def build_dERI(U, W_full, nf, kind, core=None):
+    """U: (nbf, nbf) CPHF coefficients; W_full: physicists' MO integrals over ALL nbf orbitals; t = [nf, nbf).
+    kind "H": analytic_aats.py:730-733; kind "R": :977-981 (+ the derivative-integral term `core`)."""
+    nbf = U.shape[0]
+    t = slice(nf, nbf)
+    sgn = -1.0 if kind == "H" else 1.0
+    d = np.einsum("tr,pqts->pqrs", U[:, t], W_full[t, t, :, t], optimize=True)
+    d = d + np.einsum("ts,pqrt->pqrs", U[:, t], W_full[t, t, t, :], optimize=True)
+    d = d + sgn * np.einsum("tp,tqrs->pqrs", U[:, t], W_full[:, t, t, t], optimize=True)
+    d = d + sgn * np.einsum("tq,ptrs->pqrs", U[:, t], W_full[t, :, t, t], optimize=True)
+    return d if core is None else core + d

@@ -283,3 +283,31 @@ def test_concurrent_identical_batches_equal_sequential():
             assert abs(r[0] - Eo) < E_TOL and np.abs(r[2] - t2o).max() < T_TOL
     finally:
         cfg.SOLVE_CONCURRENT, cfg.RETURN_DEVICE = old
+
+
+@pytest.mark.parametrize("kind", ["H", "R"])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_perturbed_mp2_amplitudes_and_dERI(kind, cplx):
+    """a21: closed-form perturbed MP2 amplitudes (analytic_aats.py:347-352, 446-451) and the perturbed-integral builds
+    (:730-733, 977-981) vs the oracle's transcription of those lines"""
+    import apyib_b200
+    from apyib_b200.utils import build_dERI
+    nbf, no, nf = 9, 3, 1
+    w = orc.rotated_wfn(nbf, no, 930 + (kind == "R"), cplx, nf)
+    p = par("MP2", fc=True)
+    mp = apyib_b200.mp2_wfn(p, w)
+    E, t2 = mp.solve_MP2()
+    rng = np.random.default_rng(931)
+    n = nbf - nf
+    O, V = no - nf, nbf - no
+    rnd = lambda *s: rng.standard_normal(s) + (1j * rng.standard_normal(s) if cplx else 0)
+    dF, dW = 0.1 * rnd(n, n), 0.05 * rnd(n, n, n, n)
+    got = mp.perturbed_t2(t2, dF, dW, kind)
+    want = orc.perturbed_MP2_t2(t2, dF, dW, mp.D_ijab, O, V, kind)
+    assert got.shape == want.shape == (O, O, V, V) and got.dtype == want.dtype
+    assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+    U, Wfull = 0.1 * rnd(nbf, nbf), 0.05 * rnd(nbf, nbf, nbf, nbf)
+    core = 0.05 * rnd(n, n, n, n) if kind == "R" else None
+    gd = build_dERI(U, Wfull, nf, kind, core)
+    wd = orc.build_dERI(U, Wfull, nf, kind, core)
+    assert gd.shape == (n, n, n, n) and np.abs(gd - wd).max() < 1e-12 * max(1.0, np.abs(wd).max())
