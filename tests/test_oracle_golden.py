@@ -213,3 +213,26 @@ def test_streamed_aat_oracle_equals_dense_oracle(method, nbf, no, nf):
             s = sp.spatial_aat_terms_streamed(A, 1, 2, norm)
             for k in d:
                 assert abs(d[k] - s[k]) < 1e-14 * max(1.0, abs(d[k])), (k, d[k], s[k])
+
+
+def test_perturbed_mp2_oracle_conventions_agree():
+    """oracle.perturbed_MP2_t2: the magnetic-field (analytic_aats.py:347-352) and nuclear (:446-451) transcriptions differ
+    only in index conventions -- for a symmetric perturbed Fock matrix and the same <ab|ij> block they must coincide;
+    build_dERI: the two kinds differ by the sign of the bra terms."""
+    rng = np.random.default_rng(0)
+    O, V = 2, 3
+    n = O + V
+    t2 = rng.standard_normal((O, O, V, V))
+    dF = rng.standard_normal((n, n))
+    dF = dF + dF.T
+    dW = rng.standard_normal((n,) * 4)
+    D = rng.standard_normal((O, O, V, V)) + 5
+    a = orc.perturbed_MP2_t2(t2, dF, dW, D, O, V, "H")
+    dWr = np.zeros_like(dW)
+    dWr[:O, :O, O:, O:] = dW.swapaxes(0, 2).swapaxes(1, 3)[:O, :O, O:, O:]
+    b = orc.perturbed_MP2_t2(t2, dF, dWr, D, O, V, "R")
+    assert np.abs(a - b).max() < 1e-14
+    U, W = rng.standard_normal((6, 6)), rng.standard_normal((6,) * 4)
+    h, r = orc.build_dERI(U, W, 1, "H"), orc.build_dERI(U, W, 1, "R")
+    ket = np.einsum("tr,pqts->pqrs", U[:, 1:], W[1:, 1:, :, 1:]) + np.einsum("ts,pqrt->pqrs", U[:, 1:], W[1:, 1:, 1:, :])
+    assert h.shape == (5, 5, 5, 5) and np.abs((h + r) / 2 - ket).max() < 1e-13
