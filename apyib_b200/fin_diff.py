@@ -88,6 +88,7 @@ class finite_difference(object):
         res = {("R", +1): ([None] * n3, [None] * n3, [None] * n3), ("R", -1): ([None] * n3, [None] * n3, [None] * n3),
                ("B", +1): ([None] * 3, [None] * 3, [None] * 3), ("B", -1): ([None] * 3, [None] * 3, [None] * 3)}
         pts = list(aat_points(self.natom) if points is None else points)
+        self._point_energies = {}
         extra = None
         chunk_p, chunk_w, nbytes = [], [], 0
 
@@ -101,6 +102,7 @@ class finite_difference(object):
                 for pt, wfn, (E, T_list) in zip(chunk_p, chunk_w, solved):
                     Cs, Bs, Ts = res[(pt[0], pt[2])]
                     Cs[pt[1]], Bs[pt[1]], Ts[pt[1]] = wfn.C, wfn.H.basis_set, T_list
+                    self._point_energies[pt] = wfn.E_SCF + E + wfn.H.E_nuc       # total energy (gradient drivers)
                     release_ao(wfn)
                     try:
                         wfn.H.ERI = None                       # nbf^4 words of host memory per point
@@ -203,17 +205,17 @@ class finite_difference(object):
         """Central-difference energy gradient over the R (n = 3N) or B (n = 3) points of compute_AAT,
         phase-corrected like them; returns (E+ - E-)/2h and the per-point C / basis / T lists."""
         pts = [(kind, i, +1) for i in range(n)] + [(kind, i, -1) for i in range(n)]
-        wfns = [self.scf_aat_point(pt, h_R, h_B) for pt in pts]
-        solved = correlated_many(self.parameters, wfns)
-        E = [w.E_SCF + e + w.H.E_nuc for w, (e, _) in zip(wfns, solved)]
+        # the same chunked point loop as compute_AAT (host SCFs, batched device solves, AO integrals released per
+        # chunk); it also records the total energy of every point
+        lists = self.compute_AAT(h_R, h_B, points=pts)
+        E = [self._point_energies[pt] for pt in pts]
         h = h_R if kind == "R" else h_B
         grad = np.zeros(n)
         for i in range(n):
             grad[i] = np.real(E[i] - E[n + i]) / (2 * h)     # the reference stores into a float array
-        C = [w.C for w in wfns]
-        B = [w.H.basis_set for w in wfns]
-        T = [t for _, t in solved]
-        return grad, C[:n], C[n:], B[:n], B[n:], T[:n], T[n:]
+        k0 = 0 if kind == "R" else 6
+        posC, negC, posB, negB, posT, negT = lists[k0:k0 + 6]
+        return grad, posC, negC, posB, negB, posT, negT
 
     def compute_Nuclear_Gradient(self, nuc_pert_strength):
         """fin_diff.py:376-447: returns (gradient (N,3), nuc_pos_C, nuc_neg_C, nuc_pos_basis, nuc_neg_basis,
