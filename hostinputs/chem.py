@@ -285,7 +285,13 @@ class Psi4Provider:
         return True
 
     def _psi_mol(self, molecule):
-        return self.psi4.geometry(molecule.create_psi4_string_from_molecule())
+        """psi4 molecule in the INPUT frame: E_nuc(F_el), the displacements and the dipole / angular-momentum integrals
+        must refer to the same axes, so recentring / reorientation is switched off unless the geometry string says
+        otherwise already."""
+        text = molecule.create_psi4_string_from_molecule()
+        low = text.lower()
+        extra = [d for d in ("no_com", "no_reorient") if d not in low]
+        return self.psi4.geometry(text + "".join(d + "\n" for d in extra))
 
     def basis(self, molecule):
         psi4 = self.psi4
